@@ -1,0 +1,465 @@
+#!/usr/bin/env python
+"""bench.py — hash-join probe rows/sec (BASELINE.json metric) on 1..N B200s.
+
+  python bench.py --gpus 1 --steps K --warmup W                       (N = 1)
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (N > 1)
+  python bench.py --impl reference ...      the reference algorithm's CPU restatement on the host cores
+
+N = 1 workload = BASELINE.json configs[1]: hash join 100M ⋈ 10M int64 keys, 8-byte payload, 100 % match,
+output (probe.k, probe.v, build.k, build.v).  A step = one pass of the probe over the whole 100M-row
+probe side against the already built table:
+  value : columns resident in HBM, kernel-only (tg_join_probe_dev), CUDA events on the launch stream
+  e2e   : the same probe through the host-facing C-ABI (tg_join_probe_push / tg_join_next) with pinned HOST
+          buffers, host→device and device→host copies inside the timed region
+N > 1 (weak scaling, per-GPU work fixed): every rank owns 10M build + 100M probe rows whose keys are uniform
+over the GLOBAL key set, so a key-hash repartition is mandatory: build side repartitioned once (untimed,
+like the build itself), every timed step = partition kernel + exchange of the probe columns over NVLink +
+shard-local probe.
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+ODD = 0x9E3779B97F4A7C15 - (1 << 64)   # odd 64-bit multiplier (as int64): a bijection, keys are unique but not dense
+BYTES_PER_PROBE_ROW = 64                # 16 read + 16 gathered + 32 written at 100 % match
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_plan(device: int, stream: int):
+    from tidb_b200 import abi
+    from tidb_b200.plan import FieldType, JoinPlan
+    INT = FieldType(abi.TYPE_LONGLONG, abi.FLAG_NOT_NULL)
+    # probe = left child, build = right child (RightAsBuildSide), all columns used (benchmark_test.go:722-729)
+    return JoinPlan(abi.JOIN_INNER, [INT, INT], [INT, INT], [0], [0], build_is_right=True, device=device, stream=stream)
+
+
+def gen_local(torch, dev, rank, world, n_build, n_probe):
+    """Synthetic fixed-width columns, generated on the device (seeds 42/43 per BASELINE.md)."""
+    g = torch.Generator(device=dev); g.manual_seed(42 + 1000 * rank)
+    ids = torch.randperm(n_build, device=dev, generator=g, dtype=torch.int64) + rank * n_build
+    bk = ids * ODD                                   # wraps mod 2^64: unique, scattered keys
+    bv = ids * 7
+    g.manual_seed(43 + 1000 * rank)
+    pid = torch.randint(0, n_build * world, (n_probe,), device=dev, generator=g, dtype=torch.int64)
+    pk = pid * ODD
+    pv = torch.arange(n_probe, device=dev, dtype=torch.int64) + rank * n_probe
+    return bk, bv, pk, pv
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU legs (oracle): the only place bench.py touches oracle/
+# ---------------------------------------------------------------------------------------------------------
+def cpu_probe_rate(bk, bv, pk, pv, sample_rows, threads, steps, warmup):
+    """Probe rows/s of the reference algorithm's restatement (oracle/join.cpp) on `threads` host threads:
+    full build, probe of the first `sample_rows` probe rows fed as 1024-row chunks."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    from tidb_b200.chunk import Chunk, Column, chunk_array
+    plan = make_plan(0, 0)
+    j = O.OracleJoin(plan, threads)
+    build_chunks = Chunk([Column(bk), Column(bv)]).split(1024)
+    j.build(build_chunks)
+    pchunks = Chunk([Column(pk[:sample_rows]), Column(pv[:sample_rows])]).split(1024)
+    parr = chunk_array(pchunks)
+    times = []
+    rows = 0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        rows = j.probe(parr, len(pchunks))
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    bsec = j.stat("build_seconds")
+    j.close()
+    return sample_rows / (sum(times) / len(times)), (sum(times) / len(times)) * 1e3, rows, bsec
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nb, sample = args.build_rows, min(args.probe_rows, args.ref_sample_rows)
+    rng = np.random.default_rng(42)
+    ids = rng.permutation(nb).astype(np.int64)
+    bk = ids * np.int64(ODD); bv = ids * 7
+    rng = np.random.default_rng(43)
+    pk = rng.integers(0, nb, sample).astype(np.int64) * np.int64(ODD)
+    pv = np.arange(sample, dtype=np.int64)
+    threads = os.cpu_count() or 1
+    rate, ms, rows, bsec = cpu_probe_rate(bk, bv, pk, pv, sample, threads, args.steps, args.warmup)
+    assert rows == sample
+    line = {
+        "impl": "reference", "metric": "hash-join probe rows/sec", "value": rate, "unit": "rows/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": f"hash join {args.probe_rows}x{nb} int64 keys, 8-byte payload, 100% match (BASELINE configs[1])",
+                   "note": "CPU restatement of TiDB's HashJoinV2 algorithm (oracle/join.cpp), NOT the Go binary: no Go toolchain in this image"},
+        "cpu_baseline": {"value": rate, "unit": "rows/s", "cores": threads, "kind": "port",
+                         "sample": f"full {nb}-row build ({bsec:.2f}s, untimed) + probe of {sample} rows as 1024-row chunks per step"},
+        "e2e": {"value": rate, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from tidb_b200 import abi
+    from tidb_b200.device import DeviceJoin, dev_chunk, fetch_device
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = abi.load_lib()
+    assert lib.tg_device_count() > 0
+    stream = torch.cuda.Stream(device=dev)
+    nb, npb = args.build_rows, args.probe_rows
+    hbm_peak, peak_src = peaks()
+
+    with torch.cuda.stream(stream):
+        bk, bv, pk, pv = gen_local(torch, dev, rank, world, nb, npb)
+    stream.synchronize()
+    plan = make_plan(local, stream.cuda_stream)
+    launches_extra = 0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- build side (untimed): repartition by key hash when N > 1, then build the local table ---------
+    def exchange(key, cols):
+        """key-hash repartition of `cols` (list of int64 tensors, key first) to their owner ranks"""
+        nonlocal launches_extra
+        n = key.numel()
+        dst = [torch.empty_like(c) for c in cols]
+        offs = torch.zeros(world + 1, dtype=torch.int64, device=dev)
+        src_p = (C.c_void_p * len(cols))(*[c.data_ptr() for c in cols])
+        dst_p = (C.c_void_p * len(cols))(*[c.data_ptr() for c in dst])
+        abi.check(lib.tg_partition_by_key(local, C.c_void_p(key.data_ptr()), None, C.c_int64(n), world, len(cols), src_p, dst_p,
+                                          C.c_void_p(offs.data_ptr()), C.c_void_p(stream.cuda_stream)))
+        launches_extra += 3
+        send = torch.diff(offs)
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send)
+        send_l, recv_l = send.tolist(), recv.tolist()
+        out = []
+        for c in dst:
+            r = torch.empty(sum(recv_l), dtype=c.dtype, device=dev)
+            dist.all_to_all_single(r, c, recv_l, send_l)
+            out.append(r)
+        return out
+
+    join = DeviceJoin(plan)
+    with torch.cuda.stream(stream):
+        if world > 1:
+            lbk, lbv = exchange(bk, [bk, bv])
+        else:
+            lbk, lbv = bk, bv
+        join.build([lbk, lbv])
+    bstats = join.stats()
+
+    # ---- one step ------------------------------------------------------------------------------------------
+    def step(sync: bool):
+        if world > 1:
+            lpk, lpv = exchange(pk, [pk, pv])
+        else:
+            lpk, lpv = pk, pv
+        rows, cols, _ = join.probe([lpk, lpv], sync=sync)
+        return rows, cols, lpk.numel()
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step(False)
+        # correctness of the timed configuration: bit-exact output row count and a checksum of checksums
+        rows, cols, nlocal = step(True)
+        total_rows = torch.tensor([rows], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(total_rows)
+        assert int(total_rows.item()) == npb * world, f"output rows {int(total_rows.item())} != {npb * world}"
+
+    # verify the join semantics on the device result with size-independent properties
+    with torch.cuda.stream(stream):
+        n_out = rows
+        def col_tensor(p):
+            class _A:   # __cuda_array_interface__ wrapper for a raw device pointer
+                pass
+            a = _A()
+            a.__cuda_array_interface__ = {"shape": (n_out,), "typestr": "<i8", "data": (p, False), "version": 3}
+            return torch.as_tensor(a, device=dev)
+        o_pk, o_pv, o_bk, o_bv = [col_tensor(p) for p in cols]
+        assert bool((o_pk == o_bk).all()), "joined rows must carry equal keys"
+        # build payload is 7 * id and key = id * ODD  ⇒  bv * ODD == bk * 7
+        assert bool((o_bv * ODD == o_bk * 7).all()), "build payload does not belong to the matched key"
+        chk = torch.stack([o_pv.sum(), (o_pv * o_pv).sum()])
+        if world > 1:
+            dist.all_reduce(chk)
+        pvs = torch.stack([pv.sum(), (pv * pv).sum()])
+        if world > 1:
+            dist.all_reduce(pvs)
+        assert torch.equal(chk, pvs), "every probe row must appear exactly once in the output (100% match, unique build keys)"
+    stream.synchronize()
+
+    # ---- timed region: value (device resident) ----------------------------------------------------------------
+    sampler = ClockSampler(local)
+    l0 = join.stats().kernel_launches
+    lx0 = launches_extra
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step(False)
+        ev1.record(stream)
+    stream.synchronize()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    launches = (join.stats().kernel_launches - l0) + (launches_extra - lx0)
+    value = npb * world / (ms_step * 1e-3)
+
+    # kernel-only duration for the roofline at N = 1 (the step IS the probe kernel + an 8-byte memset)
+    roof = None
+    if world == 1:
+        achieved = BYTES_PER_PROBE_ROW * npb / (ms_step * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": args.ncu_traffic_bytes, "peak_source": peak_src,
+                "kernel": "k_probe_inner_u1<4>", "algorithmic_bytes_per_launch": BYTES_PER_PROBE_ROW * npb,
+                "read_only_frac": 32 * npb / (ms_step * 1e-3) / 1e9 / hbm_peak}
+
+    # ---- e2e: host buffers through tg_join_probe_push / tg_join_next (N = 1 path; per rank at N > 1) ---------
+    e2e = None
+    if not args.skip_e2e:
+        e2e = run_e2e(args, lib, abi, torch, dev, local, rank, world, bk, bv, pk, pv, barrier)
+
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample on the box's host cores ------------------------------
+    cpu = None
+    if world == 1 and not args.skip_cpu:
+        sample = min(npb, args.cpu_sample_rows)
+        threads = os.cpu_count() or 1
+        rate, ms, rows_c, bsec = cpu_probe_rate(bk.cpu().numpy(), bv.cpu().numpy(), pk[:sample].cpu().numpy(), pv[:sample].cpu().numpy(),
+                                                sample, threads, 2, 1)
+        assert rows_c == sample
+        cpu = {"value": rate, "unit": "rows/s", "cores": threads, "kind": "port",
+               "sample": f"full {nb}-row build ({bsec:.2f}s, untimed) + probe of the first {sample} probe rows as 1024-row chunks, mean of 2 after 1 warm-up; "
+                         "oracle/join.cpp restates TiDB's HashJoinV2 (not the Go binary)"}
+
+    if rank == 0:
+        line = {
+            "metric": "hash-join probe rows/sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64", "data": "synthetic",
+            "config": {"workload": f"hash join {npb}x{nb} int64 keys per GPU, 8-byte payload, 100% match, output 4 columns (BASELINE configs[1])",
+                       "l2": "inputs larger than L2 (1.6 GB probe columns + 3.2 GB output + %.0f MB table per step vs 126 MB L2)" % (bstats.table_slots * 16 / 1e6),
+                       "table": {"slots": bstats.table_slots, "mode": bstats.table_mode, "distinct_keys": bstats.distinct_keys, "build_ms": bstats.build_ms},
+                       "exchange": "none" if world == 1 else "tg_partition_by_key + NCCL all_to_all_single per column"},
+            "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
+        }
+        if roof:
+            line["roofline"] = roof
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    join.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, lib, abi, torch, dev, local, rank, world, bk, bv, pk, pv, barrier):
+    """The probe through the host-facing C-ABI: pinned host columns in, pinned host columns out."""
+    from tidb_b200.plan import JoinPlan
+    nb, npb = bk.numel(), pk.numel()
+    chunk_rows = args.e2e_chunk_rows
+
+    def pinned(nbytes):
+        p = C.c_void_p()
+        abi.check(lib.tg_host_alloc(C.c_size_t(nbytes), C.byref(p)))
+        return p
+
+    def np_view(p, n):
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int64)), shape=(n,))
+
+    # the rank's own shard as host columns (what a TableReader would hand to the executor)
+    hp = [pinned(npb * 8) for _ in range(2)]
+    hb = [pinned(nb * 8) for _ in range(2)]
+    for p, t in zip(hp, (pk, pv)):
+        np_view(p, npb)[:] = t.cpu().numpy()
+    for p, t in zip(hb, (bk, bv)):
+        np_view(p, nb)[:] = t.cpu().numpy()
+    out = [pinned(chunk_rows * 8) for _ in range(4)]
+    plan = make_plan(local, 0)
+    desc, keep = plan.to_struct()
+    h = C.c_void_p()
+    abi.check(lib.tg_join_open(C.byref(desc), C.byref(h)))
+
+    def host_chunk(ptrs, lo, n):
+        arr = (abi.TgColumn * 2)()
+        for i, p in enumerate(ptrs):
+            arr[i].length = n; arr[i].data = p.value + lo * 8; arr[i].elem_len = 8
+        ck = abi.TgChunk(); ck.ncols = 2; ck.cols = C.cast(arr, C.POINTER(abi.TgColumn)); ck._keep = arr
+        return ck
+
+    for lo in range(0, nb, chunk_rows):
+        ck = host_chunk(hb, lo, min(chunk_rows, nb - lo))
+        abi.check(lib.tg_join_build_push(h, C.byref(ck)))
+    abi.check(lib.tg_join_build_finish(h))
+    mc = (abi.TgMutColumn * 4)()
+    for i in range(4):
+        mc[i].data = out[i].value; mc[i].null_bitmap = None; mc[i].elem_len = 8
+    mch = abi.TgMutChunk(); mch.ncols = 4; mch.cols = C.cast(mc, C.POINTER(abi.TgMutColumn)); mch.capacity_rows = chunk_rows
+
+    def one_pass():
+        """a fresh probe of the whole probe side: push every chunk, drain Next between pushes"""
+        got = 0
+        n = C.c_int64(0)
+        for lo in range(0, npb, chunk_rows):
+            ck = host_chunk(hp, lo, min(chunk_rows, npb - lo))
+            abi.check(lib.tg_join_probe_push(h, C.byref(ck)))
+            while True:
+                abi.check(lib.tg_join_next(h, C.byref(mch), C.c_int64(chunk_rows), C.byref(n)))
+                if n.value == 0:
+                    break
+                got += n.value
+        return got
+
+    for _ in range(max(1, args.warmup // 2)):
+        assert one_pass() == npb
+    barrier()
+    t0 = time.perf_counter()
+    steps = max(1, args.steps // 2)
+    for _ in range(steps):
+        got = one_pass()
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    assert got == npb
+    st = abi.TgJoinStats()
+    abi.check(lib.tg_join_get_stats(h, C.byref(st)))
+    lib.tg_join_close(h)
+    for p in hp + hb + out:
+        lib.tg_host_free(p)
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    sec_step = float(tt.item()) / steps
+    return {"value": npb * world / sec_step, "unit": "rows/s", "h2d_bytes_per_step": 16 * npb, "d2h_bytes_per_step": 32 * npb,
+            "ms_per_step": sec_step * 1e3, "steps": steps, "chunk_rows": chunk_rows,
+            "path": "tg_join_probe_push(host pinned chunk) -> kernels -> tg_join_next(host pinned buffers); per rank its own shard, no exchange"
+                    if world > 1 else "tg_join_probe_push(host pinned chunk) -> kernels -> tg_join_next(host pinned buffers)",
+            "timing": "host wall clock around the passes, device synchronised on both sides (host work is part of the path)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--build-rows", type=int, default=10_000_000)
+    ap.add_argument("--probe-rows", type=int, default=100_000_000)
+    ap.add_argument("--cpu-sample-rows", type=int, default=8_000_000)
+    ap.add_argument("--ref-sample-rows", type=int, default=8_000_000)
+    ap.add_argument("--e2e-chunk-rows", type=int, default=4 << 20)
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--ncu-traffic-bytes", type=float, default=None, help="dram bytes per launch from the committed ncu capture")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

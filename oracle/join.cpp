@@ -826,7 +826,7 @@ struct ProbeWorker {
   }
 };
 
-static bool run_join(Join& j, const tg_chunk* build, int64_t nb, const tg_chunk* probe, int64_t np) {
+static bool run_build(Join& j, const tg_chunk* build, int64_t nb) {
   using clk = std::chrono::steady_clock;
   uint32_t C = j.concurrency;
   j.rowTables.clear();
@@ -849,8 +849,16 @@ static bool run_join(Join& j, const tg_chunk* build, int64_t nb, const tg_chunk*
     if (!ok.load()) return false;
   }
   build_hash_table(j);
+  j.buildSeconds = std::chrono::duration<double>(clk::now() - t0).count();
+  return true;
+}
+
+// probe phase; may be repeated against the same built table (results are reset each time).  For joins
+// that scan the row table afterwards the used flags accumulate, so repeat only inner / probe-outer joins.
+static bool run_probe(Join& j, const tg_chunk* probe, int64_t np) {
+  using clk = std::chrono::steady_clock;
+  uint32_t C = j.concurrency;
   auto t1 = clk::now();
-  j.buildSeconds = std::chrono::duration<double>(t1 - t0).count();
   // probe: C workers (hash_join_v2.go:970 runJoinWorker)
   j.results.clear();
   j.results.resize(C);
@@ -883,6 +891,10 @@ static bool run_join(Join& j, const tg_chunk* build, int64_t nb, const tg_chunk*
   }
   j.probeSeconds = std::chrono::duration<double>(clk::now() - t1).count();
   return true;
+}
+
+static bool run_join(Join& j, const tg_chunk* build, int64_t nb, const tg_chunk* probe, int64_t np) {
+  return run_build(j, build, nb) && run_probe(j, probe, np);
 }
 
 }  // namespace orc
@@ -961,6 +973,8 @@ int orc_join_open(const tg_join_desc* d, int32_t concurrency, orc_join** out) {
 int orc_join_run(orc_join* h, const tg_chunk* b, int64_t nb, const tg_chunk* p, int64_t np) {
   return run_join(h->j, b, nb, p, np) ? 0 : TG_ERR_UNSUPPORTED;
 }
+int orc_join_build(orc_join* h, const tg_chunk* b, int64_t nb) { return run_build(h->j, b, nb) ? 0 : TG_ERR_UNSUPPORTED; }
+int orc_join_probe(orc_join* h, const tg_chunk* p, int64_t np) { return run_probe(h->j, p, np) ? 0 : TG_ERR_UNSUPPORTED; }
 int64_t orc_join_result_rows(orc_join* h) {
   int64_t n = 0;
   for (auto& r : h->j.results) if (!r.empty()) n += r[0].length;

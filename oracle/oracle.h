@@ -79,6 +79,9 @@ int orc_join_open(const tg_join_desc* desc, int32_t concurrency, orc_join** out)
  * `concurrency` build and probe worker threads exactly like hash_join_v2.go:1266-1479 / :793-852 */
 int orc_join_run(orc_join* j, const tg_chunk* build_chunks, int64_t n_build_chunks,
                  const tg_chunk* probe_chunks, int64_t n_probe_chunks);
+/* the two phases separately: build once, probe repeatedly (bench.py's CPU baseline times the probe) */
+int orc_join_build(orc_join* j, const tg_chunk* build_chunks, int64_t n_build_chunks);
+int orc_join_probe(orc_join* j, const tg_chunk* probe_chunks, int64_t n_probe_chunks);
 int64_t orc_join_result_rows(orc_join* j);
 int32_t orc_join_result_cols(orc_join* j);
 /* copy the whole result (all worker outputs concatenated) into caller buffers */

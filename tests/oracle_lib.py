@@ -104,6 +104,19 @@ class OracleJoin:
             raise RuntimeError(f"oracle join fetch failed ({rc}): {_err()}")
         return n, out.columns(n)
 
+    def build(self, build: Sequence[Chunk]) -> None:
+        ba = chunk_array(build)
+        rc = lib().orc_join_build(self._h, ba, C.c_int64(len(build)))
+        if rc != 0:
+            raise RuntimeError(f"oracle join build failed ({rc}): {_err()}")
+
+    def probe(self, probe_arr, n_chunks: int) -> int:
+        """probe_arr: a prepared chunk_array (so that marshalling stays outside timed regions)"""
+        rc = lib().orc_join_probe(self._h, probe_arr, C.c_int64(n_chunks))
+        if rc != 0:
+            raise RuntimeError(f"oracle join probe failed ({rc}): {_err()}")
+        return lib().orc_join_result_rows(self._h)
+
     def stat(self, name: str):
         return getattr(lib(), "orc_join_" + name)(self._h)
 

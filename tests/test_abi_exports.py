@@ -1,0 +1,86 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol
+include/tidbgpu.h declares, validates descriptors without a GPU, and fails loudly (no CPU fallback)
+when no device is present."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from tidb_b200 import abi
+from tidb_b200.plan import AggFunc, AggPlan, FieldType, JoinPlan
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INT_NN = FieldType(abi.TYPE_LONGLONG, abi.FLAG_NOT_NULL)
+DBL = FieldType(abi.TYPE_DOUBLE, 0)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from tidb_b200 import build
+    build.build()
+    return abi.load_lib()
+
+
+def test_header_symbols_all_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "tidbgpu.h")).read()
+    declared = set(re.findall(r"\b(tg_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(abi.EXPORTED_SYMBOLS), declared ^ set(abi.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in tidbgpu.h but not exported"
+    assert lib.tg_abi_version() == 1
+
+
+def test_fixed_len_matches_reference(lib):
+    # pkg/util/chunk/codec.go:165-179 getFixedLen
+    for tp, n in ((abi.TYPE_FLOAT, 4), (abi.TYPE_TINY, 8), (abi.TYPE_LONGLONG, 8), (abi.TYPE_DOUBLE, 8), (abi.TYPE_YEAR, 8),
+                  (abi.TYPE_DURATION, 8), (abi.TYPE_DATETIME, 8), (abi.TYPE_NEWDECIMAL, 40), (abi.TYPE_VARSTRING, -1)):
+        assert lib.tg_fixed_len(tp) == n
+
+
+def test_join_supported_gate(lib):
+    ok = JoinPlan(abi.JOIN_INNER, [INT_NN, INT_NN], [INT_NN, INT_NN], [0], [0])
+    d, keep = ok.to_struct()
+    assert lib.tg_join_supported(C.byref(d)) == abi.TG_OK
+    multi = JoinPlan(abi.JOIN_INNER, [INT_NN, INT_NN], [INT_NN, INT_NN], [0, 1], [0, 1])
+    d, keep = multi.to_struct()
+    assert lib.tg_join_supported(C.byref(d)) == abi.TG_ERR_UNSUPPORTED
+    strkey = JoinPlan(abi.JOIN_INNER, [FieldType(abi.TYPE_VARSTRING)], [FieldType(abi.TYPE_VARSTRING)], [0], [0])
+    d, keep = strkey.to_struct()
+    assert lib.tg_join_supported(C.byref(d)) == abi.TG_ERR_UNSUPPORTED
+    # NewJoinProbe panics for semi joins with right-side output columns (base_join_probe.go:896)
+    semi = JoinPlan(abi.JOIN_SEMI, [INT_NN], [INT_NN], [0], [0], rused=[0])
+    d, keep = semi.to_struct()
+    assert lib.tg_join_supported(C.byref(d)) == abi.TG_ERR_INVALID
+
+
+def test_agg_supported_gate(lib):
+    ok = AggPlan([INT_NN, DBL], [0], [AggFunc(abi.AGG_FIRSTROW, 0), AggFunc(abi.AGG_SUM, 1, abi.TYPE_DOUBLE), AggFunc(abi.AGG_COUNT, 1, abi.TYPE_DOUBLE)])
+    d, keep = ok.to_struct()
+    assert lib.tg_agg_supported(C.byref(d)) == abi.TG_OK
+    # SUM(int) returns DECIMAL in TiDB (aggregation/base_func.go:223): declined
+    bad = AggPlan([INT_NN, INT_NN], [0], [AggFunc(abi.AGG_SUM, 1, abi.TYPE_LONGLONG)])
+    d, keep = bad.to_struct()
+    assert lib.tg_agg_supported(C.byref(d)) == abi.TG_ERR_UNSUPPORTED
+
+
+def test_no_cpu_fallback_without_device(lib):
+    if lib.tg_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    plan = JoinPlan(abi.JOIN_INNER, [INT_NN], [INT_NN], [0], [0])
+    d, keep = plan.to_struct()
+    h = C.c_void_p()
+    assert lib.tg_join_open(C.byref(d), C.byref(h)) == abi.TG_ERR_CUDA
+    assert b"no CPU fallback" in lib.tg_last_error()
+    p = C.c_void_p()
+    assert lib.tg_dev_alloc(0, C.c_size_t(16), C.byref(p)) == abi.TG_ERR_CUDA
+
+
+def test_partition_function_is_stable(lib):
+    # host mirror of the device partition function: spreads keys, deterministic
+    import collections
+    cnt = collections.Counter(lib.tg_partition_of_key(k * 2654435761, 8) for k in range(80000))
+    assert set(cnt) == set(range(8))
+    assert max(cnt.values()) < 1.1 * 10000 and min(cnt.values()) > 0.9 * 10000
+    assert lib.tg_partition_of_key(12345, 1) == 0

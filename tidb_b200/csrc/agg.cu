@@ -1,0 +1,793 @@
+// agg.cu — tg_agg_*: GPU hash aggregation behind HashAggExec's Open/Next/Close contract
+// (pkg/executor/aggregate/agg_hash_executor.go:93, :237, :441, :164).
+//
+// What the kernels replace:
+//   GetGroupKey + getPartialResultsOfEachRow + per-row af.UpdatePartialResult
+//     (agg_util.go:106, agg_hash_partial_worker.go:219, :256)         → k_agg_update / k_agg_update_nogroup
+//   HashAggFinalWorker merge + AppendFinalResult2Chunk (agg_hash_final_worker.go:73, :121;
+//     func_sum.go:80, func_avg.go:332, func_count.go:43)              → k_agg_finalize
+// There is no partial/final split on one GPU: every row updates the single device-resident group table
+// with atomics (the 1M-group table of config 3 is 32–48 MB and lives in the 126 MB L2).
+//
+// Layout: structure-of-arrays open-addressing table — keys[S+2] (int64, sentinel = empty), rows[S+2]
+// (group row count), and one or two 8-byte state arrays per aggregate.  Slot S holds the NULL group
+// (NULL group keys DO form a group: codec.go:1766), slot S+1 the group whose key equals the sentinel.
+#include <memory>
+#include <algorithm>
+#include "common.cuh"
+
+namespace tg {
+
+#define TG_MAX_AGG 12
+enum { GK_I64 = 0, GK_F64 = 1, GK_NONE = 2 };
+
+struct AggFuncDev {
+  int32_t name;         // TG_AGG_*
+  int32_t arg_col;      // -1: COUNT(*)
+  int32_t is_real;
+  int32_t is_unsigned;
+  int32_t s0, s1;       // state array indices (-1 = unused): s0 value (sum / min / max / count), s1 non-NULL count
+  int32_t final_mode;   // TG_AGGMODE_FINAL: inputs are partial results
+  int32_t arg_col2;
+};
+struct AggSpec { int32_t n; int32_t pad; AggFuncDev f[TG_MAX_AGG]; };
+struct AggTable {
+  long long* keys;
+  unsigned long long* rows;
+  unsigned long long* state[2 * TG_MAX_AGG];
+  unsigned long long nslots;
+};
+struct GroupKey { const void* data; const uint8_t* nulls; int32_t kind; int32_t pad; };
+
+// order-preserving map double → u64 so that MIN/MAX(double) can use integer atomics
+__device__ __forceinline__ unsigned long long f64_to_ordered(double d) {
+  unsigned long long u = (unsigned long long)__double_as_longlong(d);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double ordered_to_f64(unsigned long long u) {
+  u = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+  return __longlong_as_double((long long)u);
+}
+__device__ __forceinline__ unsigned long long i64_to_ordered(long long v) { return (unsigned long long)v ^ 0x8000000000000000ull; }
+
+__global__ void k_agg_init(AggTable t, AggSpec spec, unsigned long long n_total) {
+  unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (; i < n_total; i += stride) {
+    t.keys[i] = kEmptyKey;
+    t.rows[i] = 0;
+    for (int k = 0; k < spec.n; k++) {
+      const AggFuncDev& f = spec.f[k];
+      if (f.s0 >= 0) {
+        unsigned long long init = 0;
+        if (f.name == TG_AGG_MIN) init = ~0ull;          // ordered domain: larger than everything
+        t.state[f.s0][i] = init;
+      }
+      if (f.s1 >= 0) t.state[f.s1][i] = 0;
+    }
+  }
+}
+
+__device__ __forceinline__ void agg_apply(const AggTable& t, const AggSpec& spec, const DevCols& cols, int64_t row,
+                                          unsigned long long s) {
+  atomicAdd(&t.rows[s], 1ull);
+  for (int k = 0; k < spec.n; k++) {
+    const AggFuncDev& f = spec.f[k];
+    if (f.arg_col < 0 || f.s0 < 0) continue;   // COUNT(*) and NOT NULL COUNT(x) read rows[]; FIRSTROW reads the key
+    const uint8_t* nb = cols.nulls[f.arg_col];
+    if (nb && !bit_not_null(nb, row)) continue;
+    switch (f.name) {
+      case TG_AGG_COUNT:
+        if (f.final_mode) atomicAdd(&t.state[f.s0][s], reinterpret_cast<const unsigned long long*>(cols.data[f.arg_col])[row]);
+        else atomicAdd(&t.state[f.s0][s], 1ull);
+        break;
+      case TG_AGG_SUM:
+        atomicAdd(reinterpret_cast<double*>(&t.state[f.s0][s]), reinterpret_cast<const double*>(cols.data[f.arg_col])[row]);
+        if (f.s1 >= 0) atomicAdd(&t.state[f.s1][s], 1ull);
+        break;
+      case TG_AGG_AVG:
+        if (f.final_mode) {   // args: count column, sum column (func_avg.go:405)
+          const uint8_t* nb2 = cols.nulls[f.arg_col2];
+          if (nb2 && !bit_not_null(nb2, row)) break;
+          atomicAdd(reinterpret_cast<double*>(&t.state[f.s0][s]), reinterpret_cast<const double*>(cols.data[f.arg_col2])[row]);
+          atomicAdd(&t.state[f.s1][s], reinterpret_cast<const unsigned long long*>(cols.data[f.arg_col])[row]);
+        } else {
+          atomicAdd(reinterpret_cast<double*>(&t.state[f.s0][s]), reinterpret_cast<const double*>(cols.data[f.arg_col])[row]);
+          if (f.s1 >= 0) atomicAdd(&t.state[f.s1][s], 1ull);
+        }
+        break;
+      case TG_AGG_MIN: case TG_AGG_MAX: {
+        unsigned long long v;
+        if (f.is_real) v = f64_to_ordered(reinterpret_cast<const double*>(cols.data[f.arg_col])[row]);
+        else if (f.is_unsigned) v = reinterpret_cast<const unsigned long long*>(cols.data[f.arg_col])[row];
+        else v = i64_to_ordered(reinterpret_cast<const long long*>(cols.data[f.arg_col])[row]);
+        if (f.name == TG_AGG_MIN) atomicMin(&t.state[f.s0][s], v); else atomicMax(&t.state[f.s0][s], v);
+        if (f.s1 >= 0) atomicAdd(&t.state[f.s1][s], 1ull);
+        break;
+      }
+      default: break;
+    }
+  }
+}
+
+// One thread per row: find-or-insert the group slot, then atomics.  Rows whose NEW key would push the
+// table past max_fill are deferred (bit set in `deferred`) so the host can grow the table and re-run
+// them; `only` restricts a re-run to those rows.
+__global__ void __launch_bounds__(256)
+k_agg_update(GroupKey gk, DevCols cols, int64_t n, AggTable t, AggSpec spec, unsigned long long max_fill,
+             unsigned long long* fill, uint32_t* deferred, const uint32_t* only, unsigned long long* n_deferred) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    if (only && !((only[i >> 5] >> (i & 31)) & 1u)) continue;
+    unsigned long long s;
+    bool is_null = gk.nulls && !bit_not_null(gk.nulls, i);
+    if (is_null) s = t.nslots;
+    else {
+      long long k;
+      if (gk.kind == GK_I64) k = reinterpret_cast<const long long*>(gk.data)[i];
+      else {
+        double d = reinterpret_cast<const double*>(gk.data)[i];
+        if (d == 0) d = 0;   // -0 and +0 encode to the same group key (codec float.go:23)
+        k = __double_as_longlong(d);
+      }
+      if (k == kEmptyKey) s = t.nslots + 1;
+      else {
+        s = slot_of(mix64((uint64_t)k), t.nslots);
+        bool defer = false;
+        for (;;) {
+          long long cur = *reinterpret_cast<volatile long long*>(&t.keys[s]);
+          if (cur == k) break;
+          if (cur == kEmptyKey) {
+            unsigned long long f = atomicAdd(fill, 1ull);
+            if (f >= max_fill) { atomicAdd(fill, (unsigned long long)-1ll); defer = true; break; }
+            unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&t.keys[s]), (unsigned long long)kEmptyKey,
+                                               (unsigned long long)k);
+            if (old == (unsigned long long)kEmptyKey) break;
+            atomicAdd(fill, (unsigned long long)-1ll);
+            if (old == (unsigned long long)k) break;
+          }
+          if (++s == t.nslots) s = 0;
+        }
+        if (defer) {
+          atomicOr(&deferred[i >> 5], 1u << (i & 31));
+          atomicAdd(n_deferred, 1ull);
+          continue;
+        }
+      }
+    }
+    agg_apply(t, spec, cols, i, s);
+  }
+}
+
+// no GROUP BY: one group.  Warp-shuffle partial reduction, then one atomic per warp and aggregate.
+__global__ void __launch_bounds__(256)
+k_agg_update_nogroup(DevCols cols, int64_t n, AggTable t, AggSpec spec) {
+  int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  unsigned long long my_rows = 0;
+  for (int64_t i = i0; i < n; i += stride) my_rows++;
+  for (int o = 16; o; o >>= 1) my_rows += __shfl_xor_sync(0xffffffffu, my_rows, o);
+  if (lane == 0 && my_rows) atomicAdd(&t.rows[t.nslots], my_rows);
+  for (int k = 0; k < spec.n; k++) {
+    const AggFuncDev& f = spec.f[k];
+    if (f.arg_col < 0 || f.s0 < 0) continue;
+    const uint8_t* nb = cols.nulls[f.arg_col];
+    double fs = 0; unsigned long long cnt = 0, ext = f.name == TG_AGG_MIN ? ~0ull : 0ull, isum = 0;
+    for (int64_t i = i0; i < n; i += stride) {
+      if (nb && !bit_not_null(nb, i)) continue;
+      if (f.name == TG_AGG_AVG && f.final_mode) {
+        const uint8_t* nb2 = cols.nulls[f.arg_col2];
+        if (nb2 && !bit_not_null(nb2, i)) continue;
+        fs += reinterpret_cast<const double*>(cols.data[f.arg_col2])[i];
+        cnt += reinterpret_cast<const unsigned long long*>(cols.data[f.arg_col])[i];
+        continue;
+      }
+      cnt++;
+      if (f.name == TG_AGG_SUM || f.name == TG_AGG_AVG) fs += reinterpret_cast<const double*>(cols.data[f.arg_col])[i];
+      else if (f.name == TG_AGG_COUNT) { if (f.final_mode) isum += reinterpret_cast<const unsigned long long*>(cols.data[f.arg_col])[i]; else isum++; }
+      else {
+        unsigned long long v;
+        if (f.is_real) v = f64_to_ordered(reinterpret_cast<const double*>(cols.data[f.arg_col])[i]);
+        else if (f.is_unsigned) v = reinterpret_cast<const unsigned long long*>(cols.data[f.arg_col])[i];
+        else v = i64_to_ordered(reinterpret_cast<const long long*>(cols.data[f.arg_col])[i]);
+        ext = f.name == TG_AGG_MIN ? (v < ext ? v : ext) : (v > ext ? v : ext);
+      }
+    }
+    for (int o = 16; o; o >>= 1) {
+      fs += __shfl_xor_sync(0xffffffffu, fs, o);
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      isum += __shfl_xor_sync(0xffffffffu, isum, o);
+      unsigned long long e2 = __shfl_xor_sync(0xffffffffu, ext, o);
+      ext = f.name == TG_AGG_MIN ? (e2 < ext ? e2 : ext) : (e2 > ext ? e2 : ext);
+    }
+    if (lane == 0 && cnt) {
+      unsigned long long s = t.nslots;
+      if (f.name == TG_AGG_SUM || f.name == TG_AGG_AVG) atomicAdd(reinterpret_cast<double*>(&t.state[f.s0][s]), fs);
+      else if (f.name == TG_AGG_COUNT) atomicAdd(&t.state[f.s0][s], isum);
+      else if (f.name == TG_AGG_MIN) atomicMin(&t.state[f.s0][s], ext);
+      else atomicMax(&t.state[f.s0][s], ext);
+      if (f.s1 >= 0 && !(f.name == TG_AGG_COUNT)) atomicAdd(&t.state[f.s1][s], cnt);
+    }
+  }
+}
+
+// re-insert every group of an old table into a bigger one (no atomics on the states: keys are unique)
+__global__ void k_agg_rehash(AggTable oldt, AggTable newt, AggSpec spec, int nstates, unsigned long long* fill) {
+  unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (; i < oldt.nslots + 2; i += stride) {
+    unsigned long long s;
+    if (i >= oldt.nslots) { if (oldt.rows[i] == 0) continue; s = newt.nslots + (i - oldt.nslots); }
+    else {
+      long long k = oldt.keys[i];
+      if (k == kEmptyKey) continue;
+      s = slot_of(mix64((uint64_t)k), newt.nslots);
+      for (;;) {
+        unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&newt.keys[s]), (unsigned long long)kEmptyKey, (unsigned long long)k);
+        if (old == (unsigned long long)kEmptyKey) break;
+        if (++s == newt.nslots) s = 0;
+      }
+      atomicAdd(fill, 1ull);
+    }
+    newt.rows[s] = oldt.rows[i];
+    for (int a = 0; a < nstates; a++) newt.state[a][s] = oldt.state[a][i];
+  }
+}
+
+struct AggOut { void* data[TG_MAX_AGG]; uint8_t* valid[TG_MAX_AGG]; };
+
+// compact the occupied slots into the result columns (Go-map iteration order is unspecified in the
+// reference too; here it is slot order within warps, warp order by the atomic cursor)
+__global__ void __launch_bounds__(256)
+k_agg_finalize(AggTable t, AggSpec spec, int gk_kind, AggOut out, unsigned long long* cursor) {
+  unsigned long long n_total = t.nslots + 2;
+  unsigned long long base = blockIdx.x * (unsigned long long)blockDim.x;
+  unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  for (; base < n_total; base += stride) {
+    unsigned long long i = base + threadIdx.x;
+    bool occ = false;
+    if (i < t.nslots) occ = t.keys[i] != kEmptyKey;
+    else if (i < n_total) occ = t.rows[i] != 0;
+    unsigned b = __ballot_sync(0xffffffffu, occ);
+    unsigned long long wbase = 0;
+    if (lane == 0 && b) wbase = atomicAdd(cursor, (unsigned long long)__popc(b));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (!occ) continue;
+    unsigned long long o = wbase + __popc(b & ((1u << lane) - 1));
+    unsigned long long rows = t.rows[i];
+    for (int k = 0; k < spec.n; k++) {
+      const AggFuncDev& f = spec.f[k];
+      unsigned long long nn = f.s1 >= 0 ? t.state[f.s1][i] : rows;   // non-NULL inputs seen
+      bool valid = true;
+      unsigned long long v = 0;
+      switch (f.name) {
+        case TG_AGG_COUNT: v = (f.arg_col < 0 || f.s0 < 0) ? rows : t.state[f.s0][i]; break;
+        case TG_AGG_SUM: valid = nn != 0; v = t.state[f.s0][i]; break;   // NULL when no non-NULL input (func_sum.go:80)
+        case TG_AGG_AVG:
+          valid = nn != 0;
+          if (valid) v = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)t.state[f.s0][i]) / (double)nn);   // func_avg.go:332
+          break;
+        case TG_AGG_MIN: case TG_AGG_MAX: {
+          valid = nn != 0;
+          unsigned long long u = t.state[f.s0][i];
+          if (f.is_real) v = (unsigned long long)__double_as_longlong(ordered_to_f64(u));
+          else if (f.is_unsigned) v = u;
+          else v = u ^ 0x8000000000000000ull;
+          break;
+        }
+        default:   // FIRSTROW(group column): the group key itself (firstRow4Int func_first_row.go:140)
+          if (i == t.nslots) valid = false;                       // NULL group
+          else if (i == t.nslots + 1) v = (unsigned long long)kEmptyKey;
+          else v = (unsigned long long)t.keys[i];
+          (void)gk_kind;
+          break;
+      }
+      reinterpret_cast<unsigned long long*>(out.data[k])[o] = valid ? v : 0ull;
+      if (out.valid[k]) out.valid[k][o] = valid ? 1 : 0;
+    }
+  }
+}
+
+__global__ void k_pack_bitmap_agg(const uint8_t* __restrict__ valid, int64_t n, uint8_t* __restrict__ bitmap) {
+  int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t nbytes = (n + 7) / 8;
+  for (; b < nbytes; b += stride) {
+    uint8_t v = 0;
+    for (int j = 0; j < 8; j++) { int64_t r = b * 8 + j; if (r < n && valid[r]) v |= (uint8_t)(1u << j); }
+    bitmap[b] = v;
+  }
+}
+
+struct AggHostStage {
+  std::vector<std::unique_ptr<PinBuf>> data, nulls;
+  std::vector<char> has_nulls;
+  int64_t rows = 0;
+};
+
+}  // namespace tg
+
+using namespace tg;
+
+struct tg_agg {
+  std::mutex mu;
+  std::atomic<bool> closed{false};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int nsm = 148;
+
+  int ncols = 0;
+  std::vector<int> types, elem;
+  std::vector<uint32_t> flags;
+  std::vector<char> needed;
+  int group_col = -1;          // -1: no GROUP BY
+  int gk_kind = GK_NONE;
+  AggSpec spec{};
+  int nstates = 0;
+  std::vector<char> out_nullable;
+
+  // table
+  DevBuf tbl_mem;
+  AggTable tbl{};
+  unsigned long long nslots = 0;
+  DevBuf scalars;              // [0] fill [1] n_deferred [2] out cursor
+  DevBuf deferred;
+  int64_t expected_groups = 0;
+
+  // staging
+  AggHostStage stage;
+  std::vector<std::unique_ptr<DevBuf>> dcols, dnulls;
+
+  // result
+  bool finished = false;
+  std::vector<std::unique_ptr<DevBuf>> out_cols, out_valid, out_bitmaps;
+  int64_t out_rows = 0, consumed = 0;
+  tg_agg_stats stats{};
+};
+
+namespace tg {
+
+static int agrid(const tg_agg* a, int64_t n, int block = 256, int per_sm = 8) {
+  int64_t need = (n + block - 1) / block, cap = (int64_t)a->nsm * per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+static int agg_setup(tg_agg* a, const tg_agg_desc* d) {
+  if (!d) return fail(TG_ERR_INVALID, "desc is NULL");
+  if (d->n_cols <= 0 || d->n_cols > TG_MAX_COLS) return fail(TG_ERR_UNSUPPORTED, "child schema must have 1..16 columns");
+  a->ncols = d->n_cols;
+  a->types.assign(d->col_types, d->col_types + d->n_cols);
+  a->flags.resize(d->n_cols);
+  for (int i = 0; i < d->n_cols; i++) a->flags[i] = d->col_flags ? d->col_flags[i] : 0;
+  a->elem.resize(d->n_cols);
+  for (int i = 0; i < d->n_cols; i++) a->elem[i] = fixed_len(a->types[i]);
+  a->needed.assign(d->n_cols, 0);
+  if (d->n_group_by > 1) return fail(TG_ERR_UNSUPPORTED, "GPU hash aggregation handles zero or one GROUP BY column");
+  a->group_col = -1; a->gk_kind = GK_NONE;
+  if (d->n_group_by == 1) {
+    int g = d->group_by_cols[0];
+    if (g < 0 || g >= a->ncols) return fail(TG_ERR_INVALID, "group-by column out of range");
+    if (is_int_family(a->types[g])) a->gk_kind = GK_I64;
+    else if (a->types[g] == TG_TYPE_DOUBLE) a->gk_kind = GK_F64;
+    else return fail(TG_ERR_UNSUPPORTED, "GROUP BY column type is not offloaded (int family / double only)");
+    a->group_col = g;
+    a->needed[g] = 1;
+  }
+  if (d->n_funcs <= 0 || d->n_funcs > TG_MAX_AGG) return fail(TG_ERR_UNSUPPORTED, "1..12 aggregate functions are offloaded");
+  a->spec.n = d->n_funcs;
+  a->nstates = 0;
+  a->out_nullable.assign(d->n_funcs, 0);
+  for (int k = 0; k < d->n_funcs; k++) {
+    const tg_agg_func& f = d->funcs[k];
+    AggFuncDev& o = a->spec.f[k];
+    o = AggFuncDev{f.name, f.arg_col, 0, 0, -1, -1, 0, f.arg_col2};
+    if (f.mode != TG_AGGMODE_COMPLETE && f.mode != TG_AGGMODE_FINAL) return fail(TG_ERR_UNSUPPORTED, "only Complete and Final aggregate modes are offloaded");
+    o.final_mode = f.mode == TG_AGGMODE_FINAL;
+    if (f.arg_col >= a->ncols || f.arg_col2 >= a->ncols) return fail(TG_ERR_INVALID, "aggregate argument column out of range");
+    bool arg_nullable = f.arg_col >= 0 && !(a->flags[f.arg_col] & TG_FLAG_NOT_NULL);
+    if (f.arg_col >= 0) { if (a->elem[f.arg_col] != 8) return fail(TG_ERR_UNSUPPORTED, "aggregate arguments must be 8-byte columns"); a->needed[f.arg_col] = 1; }
+    int atype = f.arg_col >= 0 ? a->types[f.arg_col] : TG_TYPE_LONGLONG;
+    o.is_real = atype == TG_TYPE_DOUBLE;
+    o.is_unsigned = f.arg_col >= 0 && (a->flags[f.arg_col] & TG_FLAG_UNSIGNED) != 0;
+    switch (f.name) {
+      case TG_AGG_COUNT:
+        if (o.final_mode) { if (f.arg_col < 0) return fail(TG_ERR_INVALID, "final COUNT needs the partial count column"); o.s0 = a->nstates++; }
+        else if (f.arg_col >= 0 && arg_nullable) o.s0 = a->nstates++;   // NOT NULL COUNT(x) == COUNT(*) == rows[]
+        break;
+      case TG_AGG_SUM:
+        // SUM(int) yields DECIMAL in TiDB (aggregation/base_func.go:223-245): not offloaded
+        if (f.arg_col < 0 || atype != TG_TYPE_DOUBLE) return fail(TG_ERR_UNSUPPORTED, "SUM is offloaded for DOUBLE arguments only (SUM(int) is DECIMAL)");
+        o.s0 = a->nstates++;
+        if (arg_nullable) o.s1 = a->nstates++;
+        a->out_nullable[k] = 1;
+        break;
+      case TG_AGG_AVG:
+        if (o.final_mode) {
+          if (f.arg_col < 0 || f.arg_col2 < 0 || a->types[f.arg_col2] != TG_TYPE_DOUBLE || !is_int_family(a->types[f.arg_col]))
+            return fail(TG_ERR_UNSUPPORTED, "final AVG takes (count BIGINT, sum DOUBLE)");
+          a->needed[f.arg_col2] = 1;
+          o.s0 = a->nstates++; o.s1 = a->nstates++;
+        } else {
+          if (f.arg_col < 0 || atype != TG_TYPE_DOUBLE) return fail(TG_ERR_UNSUPPORTED, "AVG is offloaded for DOUBLE arguments only");
+          o.s0 = a->nstates++;
+          if (arg_nullable) o.s1 = a->nstates++;
+        }
+        a->out_nullable[k] = 1;
+        break;
+      case TG_AGG_MIN: case TG_AGG_MAX:
+        if (f.arg_col < 0 || !(is_int_family(atype) || atype == TG_TYPE_DOUBLE)) return fail(TG_ERR_UNSUPPORTED, "MIN/MAX are offloaded for int family / DOUBLE");
+        o.s0 = a->nstates++;
+        if (arg_nullable) o.s1 = a->nstates++;
+        a->out_nullable[k] = 1;
+        break;
+      case TG_AGG_FIRSTROW:
+        if (f.arg_col < 0 || f.arg_col != a->group_col) return fail(TG_ERR_UNSUPPORTED, "FIRSTROW is offloaded only for the GROUP BY column (deterministic)");
+        a->out_nullable[k] = !(a->flags[f.arg_col] & TG_FLAG_NOT_NULL);
+        break;
+      default: return fail(TG_ERR_UNSUPPORTED, "aggregate function is not offloaded");
+    }
+  }
+  a->device = d->device;
+  a->expected_groups = d->expected_groups;
+  return TG_OK;
+}
+
+static void layout_table(tg_agg* a, uint8_t* mem, unsigned long long nslots, AggTable& t) {
+  size_t n = (size_t)nslots + 2;
+  t.nslots = nslots;
+  t.keys = reinterpret_cast<long long*>(mem);
+  t.rows = reinterpret_cast<unsigned long long*>(mem + n * 8);
+  for (int s = 0; s < a->nstates; s++) t.state[s] = reinterpret_cast<unsigned long long*>(mem + n * 8 * (2 + s));
+}
+
+static int alloc_table(tg_agg* a, unsigned long long nslots, DevBuf& mem, AggTable& t) {
+  size_t n = (size_t)nslots + 2;
+  TG_TRY(mem.ensure(a->device, n * 8 * (2 + a->nstates)));
+  layout_table(a, mem.as<uint8_t>(), nslots, t);
+  k_agg_init<<<agrid(a, (int64_t)n), 256, 0, a->stream>>>(t, a->spec, n);
+  a->stats.kernel_launches++;
+  return TG_OK;
+}
+
+static int grow_table(tg_agg* a, unsigned long long want_slots) {
+  std::unique_ptr<DevBuf> nm(new DevBuf());
+  AggTable nt{};
+  TG_TRY(alloc_table(a, want_slots, *nm, nt));
+  unsigned long long* sc = a->scalars.as<unsigned long long>();
+  TG_CUDA(cudaMemsetAsync(sc, 0, 8, a->stream));
+  k_agg_rehash<<<agrid(a, (int64_t)a->tbl.nslots + 2), 256, 0, a->stream>>>(a->tbl, nt, a->spec, a->nstates, sc);
+  a->stats.kernel_launches++;
+  TG_CUDA(cudaStreamSynchronize(a->stream));
+  std::swap(a->tbl_mem.p, nm->p); std::swap(a->tbl_mem.cap, nm->cap); std::swap(a->tbl_mem.device, nm->device);
+  a->tbl = nt;
+  a->nslots = want_slots;
+  return TG_OK;
+}
+
+// aggregate n device-resident rows
+static int update_device(tg_agg* a, const DevCols& cols, int64_t n) {
+  if (n == 0) return TG_OK;
+  a->stats.input_rows += n;
+  TG_TRY(a->scalars.ensure(a->device, 64));
+  unsigned long long* sc = a->scalars.as<unsigned long long>();
+  if (a->nslots == 0) {
+    unsigned long long want = 1024;
+    if (a->group_col >= 0) {
+      if (a->expected_groups > 0) want = std::max<unsigned long long>(1024, (unsigned long long)a->expected_groups * 2);
+      else want = std::max<unsigned long long>(1024, (unsigned long long)std::min<int64_t>(n, 1ll << 22) * 2);
+    }
+    TG_CUDA(cudaMemsetAsync(sc, 0, 64, a->stream));
+    TG_TRY(alloc_table(a, want, a->tbl_mem, a->tbl));
+    a->nslots = want;
+  }
+  TG_CUDA(cudaEventRecord(a->ev0, a->stream));
+  if (a->group_col < 0) {
+    k_agg_update_nogroup<<<agrid(a, n, 256, 4), 256, 0, a->stream>>>(cols, n, a->tbl, a->spec);
+    a->stats.kernel_launches++;
+  } else {
+    GroupKey gk{cols.data[a->group_col], cols.nulls[a->group_col], a->gk_kind, 0};
+    size_t dwords = (size_t)((n + 31) / 32);
+    TG_TRY(a->deferred.ensure(a->device, dwords * 4 + 16));
+    TG_CUDA(cudaMemsetAsync(a->deferred.p, 0, dwords * 4, a->stream));
+    TG_CUDA(cudaMemsetAsync(sc + 1, 0, 8, a->stream));
+    const uint32_t* only = nullptr;
+    DevBuf prev_deferred;
+    for (int round = 0; round < 40; round++) {
+      unsigned long long max_fill = (unsigned long long)((double)a->nslots * 0.6);
+      k_agg_update<<<agrid(a, n), 256, 0, a->stream>>>(gk, cols, n, a->tbl, a->spec, max_fill, sc, a->deferred.as<uint32_t>(), only, sc + 1);
+      a->stats.kernel_launches++;
+      unsigned long long nd = 0;
+      TG_CUDA(cudaMemcpyAsync(&nd, sc + 1, 8, cudaMemcpyDeviceToHost, a->stream));
+      TG_CUDA(cudaStreamSynchronize(a->stream));
+      if (nd == 0) break;
+      // grow ×4 (at least enough for every deferred row to be a new group), re-run only the deferred rows
+      unsigned long long want = std::max<unsigned long long>(a->nslots * 4, (unsigned long long)((a->nslots * 0.6 + (double)nd) * 2));
+      TG_TRY(grow_table(a, want));
+      TG_TRY(prev_deferred.ensure(a->device, dwords * 4 + 16));
+      TG_CUDA(cudaMemcpyAsync(prev_deferred.p, a->deferred.p, dwords * 4, cudaMemcpyDeviceToDevice, a->stream));
+      TG_CUDA(cudaMemsetAsync(a->deferred.p, 0, dwords * 4, a->stream));
+      TG_CUDA(cudaMemsetAsync(sc + 1, 0, 8, a->stream));
+      only = prev_deferred.as<uint32_t>();
+      if (round == 39) return fail(TG_ERR_CUDA, "internal: aggregation table failed to converge");
+    }
+  }
+  TG_CUDA(cudaEventRecord(a->ev1, a->stream));
+  TG_CUDA(cudaStreamSynchronize(a->stream));
+  TG_CUDA(cudaGetLastError());
+  float ms = 0; cudaEventElapsedTime(&ms, a->ev0, a->ev1); a->stats.update_ms += ms;
+  return TG_OK;
+}
+
+static int64_t alogical_rows(const tg_chunk* c) { return c->sel ? c->nsel : (c->ncols > 0 ? c->cols[0].length : 0); }
+
+static int avalidate(const tg_agg* a, const tg_chunk* chk) {
+  if (!chk || chk->ncols != a->ncols) return fail(TG_ERR_INVALID, "chunk column count does not match the child schema");
+  int64_t phys = chk->cols[0].length;
+  for (int c = 0; c < a->ncols; c++) {
+    if (!a->needed[c]) continue;
+    if (chk->cols[c].elem_len != a->elem[c]) return fail(TG_ERR_INVALID, "chunk column elem_len does not match the schema type");
+    if (chk->cols[c].length != phys) return fail(TG_ERR_INVALID, "chunk columns have different lengths");
+  }
+  return TG_OK;
+}
+
+static int astage_append(tg_agg* a, const tg_chunk* chk) {
+  AggHostStage& st = a->stage;
+  int64_t n = alogical_rows(chk);
+  if (n == 0) return TG_OK;
+  for (int c = 0; c < a->ncols; c++) {
+    if (!a->needed[c]) continue;
+    const tg_column& col = chk->cols[c];
+    PinBuf& d = *st.data[c];
+    TG_TRY(d.reserve((size_t)(st.rows + n) * 8));
+    uint64_t* dst = reinterpret_cast<uint64_t*>(d.p) + st.rows;
+    const uint64_t* src = reinterpret_cast<const uint64_t*>(col.data);
+    if (!chk->sel) std::memcpy(dst, src, (size_t)n * 8);
+    else for (int64_t i = 0; i < n; i++) dst[i] = src[chk->sel[i]];
+    d.used = (size_t)(st.rows + n) * 8;
+    bool bring = col.null_bitmap != nullptr;
+    if (bring || st.has_nulls[c]) {
+      PinBuf& nb = *st.nulls[c];
+      size_t need = (size_t)((st.rows + n + 7) / 8) + 1;
+      TG_TRY(nb.reserve(need));
+      if (!st.has_nulls[c]) { std::memset(nb.p, 0xff, (size_t)((st.rows + 7) / 8) + 1); st.has_nulls[c] = 1; }
+      if (bring && !chk->sel) append_bits(nb.p, st.rows, col.null_bitmap, n);
+      else for (int64_t i = 0; i < n; i++) {
+        bool nn = bring ? bit_not_null(col.null_bitmap, chk->sel ? chk->sel[i] : i) : true;
+        int64_t r = st.rows + i;
+        if (nn) nb.p[r >> 3] |= (uint8_t)(1u << (r & 7)); else nb.p[r >> 3] &= (uint8_t)~(1u << (r & 7));
+      }
+      nb.used = need;
+    }
+  }
+  st.rows += n;
+  return TG_OK;
+}
+
+static int aflush(tg_agg* a) {
+  AggHostStage& st = a->stage;
+  if (st.rows == 0) return TG_OK;
+  DevCols v{};
+  for (int c = 0; c < a->ncols; c++) {
+    v.elem_len[c] = a->elem[c];
+    if (!a->needed[c]) continue;
+    size_t bytes = (size_t)st.rows * 8;
+    TG_TRY(a->dcols[c]->ensure(a->device, bytes + 16));
+    TG_CUDA(cudaMemcpyAsync(a->dcols[c]->p, st.data[c]->p, bytes, cudaMemcpyHostToDevice, a->stream));
+    a->stats.h2d_bytes += bytes;
+    v.data[c] = a->dcols[c]->p;
+    if (st.has_nulls[c]) {
+      size_t nb = (size_t)((st.rows + 7) / 8);
+      TG_TRY(a->dnulls[c]->ensure(a->device, nb + 16));
+      TG_CUDA(cudaMemcpyAsync(a->dnulls[c]->p, st.nulls[c]->p, nb, cudaMemcpyHostToDevice, a->stream));
+      a->stats.h2d_bytes += nb;
+      v.nulls[c] = a->dnulls[c]->as<uint8_t>();
+    }
+  }
+  int64_t n = st.rows;
+  int rc = update_device(a, v, n);
+  st.rows = 0;
+  std::fill(st.has_nulls.begin(), st.has_nulls.end(), 0);
+  return rc;
+}
+
+static int afinalize(tg_agg* a) {
+  TG_TRY(a->scalars.ensure(a->device, 64));
+  unsigned long long* sc = a->scalars.as<unsigned long long>();
+  int nf = a->spec.n;
+  a->out_cols.clear(); a->out_valid.clear(); a->out_bitmaps.clear();
+  for (int k = 0; k < nf; k++) { a->out_cols.emplace_back(new DevBuf()); a->out_valid.emplace_back(new DevBuf()); a->out_bitmaps.emplace_back(new DevBuf()); }
+  // agg_hash_executor.go:654: empty input and no GROUP BY → one row of default values (COUNT 0, rest NULL)
+  bool default_row = a->stats.input_rows == 0 && a->group_col < 0;
+  if (a->nslots == 0) {
+    if (!default_row) { a->out_rows = 0; return TG_OK; }
+    TG_CUDA(cudaMemsetAsync(sc, 0, 64, a->stream));
+    TG_TRY(alloc_table(a, 1024, a->tbl_mem, a->tbl));
+    a->nslots = 1024;
+  }
+  unsigned long long fill = 0;
+  TG_CUDA(cudaMemcpyAsync(&fill, sc, 8, cudaMemcpyDeviceToHost, a->stream));
+  TG_CUDA(cudaStreamSynchronize(a->stream));
+  int64_t cap = (int64_t)fill + 2 + 1;
+  AggOut ao{};
+  for (int k = 0; k < nf; k++) {
+    TG_TRY(a->out_cols[k]->ensure(a->device, (size_t)cap * 8 + 16));
+    ao.data[k] = a->out_cols[k]->p;
+    ao.valid[k] = nullptr;
+    if (a->out_nullable[k] || default_row) { TG_TRY(a->out_valid[k]->ensure(a->device, (size_t)cap + 16)); ao.valid[k] = a->out_valid[k]->as<uint8_t>(); }
+  }
+  TG_CUDA(cudaEventRecord(a->ev0, a->stream));
+  TG_CUDA(cudaMemsetAsync(sc + 2, 0, 8, a->stream));
+  k_agg_finalize<<<agrid(a, (int64_t)a->nslots + 2), 256, 0, a->stream>>>(a->tbl, a->spec, a->gk_kind, ao, sc + 2);
+  a->stats.kernel_launches++;
+  unsigned long long nrows = 0;
+  TG_CUDA(cudaMemcpyAsync(&nrows, sc + 2, 8, cudaMemcpyDeviceToHost, a->stream));
+  TG_CUDA(cudaStreamSynchronize(a->stream));
+  if (default_row && nrows == 0) {
+    // write the default row on the host side: COUNT → 0, everything else NULL
+    for (int k = 0; k < nf; k++) {
+      unsigned long long zero = 0; uint8_t v = a->spec.f[k].name == TG_AGG_COUNT ? 1 : 0;
+      TG_CUDA(cudaMemcpyAsync(a->out_cols[k]->p, &zero, 8, cudaMemcpyHostToDevice, a->stream));
+      TG_CUDA(cudaMemcpyAsync(a->out_valid[k]->p, &v, 1, cudaMemcpyHostToDevice, a->stream));
+      TG_CUDA(cudaStreamSynchronize(a->stream));
+    }
+    nrows = 1;
+  }
+  a->out_rows = (int64_t)nrows;
+  a->stats.groups = a->out_rows;
+  a->stats.table_slots = (int64_t)a->nslots;
+  for (int k = 0; k < nf; k++) {
+    if (!ao.valid[k]) continue;
+    TG_TRY(a->out_bitmaps[k]->ensure(a->device, (size_t)((a->out_rows + 7) / 8) + 16));
+    if (a->out_rows) { k_pack_bitmap_agg<<<agrid(a, (a->out_rows + 7) / 8), 256, 0, a->stream>>>(ao.valid[k], a->out_rows, a->out_bitmaps[k]->as<uint8_t>()); a->stats.kernel_launches++; }
+  }
+  TG_CUDA(cudaEventRecord(a->ev1, a->stream));
+  TG_CUDA(cudaStreamSynchronize(a->stream));
+  TG_CUDA(cudaGetLastError());
+  float ms = 0; cudaEventElapsedTime(&ms, a->ev0, a->ev1); a->stats.finalize_ms += ms;
+  return TG_OK;
+}
+
+}  // namespace tg
+
+#define TGA_LOCK(a)                                                            \
+  if (!(a)) return tg::fail(TG_ERR_INVALID, "handle is NULL");                 \
+  if ((a)->closed.load()) return tg::fail(TG_ERR_CANCELLED, "handle is closed"); \
+  std::lock_guard<std::mutex> lock__((a)->mu);                                 \
+  if ((a)->closed.load()) return tg::fail(TG_ERR_CANCELLED, "handle is closed"); \
+  tg::DeviceGuard guard__((a)->device);                                        \
+  if (!guard__.ok) return tg::fail(TG_ERR_CUDA, "cudaSetDevice failed (no usable CUDA device)")
+
+extern "C" {
+
+int tg_agg_supported(const tg_agg_desc* desc) { tg_agg tmp; return agg_setup(&tmp, desc); }
+
+int tg_agg_open(const tg_agg_desc* desc, tg_agg** out) {
+  if (!out) return fail(TG_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  std::unique_ptr<tg_agg> a(new tg_agg());
+  TG_TRY(agg_setup(a.get(), desc));
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(TG_ERR_CUDA, "no CUDA device: the GPU hash aggregation has no CPU fallback"); }
+  if (a->device < 0 || a->device >= ndev) return fail(TG_ERR_INVALID, "device ordinal out of range");
+  DeviceGuard g(a->device);
+  if (!g.ok) return fail(TG_ERR_CUDA, "cudaSetDevice failed");
+  if (desc->stream) { a->stream = (cudaStream_t)desc->stream; a->own_stream = false; }
+  else { TG_CUDA(cudaStreamCreateWithFlags(&a->stream, cudaStreamNonBlocking)); a->own_stream = true; }
+  TG_CUDA(cudaEventCreate(&a->ev0));
+  TG_CUDA(cudaEventCreate(&a->ev1));
+  a->nsm = device_sm_count(a->device);
+  for (int c = 0; c < a->ncols; c++) {
+    a->stage.data.emplace_back(new PinBuf()); a->stage.nulls.emplace_back(new PinBuf());
+    a->dcols.emplace_back(new DevBuf()); a->dnulls.emplace_back(new DevBuf());
+  }
+  a->stage.has_nulls.assign(a->ncols, 0);
+  *out = a.release();
+  return TG_OK;
+}
+
+int tg_agg_push(tg_agg* a, const tg_chunk* chk) {
+  TGA_LOCK(a);
+  if (a->finished) return fail(TG_ERR_STATE, "push after finish");
+  TG_TRY(avalidate(a, chk));
+  TG_TRY(astage_append(a, chk));
+  if (a->stage.rows >= (4ll << 20)) TG_TRY(aflush(a));
+  return TG_OK;
+}
+
+int tg_agg_push_dev(tg_agg* a, const tg_chunk* chk) {
+  TGA_LOCK(a);
+  if (a->finished) return fail(TG_ERR_STATE, "push after finish");
+  TG_TRY(avalidate(a, chk));
+  if (chk->sel) return fail(TG_ERR_UNSUPPORTED, "device-resident chunks must not carry a sel vector");
+  TG_TRY(aflush(a));
+  DevCols v{};
+  for (int c = 0; c < a->ncols; c++) {
+    v.elem_len[c] = a->elem[c];
+    if (!a->needed[c]) continue;
+    v.data[c] = chk->cols[c].data; v.nulls[c] = chk->cols[c].null_bitmap;
+  }
+  return update_device(a, v, chk->cols[0].length);
+}
+
+int tg_agg_finish(tg_agg* a) {
+  TGA_LOCK(a);
+  if (a->finished) return TG_OK;
+  TG_TRY(aflush(a));
+  TG_TRY(afinalize(a));
+  a->finished = true;
+  return TG_OK;
+}
+
+int tg_agg_next(tg_agg* a, tg_mut_chunk* out, int64_t max_rows, int64_t* nrows) {
+  TGA_LOCK(a);
+  if (!out || !nrows) return fail(TG_ERR_INVALID, "out / nrows is NULL");
+  *nrows = 0;
+  if (!a->finished) return fail(TG_ERR_STATE, "next before finish (hash aggregation is a pipeline breaker)");
+  if (out->ncols != a->spec.n) return fail(TG_ERR_INVALID, "output chunk column count does not match the aggregate list");
+  int64_t lo = a->consumed;
+  int64_t want = std::min<int64_t>(std::min<int64_t>(max_rows, out->capacity_rows), a->out_rows - lo);
+  if (want <= 0) return TG_OK;
+  if (want < a->out_rows - lo) want -= want % 8;
+  if (want <= 0) return fail(TG_ERR_CAPACITY, "tg_agg_next needs max_rows >= 8");
+  for (int k = 0; k < a->spec.n; k++) {
+    TG_CUDA(cudaMemcpyAsync(out->cols[k].data, a->out_cols[k]->as<uint8_t>() + (size_t)lo * 8, (size_t)want * 8, cudaMemcpyDeviceToHost, a->stream));
+    a->stats.d2h_bytes += want * 8;
+    size_t nb = (size_t)((want + 7) / 8);
+    if (a->out_bitmaps[k]->p) {
+      if (!out->cols[k].null_bitmap) return fail(TG_ERR_INVALID, "output column can be NULL but the caller passed no null bitmap");
+      TG_CUDA(cudaMemcpyAsync(out->cols[k].null_bitmap, a->out_bitmaps[k]->as<uint8_t>() + lo / 8, nb, cudaMemcpyDeviceToHost, a->stream));
+    } else if (out->cols[k].null_bitmap) {
+      std::memset(out->cols[k].null_bitmap, 0xff, nb);
+      if (want & 7) out->cols[k].null_bitmap[nb - 1] = (uint8_t)((1u << (want & 7)) - 1);
+    }
+  }
+  TG_CUDA(cudaStreamSynchronize(a->stream));
+  if (want & 7) for (int k = 0; k < a->spec.n; k++) if (a->out_bitmaps[k]->p) out->cols[k].null_bitmap[want >> 3] &= (uint8_t)((1u << (want & 7)) - 1);
+  a->consumed += want;
+  *nrows = want;
+  return TG_OK;
+}
+
+int tg_agg_result_dev(tg_agg* a, int64_t* out_rows, void** out_cols, void** out_nulls) {
+  TGA_LOCK(a);
+  if (!a->finished) return fail(TG_ERR_STATE, "result before finish");
+  if (out_rows) *out_rows = a->out_rows;
+  for (int k = 0; k < a->spec.n; k++) {
+    if (out_cols) out_cols[k] = a->out_cols[k]->p;
+    if (out_nulls) out_nulls[k] = a->out_bitmaps[k]->p;
+  }
+  return TG_OK;
+}
+
+int tg_agg_get_stats(tg_agg* a, tg_agg_stats* out) {
+  TGA_LOCK(a);
+  if (!out) return fail(TG_ERR_INVALID, "out is NULL");
+  *out = a->stats;
+  return TG_OK;
+}
+
+int tg_agg_close(tg_agg* a) {
+  if (!a) return TG_OK;
+  bool was = a->closed.exchange(true);
+  if (was) return TG_OK;
+  {
+    std::lock_guard<std::mutex> lock(a->mu);
+    DeviceGuard g(a->device);
+    if (a->stream) cudaStreamSynchronize(a->stream);
+    if (a->ev0) cudaEventDestroy(a->ev0);
+    if (a->ev1) cudaEventDestroy(a->ev1);
+    if (a->own_stream && a->stream) cudaStreamDestroy(a->stream);
+    cudaGetLastError();
+  }
+  delete a;
+  return TG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,940 @@
+// join.cu — tg_join_*: the GPU hash join behind HashJoinV2Exec's Open/Next/Close contract
+// (pkg/executor/join/hash_join_v2.go:608, :690, :1161, :647).  Host-side orchestration only; the
+// kernels live in join_kernels.cuh.
+#include <memory>
+#include <deque>
+#include <algorithm>
+#include "join_kernels.cuh"
+
+namespace tg {
+
+static const int64_t kGeneralBatchRows = 16ll << 20;   // sub-batch of the general probe path (bounds temp memory)
+static const int64_t kStageBatchRows = 4ll << 20;      // host staging batch for small pushed chunks
+static const int64_t kDirectPushRows = 128ll << 10;    // chunks at least this big are copied straight from the caller
+static const int64_t kNextWindowRows = 1ll << 20;      // D2H window that serves small tg_join_next calls
+
+struct Side {
+  int ncols = 0;
+  std::vector<int> types;
+  std::vector<uint32_t> flags;
+  std::vector<int> elem;
+  std::vector<char> needed;       // staged to the device (key ∪ used ∪ filter columns)
+  int key_col = -1;
+  std::vector<int> used;          // columns of this side that appear in the output
+  DevFilter filter{};
+};
+
+// device-resident columns of one side for one batch
+struct ColStore {
+  std::vector<std::unique_ptr<DevBuf>> data, nulls;
+  std::vector<char> has_nulls;
+  int64_t rows = 0, cap_rows = 0;
+  void init(int ncols) {
+    data.clear(); nulls.clear();
+    for (int i = 0; i < ncols; i++) { data.emplace_back(new DevBuf()); nulls.emplace_back(new DevBuf()); }
+    has_nulls.assign(ncols, 0);
+    rows = cap_rows = 0;
+  }
+  DevCols view(const Side& s) const {
+    DevCols v{};
+    for (int c = 0; c < s.ncols && c < TG_MAX_COLS; c++) {
+      v.data[c] = s.needed[c] ? data[c]->p : nullptr;
+      v.nulls[c] = (s.needed[c] && has_nulls[c]) ? nulls[c]->as<uint8_t>() : nullptr;
+      v.elem_len[c] = s.elem[c];
+    }
+    return v;
+  }
+};
+
+// host staging of pushed chunks (pinned), one buffer per needed column
+struct HostStage {
+  std::vector<std::unique_ptr<PinBuf>> data, nulls;
+  std::vector<char> has_nulls;
+  int64_t rows = 0;
+  void init(int ncols) {
+    data.clear(); nulls.clear();
+    for (int i = 0; i < ncols; i++) { data.emplace_back(new PinBuf()); nulls.emplace_back(new PinBuf()); }
+    has_nulls.assign(ncols, 0);
+    rows = 0;
+  }
+  void reset() { rows = 0; std::fill(has_nulls.begin(), has_nulls.end(), 0); for (auto& d : data) d->used = 0; for (auto& d : nulls) d->used = 0; }
+};
+
+struct ResultBatch {
+  std::vector<std::unique_ptr<DevBuf>> cols, bitmaps;
+  int64_t rows = 0;
+  int64_t consumed = 0;
+};
+
+}  // namespace tg
+
+using namespace tg;
+
+struct tg_join {
+  std::mutex mu;
+  std::atomic<bool> closed{false};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int nsm = 148;
+  double load_factor = 0.5;
+
+  int join_type = 0;
+  bool build_is_right = true;
+  Side build, probe;
+  int n_lused = 0, n_rused = 0;
+  std::vector<int> lused, rused;
+  int probe_kind = PK_INNER;
+  bool need_scan = false;          // JoinProbe.NeedScanRowTable
+  int scan_mode = 0;
+  bool has_flag_col = false;
+  int n_out = 0;
+  std::vector<int> out_elem;
+  KeySpec build_key{}, probe_key{};   // data pointers filled per launch
+
+  // build state
+  HostStage bstage;
+  ColStore bcols;
+  bool built = false;
+  DevBuf table, rows_store, row_slot, row_rank, slot_used, scalars;
+  TableView tv{};
+  RowSpec rowspec{};
+  std::vector<int> build_word_of_col;   // build column → row-store word (mode G)
+  int u1_payload_col = -1;
+
+  // probe state
+  HostStage pstage;
+  ColStore pcols_dev;
+  DevBuf tmp_cnt, tmp_slot, tmp_off, tmp_sums, out_cursor;
+  std::vector<std::unique_ptr<DevBuf>> tmp_valid;
+  std::deque<std::unique_ptr<ResultBatch>> results;
+  std::unique_ptr<ResultBatch> dev_result;      // tg_join_probe_dev output (reused across calls)
+  bool probe_finished = false;
+  // small-Next window
+  PinBuf win;
+  int64_t win_lo = 0, win_hi = 0;
+  ResultBatch* win_batch = nullptr;
+
+  tg_join_stats stats{};
+};
+
+namespace tg {
+
+static int grid_for(const tg_join* j, int64_t n, int block, int per_sm) {
+  int64_t need = (n + block - 1) / block;
+  int64_t cap = (int64_t)j->nsm * per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+// ---- descriptor → handle -------------------------------------------------------------------------------
+static int fill_side(Side& s, int n, const int32_t* types, const uint32_t* flags) {
+  if (n <= 0 || n > TG_MAX_COLS) return fail(TG_ERR_UNSUPPORTED, "child schema must have 1..16 columns");
+  s.ncols = n;
+  s.types.assign(types, types + n);
+  s.flags.resize(n);
+  for (int i = 0; i < n; i++) s.flags[i] = flags ? flags[i] : 0;
+  s.elem.resize(n);
+  for (int i = 0; i < n; i++) s.elem[i] = fixed_len(types[i]);
+  s.needed.assign(n, 0);
+  return TG_OK;
+}
+
+static int key_kind_of(int tp) {
+  if (is_int_family(tp)) return KEY_I64;
+  if (tp == TG_TYPE_DOUBLE) return KEY_F64;
+  if (tp == TG_TYPE_FLOAT) return KEY_F32;
+  return -1;
+}
+static bool key_unsigned(int tp, uint32_t flag) {
+  // getKeyProp join_table_meta.go:130: YEAR always unsigned, DURATION always signed
+  if (tp == TG_TYPE_YEAR) return true;
+  if (tp == TG_TYPE_DURATION) return false;
+  return (flag & TG_FLAG_UNSIGNED) != 0;
+}
+
+static int check_filter(const Side& s, const tg_filter_item* items, int n, DevFilter& out) {
+  if (n < 0 || n > TG_MAX_FILTER) return fail(TG_ERR_UNSUPPORTED, "at most 8 CNF filter items are offloaded");
+  out.n = n;
+  for (int i = 0; i < n; i++) {
+    const tg_filter_item& it = items[i];
+    if (it.lhs_col < 0 || it.lhs_col >= s.ncols || it.rhs_col >= s.ncols) return fail(TG_ERR_INVALID, "filter column out of range");
+    if (s.elem[it.lhs_col] != 8 || (it.rhs_col >= 0 && s.elem[it.rhs_col] != 8))
+      return fail(TG_ERR_UNSUPPORTED, "filters are offloaded on 8-byte columns only");
+    if (it.op < TG_CMP_LT || it.op > TG_CMP_NE) return fail(TG_ERR_INVALID, "bad filter op");
+    out.items[i] = it;
+  }
+  return TG_OK;
+}
+
+static int setup(tg_join* j, const tg_join_desc* d) {
+  if (!d) return fail(TG_ERR_INVALID, "desc is NULL");
+  j->join_type = d->join_type;
+  j->build_is_right = d->build_is_right != 0;
+  Side left, right;
+  TG_TRY(fill_side(left, d->n_left_cols, d->left_types, d->left_flags));
+  TG_TRY(fill_side(right, d->n_right_cols, d->right_types, d->right_flags));
+  if (d->nkeys != 1) return fail(TG_ERR_UNSUPPORTED, "GPU hash join handles exactly one equal-condition key (OneInt64 / fixed 8-byte key modes)");
+  int lk = d->left_key_idx[0], rk = d->right_key_idx[0];
+  if (lk < 0 || lk >= left.ncols || rk < 0 || rk >= right.ncols) return fail(TG_ERR_INVALID, "key column out of range");
+  left.key_col = lk; right.key_col = rk;
+  int lkind = key_kind_of(left.types[lk]), rkind = key_kind_of(right.types[rk]);
+  if (lkind < 0 || rkind < 0) return fail(TG_ERR_UNSUPPORTED, "join key type is not offloaded (int family / float / double only)");
+  if ((lkind == KEY_I64) != (rkind == KEY_I64)) return fail(TG_ERR_UNSUPPORTED, "integer vs real join keys are cast by the planner before the join");
+  auto used_list = [&](int n, const int32_t* v, int ncols, std::vector<int>& out) -> int {
+    out.clear();
+    if (n < 0) { for (int i = 0; i < ncols; i++) out.push_back(i); return TG_OK; }
+    for (int i = 0; i < n; i++) { if (v[i] < 0 || v[i] >= ncols) return fail(TG_ERR_INVALID, "used column out of range"); out.push_back(v[i]); }
+    return TG_OK;
+  };
+  TG_TRY(used_list(d->n_lused, d->lused, left.ncols, j->lused));
+  TG_TRY(used_list(d->n_rused, d->rused, right.ncols, j->rused));
+  left.used = j->lused; right.used = j->rused;
+  j->has_flag_col = false;
+  // NewJoinProbe base_join_probe.go:850-932
+  bool brt = j->build_is_right;
+  switch (j->join_type) {
+    case TG_JOIN_INNER: j->probe_kind = PK_INNER; j->need_scan = false; break;
+    case TG_JOIN_LEFT_OUTER:
+      j->need_scan = !brt; j->probe_kind = j->need_scan ? PK_INNER : PK_PROBE_OUTER; j->scan_mode = 0; break;
+    case TG_JOIN_RIGHT_OUTER:
+      j->need_scan = brt; j->probe_kind = j->need_scan ? PK_INNER : PK_PROBE_OUTER; j->scan_mode = 0; break;
+    case TG_JOIN_SEMI: case TG_JOIN_ANTI_SEMI:
+      if (!j->rused.empty()) return fail(TG_ERR_INVALID, "len(rUsed) != 0 for semi join");
+      j->need_scan = !brt;
+      if (brt) j->probe_kind = j->join_type == TG_JOIN_SEMI ? PK_SEMI : PK_ANTI;
+      else { j->probe_kind = PK_MARK_ONLY; j->scan_mode = j->join_type == TG_JOIN_SEMI ? 1 : 0; }
+      break;
+    case TG_JOIN_LEFT_OUTER_SEMI: case TG_JOIN_ANTI_LEFT_OUTER_SEMI:
+      if (!j->rused.empty()) return fail(TG_ERR_INVALID, "len(rUsed) != 0 for left outer semi join");
+      if (!brt) return fail(TG_ERR_UNSUPPORTED, "left outer semi join needs the right side as build side");
+      j->probe_kind = j->join_type == TG_JOIN_LEFT_OUTER_SEMI ? PK_LEFT_OUTER_SEMI : PK_ANTI_LEFT_OUTER_SEMI;
+      j->need_scan = false; j->has_flag_col = true;
+      break;
+    default: return fail(TG_ERR_INVALID, "unknown join type");
+  }
+  j->build = brt ? right : left;
+  j->probe = brt ? left : right;
+  TG_TRY(check_filter(j->build, d->build_filter, d->n_build_filter, j->build.filter));
+  TG_TRY(check_filter(j->probe, d->probe_filter, d->n_probe_filter, j->probe.filter));
+  for (Side* s : {&j->build, &j->probe}) {
+    s->needed[s->key_col] = 1;
+    for (int c : s->used) {
+      if (s->elem[c] != 8 && s->elem[c] != 4) return fail(TG_ERR_UNSUPPORTED, "only 4/8-byte fixed-width columns are offloaded (no DECIMAL / var-len yet)");
+      s->needed[c] = 1;
+    }
+    for (int i = 0; i < s->filter.n; i++) {
+      s->needed[s->filter.items[i].lhs_col] = 1;
+      if (s->filter.items[i].rhs_col >= 0) s->needed[s->filter.items[i].rhs_col] = 1;
+    }
+  }
+  // key specs; mixed signedness (NeedSignFlag, join_table_meta.go:296-303): the signed side's negative
+  // values can never match
+  int bk = j->build.key_col, pk = j->probe.key_col;
+  j->build_key = KeySpec{nullptr, nullptr, key_kind_of(j->build.types[bk]), 0};
+  j->probe_key = KeySpec{nullptr, nullptr, key_kind_of(j->probe.types[pk]), 0};
+  if (j->build_key.kind == KEY_I64) {
+    bool bu = key_unsigned(j->build.types[bk], j->build.flags[bk]), pu = key_unsigned(j->probe.types[pk], j->probe.flags[pk]);
+    if (bu != pu) { j->build_key.reject_negative = !bu; j->probe_key.reject_negative = !pu; }
+  }
+  // output schema: LUsed of left ‖ RUsed of right [‖ matched flag]
+  j->n_lused = (int)j->lused.size(); j->n_rused = (int)j->rused.size();
+  j->out_elem.clear();
+  for (int c : j->lused) j->out_elem.push_back(left.elem[c]);
+  for (int c : j->rused) j->out_elem.push_back(right.elem[c]);
+  if (j->has_flag_col) j->out_elem.push_back(8);
+  j->n_out = (int)j->out_elem.size();
+  if (j->n_out > TG_MAX_OUT) return fail(TG_ERR_UNSUPPORTED, "too many output columns");
+  j->device = d->device;
+  j->load_factor = (d->load_factor > 0.05 && d->load_factor <= 0.95) ? d->load_factor : 0.5;
+  return TG_OK;
+}
+
+// ---- host chunk → staging ---------------------------------------------------------------------------
+static int64_t chunk_logical_rows(const tg_chunk* c) { return c->sel ? c->nsel : (c->ncols > 0 ? c->cols[0].length : 0); }
+
+static int validate_chunk(const Side& s, const tg_chunk* chk) {
+  if (!chk || chk->ncols != s.ncols) return fail(TG_ERR_INVALID, "chunk column count does not match the child schema");
+  int64_t phys = chk->ncols ? chk->cols[0].length : 0;
+  for (int c = 0; c < s.ncols; c++) {
+    if (!s.needed[c]) continue;
+    if (chk->cols[c].elem_len != s.elem[c]) return fail(TG_ERR_INVALID, "chunk column elem_len does not match the schema type");
+    if (chk->cols[c].length != phys) return fail(TG_ERR_INVALID, "chunk columns have different lengths");
+    if (phys && !chk->cols[c].data) return fail(TG_ERR_INVALID, "chunk column data is NULL");
+  }
+  return TG_OK;
+}
+
+// append the logical rows of a host chunk to the staging buffers (gathers through sel)
+static int stage_append(HostStage& st, const Side& s, const tg_chunk* chk) {
+  int64_t n = chunk_logical_rows(chk);
+  if (n == 0) return TG_OK;
+  for (int c = 0; c < s.ncols; c++) {
+    if (!s.needed[c]) continue;
+    const tg_column& col = chk->cols[c];
+    int el = s.elem[c];
+    PinBuf& d = *st.data[c];
+    TG_TRY(d.reserve((size_t)(st.rows + n) * el));
+    uint8_t* dst = d.p + (size_t)st.rows * el;
+    if (!chk->sel) std::memcpy(dst, col.data, (size_t)n * el);
+    else if (el == 8) { auto* o = reinterpret_cast<uint64_t*>(dst); auto* in = reinterpret_cast<const uint64_t*>(col.data); for (int64_t i = 0; i < n; i++) o[i] = in[chk->sel[i]]; }
+    else { auto* o = reinterpret_cast<uint32_t*>(dst); auto* in = reinterpret_cast<const uint32_t*>(col.data); for (int64_t i = 0; i < n; i++) o[i] = in[chk->sel[i]]; }
+    d.used = (size_t)(st.rows + n) * el;
+    // null bitmap: materialised lazily, the first time a chunk brings one
+    PinBuf& nb = *st.nulls[c];
+    bool bring = col.null_bitmap != nullptr;
+    if (bring || st.has_nulls[c]) {
+      size_t need = (size_t)((st.rows + n + 7) / 8) + 1;
+      TG_TRY(nb.reserve(need));
+      if (!st.has_nulls[c]) { std::memset(nb.p, 0xff, (size_t)((st.rows + 7) / 8) + 1); st.has_nulls[c] = 1; }
+      if (bring && !chk->sel) append_bits(nb.p, st.rows, col.null_bitmap, n);
+      else {
+        for (int64_t i = 0; i < n; i++) {
+          bool nn = bring ? bit_not_null(col.null_bitmap, chk->sel ? chk->sel[i] : i) : true;
+          int64_t r = st.rows + i;
+          if (nn) nb.p[r >> 3] |= (uint8_t)(1u << (r & 7)); else nb.p[r >> 3] &= (uint8_t)~(1u << (r & 7));
+        }
+      }
+      nb.used = need;
+    }
+  }
+  st.rows += n;
+  return TG_OK;
+}
+
+// staging → device column store (replaces its contents)
+static int stage_to_device(tg_join* j, HostStage& st, const Side& s, ColStore& cs) {
+  cs.rows = st.rows;
+  for (int c = 0; c < s.ncols; c++) {
+    if (!s.needed[c]) continue;
+    size_t bytes = (size_t)st.rows * s.elem[c];
+    TG_TRY(cs.data[c]->ensure(j->device, bytes + 16));
+    if (bytes) { TG_CUDA(cudaMemcpyAsync(cs.data[c]->p, st.data[c]->p, bytes, cudaMemcpyHostToDevice, j->stream)); j->stats.h2d_bytes += bytes; }
+    cs.has_nulls[c] = st.has_nulls[c];
+    if (st.has_nulls[c]) {
+      size_t nb = (size_t)((st.rows + 7) / 8);
+      TG_TRY(cs.nulls[c]->ensure(j->device, nb + 16));
+      if (nb) { TG_CUDA(cudaMemcpyAsync(cs.nulls[c]->p, st.nulls[c]->p, nb, cudaMemcpyHostToDevice, j->stream)); j->stats.h2d_bytes += nb; }
+    }
+  }
+  return TG_OK;
+}
+
+// a whole (large) host chunk → device column store, straight from the caller's buffers
+static int chunk_to_device(tg_join* j, const tg_chunk* chk, const Side& s, ColStore& cs) {
+  int64_t n = chk->cols[0].length;
+  cs.rows = n;
+  for (int c = 0; c < s.ncols; c++) {
+    if (!s.needed[c]) continue;
+    size_t bytes = (size_t)n * s.elem[c];
+    TG_TRY(cs.data[c]->ensure(j->device, bytes + 16));
+    TG_CUDA(cudaMemcpyAsync(cs.data[c]->p, chk->cols[c].data, bytes, cudaMemcpyHostToDevice, j->stream));
+    j->stats.h2d_bytes += bytes;
+    cs.has_nulls[c] = chk->cols[c].null_bitmap != nullptr;
+    if (cs.has_nulls[c]) {
+      size_t nb = (size_t)((n + 7) / 8);
+      TG_TRY(cs.nulls[c]->ensure(j->device, nb + 16));
+      TG_CUDA(cudaMemcpyAsync(cs.nulls[c]->p, chk->cols[c].null_bitmap, nb, cudaMemcpyHostToDevice, j->stream));
+      j->stats.h2d_bytes += nb;
+    }
+  }
+  return TG_OK;
+}
+
+// device chunk → device column store (device-to-device, appended)
+static int devchunk_append(tg_join* j, const tg_chunk* chk, const Side& s, ColStore& cs) {
+  if (chk->sel) return fail(TG_ERR_UNSUPPORTED, "device-resident chunks must not carry a sel vector");
+  int64_t n = chk->ncols ? chk->cols[0].length : 0;
+  if (n == 0) return TG_OK;
+  for (int c = 0; c < s.ncols; c++) {
+    if (!s.needed[c]) continue;
+    int el = s.elem[c];
+    TG_TRY(cs.data[c]->ensure_preserve(j->device, (size_t)(cs.rows + n) * el + 16, (size_t)cs.rows * el, j->stream));
+    TG_CUDA(cudaMemcpyAsync(cs.data[c]->as<uint8_t>() + (size_t)cs.rows * el, chk->cols[c].data, (size_t)n * el, cudaMemcpyDeviceToDevice, j->stream));
+    if (chk->cols[c].null_bitmap || cs.has_nulls[c]) {
+      if (cs.rows % 8 != 0) return fail(TG_ERR_UNSUPPORTED, "device-resident chunks with NULL bitmaps must start at a multiple of 8 rows");
+      size_t need = (size_t)((cs.rows + n + 7) / 8) + 16;
+      size_t had = (size_t)((cs.rows + 7) / 8);
+      TG_TRY(cs.nulls[c]->ensure_preserve(j->device, need, cs.has_nulls[c] ? had : 0, j->stream));
+      if (!cs.has_nulls[c]) { TG_CUDA(cudaMemsetAsync(cs.nulls[c]->p, 0xff, had, j->stream)); cs.has_nulls[c] = 1; }
+      if (chk->cols[c].null_bitmap) TG_CUDA(cudaMemcpyAsync(cs.nulls[c]->as<uint8_t>() + had, chk->cols[c].null_bitmap, (size_t)((n + 7) / 8), cudaMemcpyDeviceToDevice, j->stream));
+      else TG_CUDA(cudaMemsetAsync(cs.nulls[c]->as<uint8_t>() + had, 0xff, (size_t)((n + 7) / 8), j->stream));
+    }
+  }
+  cs.rows += n;
+  return TG_OK;
+}
+
+// borrow a device chunk as a column view (no copy)
+static int devchunk_view(const tg_chunk* chk, const Side& s, DevCols& v, int64_t* rows) {
+  if (!chk || chk->ncols != s.ncols) return fail(TG_ERR_INVALID, "chunk column count does not match the child schema");
+  if (chk->sel) return fail(TG_ERR_UNSUPPORTED, "device-resident chunks must not carry a sel vector");
+  std::memset(&v, 0, sizeof(v));
+  *rows = chk->ncols ? chk->cols[0].length : 0;
+  for (int c = 0; c < s.ncols; c++) {
+    v.elem_len[c] = s.elem[c];
+    if (!s.needed[c]) continue;
+    if (chk->cols[c].elem_len != s.elem[c]) return fail(TG_ERR_INVALID, "chunk column elem_len does not match the schema type");
+    if (chk->cols[c].length != *rows) return fail(TG_ERR_INVALID, "chunk columns have different lengths");
+    v.data[c] = chk->cols[c].data;
+    v.nulls[c] = chk->cols[c].null_bitmap;
+  }
+  return TG_OK;
+}
+
+// ---- build --------------------------------------------------------------------------------------------
+static int build_table(tg_join* j) {
+  const Side& b = j->build;
+  int64_t n = j->bcols.rows;
+  j->stats.build_rows = n;
+  DevCols bview = j->bcols.view(b);
+  KeySpec ks = j->build_key;
+  ks.data = bview.data[b.key_col]; ks.nulls = bview.nulls[b.key_col];
+  unsigned long long nslots = (unsigned long long)((double)(n > 0 ? n : 1) / j->load_factor) + 32;
+  if (nslots + 1 >= 0xFFFFFFFFull) return fail(TG_ERR_UNSUPPORTED, "build side too large for 32-bit slot ids");
+  TG_TRY(j->table.ensure(j->device, (size_t)(nslots + 1) * sizeof(Slot)));
+  TG_TRY(j->row_slot.ensure(j->device, (size_t)(n + 1) * 4));
+  TG_TRY(j->row_rank.ensure(j->device, (size_t)(n + 1) * 4));
+  TG_TRY(j->scalars.ensure(j->device, 64));
+  Slot* slots = j->table.as<Slot>();
+  unsigned long long* sc = j->scalars.as<unsigned long long>();   // [0] distinct [1] maxcnt [2] cursor
+  TG_CUDA(cudaEventRecord(j->ev0, j->stream));
+  TG_CUDA(cudaMemsetAsync(sc, 0, 64, j->stream));
+  k_table_init<<<grid_for(j, (int64_t)nslots + 1, 256, 8), 256, 0, j->stream>>>(slots, nslots + 1, nslots);
+  j->stats.kernel_launches++;
+  if (n > 0) {
+    k_build_insert<<<grid_for(j, n, 256, 8), 256, 0, j->stream>>>(ks, bview, b.filter, n, slots, nslots,
+                                                                  j->row_slot.as<uint32_t>(), j->row_rank.as<uint32_t>());
+    j->stats.kernel_launches++;
+  }
+  k_table_stats<<<grid_for(j, (int64_t)nslots + 1, 256, 8), 256, 0, j->stream>>>(slots, nslots + 1, sc, sc + 1);
+  j->stats.kernel_launches++;
+  unsigned long long host_sc[3] = {0, 0, 0};
+  TG_CUDA(cudaMemcpyAsync(host_sc, sc, 16, cudaMemcpyDeviceToHost, j->stream));
+  TG_CUDA(cudaStreamSynchronize(j->stream));
+  j->stats.distinct_keys = (int64_t)host_sc[0];
+  j->stats.max_dup = (int64_t)host_sc[1];
+  j->stats.table_slots = (int64_t)nslots;
+  if (host_sc[1] > kCntMask) return fail(TG_ERR_UNSUPPORTED, "a single join key repeats more than 2^28 times on the build side");
+
+  // choose the table mode.  U1: unique keys and the build side contributes at most its key (int64) and one
+  // 8-byte NOT NULL payload column, and no build-side scan is needed afterwards.
+  std::vector<int> payload;   // used build columns other than the key
+  bool key_out = false;
+  for (int c : b.used) { if (c == b.key_col) key_out = true; else if (std::find(payload.begin(), payload.end(), c) == payload.end()) payload.push_back(c); }
+  bool u1 = host_sc[1] <= 1 && !j->need_scan && payload.size() <= 1 && (!key_out || j->build_key.kind == KEY_I64);
+  if (u1 && payload.size() == 1) {
+    int pc = payload[0];
+    if (b.elem[pc] != 8 || j->bcols.has_nulls[pc]) u1 = false;
+  }
+  j->tv = TableView{slots, nslots, nullptr, 0, -1, TABLE_NONE, 0};
+  j->build_word_of_col.assign(b.ncols, -1);
+  if (u1) {
+    j->u1_payload_col = payload.empty() ? -1 : payload[0];
+    if (n > 0) {
+      const unsigned long long* pl = j->u1_payload_col >= 0 ? reinterpret_cast<const unsigned long long*>(bview.data[j->u1_payload_col]) : nullptr;
+      k_build_scatter_u1<<<grid_for(j, n, 256, 8), 256, 0, j->stream>>>(j->row_slot.as<uint32_t>(), pl, n, slots);
+      j->stats.kernel_launches++;
+    }
+    j->tv.mode = TABLE_U1;
+  } else {
+    RowSpec rs{};
+    int w = 0;
+    bool any_nullable = false;
+    std::vector<int> cols;
+    for (int c : b.used) if (std::find(cols.begin(), cols.end(), c) == cols.end()) cols.push_back(c);
+    if ((int)cols.size() + 1 > TG_MAX_COLS) return fail(TG_ERR_UNSUPPORTED, "too many build columns");
+    for (int c : cols) {
+      rs.col[w] = c; rs.elem_len[w] = b.elem[c];
+      rs.null_bit[w] = j->bcols.has_nulls[c] ? w : -1;
+      any_nullable |= j->bcols.has_nulls[c] != 0;
+      j->build_word_of_col[c] = w;
+      w++;
+    }
+    rs.null_word = any_nullable ? w : -1;
+    rs.nwords = w + (any_nullable ? 1 : 0);
+    if (rs.nwords == 0) rs.nwords = 1;   // semi joins: no payload at all, keep a dummy word so offsets stay valid
+    j->rowspec = rs;
+    k_table_assign<<<grid_for(j, (int64_t)nslots + 1, 256, 8), 256, 0, j->stream>>>(slots, nslots + 1, sc + 2);
+    j->stats.kernel_launches++;
+    TG_TRY(j->rows_store.ensure(j->device, (size_t)(n + 1) * rs.nwords * 8));
+    if (n > 0 && w > 0) {
+      k_build_scatter_rows<<<grid_for(j, n, 256, 8), 256, 0, j->stream>>>(j->row_slot.as<uint32_t>(), j->row_rank.as<uint32_t>(), n, slots,
+                                                                          bview, rs, j->rows_store.as<unsigned long long>());
+      j->stats.kernel_launches++;
+    }
+    j->tv.mode = TABLE_G;
+    j->tv.rows = j->rows_store.as<unsigned long long>();
+    j->tv.row_words = rs.nwords;
+    j->tv.null_word = rs.null_word;
+  }
+  if (j->need_scan) {
+    TG_TRY(j->slot_used.ensure(j->device, (size_t)nslots + 1));
+    TG_CUDA(cudaMemsetAsync(j->slot_used.p, 0, (size_t)nslots + 1, j->stream));
+  }
+  TG_CUDA(cudaEventRecord(j->ev1, j->stream));
+  TG_CUDA(cudaStreamSynchronize(j->stream));
+  TG_CUDA(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, j->ev0, j->ev1);
+  j->stats.build_ms = ms;
+  j->stats.table_mode = j->tv.mode;
+  // valid keys = rows that landed in the table
+  j->stats.build_valid_keys = -1;
+  j->built = true;
+  return TG_OK;
+}
+
+// ---- output plumbing -------------------------------------------------------------------------------------
+static int ensure_result(tg_join* j, ResultBatch& rb, int64_t cap_rows, bool preserve, int64_t used_rows) {
+  if ((int)rb.cols.size() != j->n_out) {
+    rb.cols.clear(); rb.bitmaps.clear();
+    for (int i = 0; i < j->n_out; i++) { rb.cols.emplace_back(new DevBuf()); rb.bitmaps.emplace_back(new DevBuf()); }
+  }
+  for (int c = 0; c < j->n_out; c++) {
+    size_t bytes = (size_t)(cap_rows + 8) * j->out_elem[c];
+    if (preserve) TG_TRY(rb.cols[c]->ensure_preserve(j->device, bytes, (size_t)used_rows * j->out_elem[c], j->stream));
+    else TG_TRY(rb.cols[c]->ensure(j->device, bytes));
+  }
+  return TG_OK;
+}
+
+// which output columns can carry NULLs for this probe batch
+static void out_nullable(const tg_join* j, const DevCols& pview, std::vector<char>& nullable) {
+  nullable.assign(j->n_out, 0);
+  bool probe_is_left = j->build_is_right;
+  int n_l = j->n_lused;
+  for (int o = 0; o < j->n_out; o++) {
+    if (j->has_flag_col && o == j->n_out - 1) { nullable[o] = 0; continue; }
+    bool from_left = o < n_l;
+    bool from_probe = from_left == probe_is_left;
+    int col = from_left ? j->lused[o] : j->rused[o - n_l];
+    if (from_probe) nullable[o] = pview.nulls[col] != nullptr || j->need_scan;   // scan phase NULL-pads the probe side
+    else nullable[o] = j->bcols.has_nulls[col] || j->probe_kind == PK_PROBE_OUTER;
+  }
+}
+
+static void fill_outspec_probe(const tg_join* j, OutCols& oc) {
+  bool probe_is_left = j->build_is_right;
+  int n_l = j->n_lused;
+  oc.n = j->n_out;
+  for (int o = 0; o < j->n_out; o++) {
+    OutSpec& sp = oc.spec[o];
+    sp.elem_len = j->out_elem[o];
+    sp.null_bit = -1;
+    if (j->has_flag_col && o == j->n_out - 1) { sp.src = SRC_FLAG; sp.idx = 0; continue; }
+    bool from_left = o < n_l;
+    int col = from_left ? j->lused[o] : j->rused[o - n_l];
+    if (from_left == probe_is_left) { sp.src = SRC_PROBE_COL; sp.idx = col; continue; }
+    if (j->tv.mode == TABLE_U1) { sp.src = col == j->build.key_col ? SRC_BUILD_KEY : SRC_BUILD_META; sp.idx = 0; }
+    else { sp.src = SRC_BUILD_WORD; sp.idx = j->build_word_of_col[col]; sp.null_bit = j->rowspec.null_bit[sp.idx]; }
+  }
+}
+
+static int scan_counts(tg_join* j, int64_t n, unsigned long long* total_out) {
+  int64_t nblocks = (n + TG_SCAN_BLOCK * TG_SCAN_ITEMS - 1) / (TG_SCAN_BLOCK * TG_SCAN_ITEMS);
+  TG_TRY(j->tmp_sums.ensure(j->device, (size_t)(nblocks + 2) * 8));
+  TG_TRY(j->tmp_off.ensure(j->device, (size_t)(n + 2) * 8));
+  k_scan_block_sums<<<(unsigned)nblocks, TG_SCAN_BLOCK, 0, j->stream>>>(j->tmp_cnt.as<uint32_t>(), n, j->tmp_sums.as<unsigned long long>());
+  k_scan_sums<<<1, 1024, 0, j->stream>>>(j->tmp_sums.as<unsigned long long>(), nblocks);
+  k_scan_write<<<(unsigned)nblocks, TG_SCAN_BLOCK, 0, j->stream>>>(j->tmp_cnt.as<uint32_t>(), n, j->tmp_sums.as<unsigned long long>(),
+                                                                  j->tmp_off.as<unsigned long long>());
+  j->stats.kernel_launches += 3;
+  TG_CUDA(cudaMemcpyAsync(total_out, j->tmp_sums.as<unsigned long long>() + nblocks, 8, cudaMemcpyDeviceToHost, j->stream));
+  TG_CUDA(cudaStreamSynchronize(j->stream));
+  return TG_OK;
+}
+
+// valid-byte streams → bitmaps for the nullable output columns
+static int finish_bitmaps(tg_join* j, ResultBatch& rb, const std::vector<char>& nullable) {
+  for (int c = 0; c < j->n_out; c++) {
+    if (!nullable[c]) { rb.bitmaps[c]->release(); continue; }
+    TG_TRY(rb.bitmaps[c]->ensure(j->device, (size_t)((rb.rows + 7) / 8) + 16));
+    if (rb.rows) {
+      k_pack_bitmap<<<grid_for(j, (rb.rows + 7) / 8, 256, 8), 256, 0, j->stream>>>(j->tmp_valid[c]->as<uint8_t>(), rb.rows, rb.bitmaps[c]->as<uint8_t>());
+      j->stats.kernel_launches++;
+    }
+  }
+  return TG_OK;
+}
+
+static bool fast_path_ok(const tg_join* j, const DevCols& pview) {
+  if (j->tv.mode != TABLE_U1 || j->probe_kind != PK_INNER || j->need_scan) return false;
+  if (j->probe.filter.n || j->probe_key.kind != KEY_I64 || j->probe_key.reject_negative) return false;
+  if (pview.nulls[j->probe.key_col]) return false;
+  for (int c : j->probe.used) if (j->probe.elem[c] != 8 || pview.nulls[c]) return false;
+  for (int e : j->out_elem) if (e != 8) return false;
+  return true;
+}
+
+// probe `n` device-resident rows; results are appended to rb (rb.rows advanced)
+static int probe_device(tg_join* j, const DevCols& pview, int64_t n, ResultBatch& rb, bool sync_count) {
+  const Side& p = j->probe;
+  j->stats.probe_rows += n;
+  KeySpec ks = j->probe_key;
+  ks.data = pview.data[p.key_col]; ks.nulls = pview.nulls[p.key_col];
+  TG_TRY(j->out_cursor.ensure(j->device, 64));
+  if (fast_path_ok(j, pview)) {
+    TG_TRY(ensure_result(j, rb, rb.rows + n, rb.rows > 0, rb.rows));
+    OutCols oc{};
+    fill_outspec_probe(j, oc);
+    for (int c = 0; c < j->n_out; c++) { oc.data[c] = rb.cols[c]->as<uint8_t>() + (size_t)rb.rows * 8; oc.valid[c] = nullptr; rb.bitmaps[c]->release(); }
+    unsigned long long* cur = j->out_cursor.as<unsigned long long>();
+    TG_CUDA(cudaMemsetAsync(cur, 0, 8, j->stream));
+    if (n > 0) {
+      constexpr int R = 4;
+      int64_t tiles = (n + 256 * R - 1) / (256 * R);
+      int grid = (int)std::min<int64_t>(tiles, (int64_t)j->nsm * 8);
+      k_probe_inner_u1<R><<<grid, 256, 0, j->stream>>>(reinterpret_cast<const int64_t*>(ks.data), pview, n, j->tv, oc, cur);
+      j->stats.kernel_launches++;
+    }
+    if (sync_count) {
+      unsigned long long got = 0;
+      TG_CUDA(cudaMemcpyAsync(&got, cur, 8, cudaMemcpyDeviceToHost, j->stream));
+      TG_CUDA(cudaStreamSynchronize(j->stream));
+      rb.rows += (int64_t)got;
+      j->stats.output_rows += (int64_t)got;
+    }
+    return TG_OK;
+  }
+  // general path, in sub-batches
+  std::vector<char> nullable;
+  out_nullable(j, pview, nullable);
+  if ((int)j->tmp_valid.size() != j->n_out) { j->tmp_valid.clear(); for (int i = 0; i < j->n_out; i++) j->tmp_valid.emplace_back(new DevBuf()); }
+  int64_t out_start = rb.rows;
+  // valid bytes are produced for the whole call, so size them after counting all sub-batches: run count+scan
+  // per sub-batch, remembering totals, then write.  Sub-batching keeps the temporaries bounded.
+  for (int64_t lo = 0; lo < n || (lo == 0 && n == 0); lo += kGeneralBatchRows) {
+    int64_t m = std::min<int64_t>(kGeneralBatchRows, n - lo);
+    if (m <= 0) break;
+    DevCols sub = pview;
+    if (lo) {
+      if (lo % 8) return fail(TG_ERR_CUDA, "internal: sub-batch offset not byte aligned");
+      for (int c = 0; c < p.ncols; c++) {
+        if (sub.data[c]) sub.data[c] = reinterpret_cast<const uint8_t*>(sub.data[c]) + (size_t)lo * p.elem[c];
+        if (sub.nulls[c]) sub.nulls[c] += lo / 8;
+      }
+    }
+    KeySpec sks = ks;
+    sks.data = sub.data[p.key_col]; sks.nulls = sub.nulls[p.key_col];
+    TG_TRY(j->tmp_cnt.ensure(j->device, (size_t)(m + 1) * 4));
+    TG_TRY(j->tmp_slot.ensure(j->device, (size_t)(m + 1) * 4));
+    k_probe_count<<<grid_for(j, m, 256, 8), 256, 0, j->stream>>>(sks, sub, p.filter, m, j->tv, j->probe_kind, j->tmp_cnt.as<uint32_t>(),
+                                                                 j->tmp_slot.as<uint32_t>(), j->need_scan ? j->slot_used.as<uint8_t>() : nullptr);
+    j->stats.kernel_launches++;
+    unsigned long long total = 0;
+    TG_TRY(scan_counts(j, m, &total));
+    if (total) {
+      TG_TRY(ensure_result(j, rb, rb.rows + (int64_t)total, true, rb.rows));
+      OutCols oc{};
+      fill_outspec_probe(j, oc);
+      for (int c = 0; c < j->n_out; c++) {
+        oc.data[c] = rb.cols[c]->p;
+        oc.valid[c] = nullptr;
+        if (nullable[c]) {
+          TG_TRY(j->tmp_valid[c]->ensure_preserve(j->device, (size_t)(rb.rows + total) + 16, (size_t)rb.rows, j->stream));
+          oc.valid[c] = j->tmp_valid[c]->as<uint8_t>();
+        }
+      }
+      k_probe_write<<<grid_for(j, m, 256, 8), 256, 0, j->stream>>>(m, j->tmp_off.as<unsigned long long>(), j->tmp_slot.as<uint32_t>(),
+                                                                   reinterpret_cast<const int64_t*>(sks.data), sks, j->tv, sub, oc, j->probe_kind,
+                                                                   (unsigned long long)rb.rows);
+      j->stats.kernel_launches++;
+      rb.rows += (int64_t)total;
+      j->stats.output_rows += (int64_t)total;
+    }
+  }
+  (void)out_start;
+  if ((int)rb.cols.size() != j->n_out) TG_TRY(ensure_result(j, rb, 8, false, 0));
+  TG_TRY(finish_bitmaps(j, rb, nullable));
+  TG_CUDA(cudaStreamSynchronize(j->stream));
+  TG_CUDA(cudaGetLastError());
+  return TG_OK;
+}
+
+// ScanRowTable after the probe side is exhausted (hash_join_v2.go:877)
+static int scan_build_side(tg_join* j, ResultBatch& rb) {
+  const Side& b = j->build;
+  int64_t n = j->bcols.rows;
+  if (n == 0) { if ((int)rb.cols.size() != j->n_out) TG_TRY(ensure_result(j, rb, 8, false, 0)); return TG_OK; }
+  DevCols bview = j->bcols.view(b);
+  TG_TRY(j->tmp_cnt.ensure(j->device, (size_t)(n + 1) * 4));
+  k_build_scan_count<<<grid_for(j, n, 256, 8), 256, 0, j->stream>>>(j->row_slot.as<uint32_t>(), j->slot_used.as<uint8_t>(), n, j->scan_mode, j->tmp_cnt.as<uint32_t>());
+  j->stats.kernel_launches++;
+  unsigned long long total = 0;
+  TG_TRY(scan_counts(j, n, &total));
+  std::vector<char> nullable(j->n_out, 0);
+  bool probe_is_left = j->build_is_right;
+  OutCols oc{};
+  oc.n = j->n_out;
+  if ((int)j->tmp_valid.size() != j->n_out) { j->tmp_valid.clear(); for (int i = 0; i < j->n_out; i++) j->tmp_valid.emplace_back(new DevBuf()); }
+  TG_TRY(ensure_result(j, rb, rb.rows + (int64_t)total, false, 0));
+  for (int o = 0; o < j->n_out; o++) {
+    bool from_left = o < j->n_lused;
+    int col = from_left ? j->lused[o] : j->rused[o - j->n_lused];
+    bool from_probe = from_left == probe_is_left;
+    oc.spec[o].elem_len = j->out_elem[o];
+    oc.spec[o].null_bit = -1;
+    oc.spec[o].src = from_probe ? SRC_PROBE_COL : SRC_BUILD_WORD;
+    oc.spec[o].idx = col;
+    nullable[o] = from_probe || j->bcols.has_nulls[col];
+    oc.data[o] = rb.cols[o]->p;
+    oc.valid[o] = nullptr;
+    if (nullable[o]) { TG_TRY(j->tmp_valid[o]->ensure(j->device, (size_t)total + 16)); oc.valid[o] = j->tmp_valid[o]->as<uint8_t>(); }
+  }
+  if (total) {
+    k_build_scan_write<<<grid_for(j, n, 256, 8), 256, 0, j->stream>>>(n, j->tmp_off.as<unsigned long long>(), bview, oc, 0ull);
+    j->stats.kernel_launches++;
+  }
+  rb.rows = (int64_t)total;
+  j->stats.output_rows += (int64_t)total;
+  TG_TRY(finish_bitmaps(j, rb, nullable));
+  TG_CUDA(cudaStreamSynchronize(j->stream));
+  TG_CUDA(cudaGetLastError());
+  return TG_OK;
+}
+
+static int flush_probe_stage(tg_join* j) {
+  if (j->pstage.rows == 0) return TG_OK;
+  TG_TRY(stage_to_device(j, j->pstage, j->probe, j->pcols_dev));
+  std::unique_ptr<ResultBatch> rb(new ResultBatch());
+  DevCols pview = j->pcols_dev.view(j->probe);
+  TG_CUDA(cudaEventRecord(j->ev0, j->stream));
+  TG_TRY(probe_device(j, pview, j->pstage.rows, *rb, true));
+  TG_CUDA(cudaEventRecord(j->ev1, j->stream));
+  TG_CUDA(cudaStreamSynchronize(j->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, j->ev0, j->ev1); j->stats.probe_ms += ms;
+  j->pstage.reset();
+  if (rb->rows > 0) j->results.push_back(std::move(rb));
+  return TG_OK;
+}
+
+}  // namespace tg
+
+// ---------------------------------------------------------------------------------------------------
+// C entry points
+// ---------------------------------------------------------------------------------------------------
+#define TG_LOCK(j)                                                             \
+  if (!(j)) return tg::fail(TG_ERR_INVALID, "handle is NULL");                 \
+  if ((j)->closed.load()) return tg::fail(TG_ERR_CANCELLED, "handle is closed"); \
+  std::lock_guard<std::mutex> lock__((j)->mu);                                 \
+  if ((j)->closed.load()) return tg::fail(TG_ERR_CANCELLED, "handle is closed"); \
+  tg::DeviceGuard guard__((j)->device);                                        \
+  if (!guard__.ok) return tg::fail(TG_ERR_CUDA, "cudaSetDevice failed (no usable CUDA device)")
+
+extern "C" {
+
+int tg_join_supported(const tg_join_desc* desc) {
+  tg_join tmp;
+  return setup(&tmp, desc);
+}
+
+int tg_join_open(const tg_join_desc* desc, tg_join** out) {
+  if (!out) return fail(TG_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  std::unique_ptr<tg_join> j(new tg_join());
+  TG_TRY(setup(j.get(), desc));
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(TG_ERR_CUDA, "no CUDA device: the GPU hash join has no CPU fallback"); }
+  if (j->device < 0 || j->device >= ndev) return fail(TG_ERR_INVALID, "device ordinal out of range");
+  DeviceGuard g(j->device);
+  if (!g.ok) return fail(TG_ERR_CUDA, "cudaSetDevice failed");
+  if (desc->stream) { j->stream = (cudaStream_t)desc->stream; j->own_stream = false; }
+  else { TG_CUDA(cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking)); j->own_stream = true; }
+  TG_CUDA(cudaEventCreate(&j->ev0));
+  TG_CUDA(cudaEventCreate(&j->ev1));
+  j->nsm = device_sm_count(j->device);
+  j->bstage.init(j->build.ncols); j->bcols.init(j->build.ncols);
+  j->pstage.init(j->probe.ncols); j->pcols_dev.init(j->probe.ncols);
+  *out = j.release();
+  return TG_OK;
+}
+
+int tg_join_build_push(tg_join* j, const tg_chunk* chk) {
+  TG_LOCK(j);
+  if (j->built) return fail(TG_ERR_STATE, "build_push after build_finish");
+  TG_TRY(validate_chunk(j->build, chk));
+  return stage_append(j->bstage, j->build, chk);
+}
+
+int tg_join_build_push_dev(tg_join* j, const tg_chunk* chk) {
+  TG_LOCK(j);
+  if (j->built) return fail(TG_ERR_STATE, "build_push after build_finish");
+  if (j->bstage.rows) return fail(TG_ERR_STATE, "host and device build pushes cannot be mixed");
+  TG_TRY(validate_chunk(j->build, chk));
+  return devchunk_append(j, chk, j->build, j->bcols);
+}
+
+int tg_join_build_finish(tg_join* j) {
+  TG_LOCK(j);
+  if (j->built) return fail(TG_ERR_STATE, "build_finish called twice");
+  if (j->bstage.rows) { TG_TRY(stage_to_device(j, j->bstage, j->build, j->bcols)); }
+  int rc = build_table(j);
+  // pinned staging of the build side is no longer needed
+  j->bstage.init(j->build.ncols);
+  return rc;
+}
+
+int tg_join_probe_push(tg_join* j, const tg_chunk* chk) {
+  TG_LOCK(j);
+  if (!j->built) return fail(TG_ERR_STATE, "probe_push before build_finish");
+  if (j->probe_finished) return fail(TG_ERR_STATE, "probe_push after probe_finish");
+  TG_TRY(validate_chunk(j->probe, chk));
+  int64_t n = chunk_logical_rows(chk);
+  if (n == 0) return TG_OK;
+  if (!chk->sel && n >= kDirectPushRows) {
+    TG_TRY(flush_probe_stage(j));
+    TG_TRY(chunk_to_device(j, chk, j->probe, j->pcols_dev));
+    std::unique_ptr<ResultBatch> rb(new ResultBatch());
+    DevCols pview = j->pcols_dev.view(j->probe);
+    TG_CUDA(cudaEventRecord(j->ev0, j->stream));
+    TG_TRY(probe_device(j, pview, n, *rb, true));
+    TG_CUDA(cudaEventRecord(j->ev1, j->stream));
+    TG_CUDA(cudaStreamSynchronize(j->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, j->ev0, j->ev1); j->stats.probe_ms += ms;
+    if (rb->rows > 0) j->results.push_back(std::move(rb));
+    return TG_OK;
+  }
+  TG_TRY(stage_append(j->pstage, j->probe, chk));
+  if (j->pstage.rows >= kStageBatchRows) TG_TRY(flush_probe_stage(j));
+  return TG_OK;
+}
+
+int tg_join_probe_finish(tg_join* j) {
+  TG_LOCK(j);
+  if (!j->built) return fail(TG_ERR_STATE, "probe_finish before build_finish");
+  if (j->probe_finished) return TG_OK;
+  TG_TRY(flush_probe_stage(j));
+  if (j->need_scan) {
+    std::unique_ptr<ResultBatch> rb(new ResultBatch());
+    TG_TRY(scan_build_side(j, *rb));
+    if (rb->rows > 0) j->results.push_back(std::move(rb));
+  }
+  j->probe_finished = true;
+  return TG_OK;
+}
+
+int tg_join_next(tg_join* j, tg_mut_chunk* out, int64_t max_rows, int64_t* nrows) {
+  TG_LOCK(j);
+  if (!out || !nrows) return fail(TG_ERR_INVALID, "out / nrows is NULL");
+  *nrows = 0;
+  if (out->ncols != j->n_out) return fail(TG_ERR_INVALID, "output chunk column count does not match the join schema");
+  for (int c = 0; c < j->n_out; c++) if (out->cols[c].elem_len != j->out_elem[c]) return fail(TG_ERR_INVALID, "output column elem_len mismatch");
+  while (!j->results.empty() && j->results.front()->consumed >= j->results.front()->rows) {
+    if (j->win_batch == j->results.front().get()) { j->win_batch = nullptr; j->win_lo = j->win_hi = 0; }
+    j->results.pop_front();
+  }
+  if (j->results.empty()) return TG_OK;   // EOF iff probe_finish was called, else "push more"
+  ResultBatch& rb = *j->results.front();
+  int64_t want = std::min<int64_t>(std::min<int64_t>(max_rows, out->capacity_rows), rb.rows - rb.consumed);
+  if (want <= 0) return TG_OK;
+  // bitmaps are bit-packed: serve whole bytes so that the caller's bitmap starts at bit 0
+  int64_t lo = rb.consumed;
+  bool has_bm = false;
+  for (int c = 0; c < j->n_out; c++) if (rb.bitmaps[c]->p) has_bm = true;
+  if (has_bm && (lo % 8)) return fail(TG_ERR_STATE, "internal: unaligned bitmap cursor");
+  if (has_bm && want < rb.rows - lo) want -= want % 8;   // keep the cursor byte aligned
+  if (want <= 0) return fail(TG_ERR_CAPACITY, "tg_join_next needs max_rows >= 8 when the result carries NULL bitmaps");
+  // row bytes of all columns, for the small-request window
+  size_t row_bytes = 0;
+  for (int c = 0; c < j->n_out; c++) row_bytes += j->out_elem[c];
+  if (want >= 64 * 1024) {
+    for (int c = 0; c < j->n_out; c++) {
+      size_t el = j->out_elem[c];
+      TG_CUDA(cudaMemcpyAsync(out->cols[c].data, rb.cols[c]->as<uint8_t>() + (size_t)lo * el, (size_t)want * el, cudaMemcpyDeviceToHost, j->stream));
+      j->stats.d2h_bytes += (int64_t)want * el;
+    }
+  } else {
+    // serve from a pinned window of up to kNextWindowRows rows fetched with one copy per column
+    if (j->win_batch != &rb || lo < j->win_lo || lo + want > j->win_hi) {
+      int64_t wn = std::min<int64_t>(kNextWindowRows, rb.rows - lo);
+      TG_TRY(j->win.reserve((size_t)wn * row_bytes));
+      size_t offb = 0;
+      for (int c = 0; c < j->n_out; c++) {
+        size_t el = j->out_elem[c];
+        TG_CUDA(cudaMemcpyAsync(j->win.p + offb, rb.cols[c]->as<uint8_t>() + (size_t)lo * el, (size_t)wn * el, cudaMemcpyDeviceToHost, j->stream));
+        j->stats.d2h_bytes += (int64_t)wn * el;
+        offb += (size_t)wn * el;
+      }
+      TG_CUDA(cudaStreamSynchronize(j->stream));
+      j->win_batch = &rb; j->win_lo = lo; j->win_hi = lo + wn;
+    }
+    int64_t wn = j->win_hi - j->win_lo;
+    size_t offb = 0;
+    for (int c = 0; c < j->n_out; c++) {
+      size_t el = j->out_elem[c];
+      std::memcpy(out->cols[c].data, j->win.p + offb + (size_t)(lo - j->win_lo) * el, (size_t)want * el);
+      offb += (size_t)wn * el;
+    }
+  }
+  for (int c = 0; c < j->n_out; c++) {
+    size_t nb = (size_t)((want + 7) / 8);
+    if (rb.bitmaps[c]->p) {
+      if (!out->cols[c].null_bitmap) return fail(TG_ERR_INVALID, "output column can be NULL but the caller passed no null bitmap");
+      TG_CUDA(cudaMemcpyAsync(out->cols[c].null_bitmap, rb.bitmaps[c]->as<uint8_t>() + lo / 8, nb, cudaMemcpyDeviceToHost, j->stream));
+      j->stats.d2h_bytes += nb;
+    } else if (out->cols[c].null_bitmap) {
+      std::memset(out->cols[c].null_bitmap, 0xff, nb);
+      if (want & 7) out->cols[c].null_bitmap[nb - 1] = (uint8_t)((1u << (want & 7)) - 1);
+    }
+  }
+  TG_CUDA(cudaStreamSynchronize(j->stream));
+  // mask the tail bits of copied bitmaps (Column.nullBitmap keeps unused bits zero)
+  if (want & 7) for (int c = 0; c < j->n_out; c++) if (rb.bitmaps[c]->p) out->cols[c].null_bitmap[(want >> 3)] &= (uint8_t)((1u << (want & 7)) - 1);
+  rb.consumed += want;
+  *nrows = want;
+  return TG_OK;
+}
+
+int tg_join_probe_dev(tg_join* j, const tg_chunk* dev_chk, int64_t* out_rows, void** out_cols, void** out_nulls) {
+  TG_LOCK(j);
+  if (!j->built) return fail(TG_ERR_STATE, "probe before build_finish");
+  DevCols pview; int64_t n = 0;
+  TG_TRY(devchunk_view(dev_chk, j->probe, pview, &n));
+  if (!j->dev_result) j->dev_result.reset(new ResultBatch());
+  ResultBatch& rb = *j->dev_result;
+  rb.rows = 0; rb.consumed = 0;
+  TG_CUDA(cudaEventRecord(j->ev0, j->stream));
+  TG_TRY(probe_device(j, pview, n, rb, out_rows != nullptr));
+  TG_CUDA(cudaEventRecord(j->ev1, j->stream));
+  if (out_rows) {
+    TG_CUDA(cudaStreamSynchronize(j->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, j->ev0, j->ev1); j->stats.probe_ms += ms;
+    *out_rows = rb.rows;
+  }
+  for (int c = 0; c < j->n_out; c++) {
+    if (out_cols) out_cols[c] = rb.cols[c]->p;
+    if (out_nulls) out_nulls[c] = rb.bitmaps[c]->p;
+  }
+  return TG_OK;
+}
+
+int tg_join_get_stats(tg_join* j, tg_join_stats* out) {
+  TG_LOCK(j);
+  if (!out) return fail(TG_ERR_INVALID, "out is NULL");
+  TG_CUDA(cudaStreamSynchronize(j->stream));
+  *out = j->stats;
+  return TG_OK;
+}
+
+int tg_join_close(tg_join* j) {
+  if (!j) return TG_OK;
+  bool was = j->closed.exchange(true);
+  if (was) return TG_OK;
+  {
+    std::lock_guard<std::mutex> lock(j->mu);   // waits for an in-flight call; later calls see `closed`
+    DeviceGuard g(j->device);
+    if (j->stream) cudaStreamSynchronize(j->stream);
+    j->results.clear();
+    j->dev_result.reset();
+    if (j->ev0) cudaEventDestroy(j->ev0);
+    if (j->ev1) cudaEventDestroy(j->ev1);
+    if (j->own_stream && j->stream) cudaStreamDestroy(j->stream);
+    cudaGetLastError();
+  }
+  delete j;
+  return TG_OK;
+}
+
+}  // extern "C"

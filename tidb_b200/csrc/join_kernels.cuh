@@ -1,0 +1,547 @@
+// join_kernels.cuh — hash-join build / probe kernels for sm_100a.
+//
+// What they replace in the reference (pkg/executor/join):
+//   build : rowTableBuilder.processOneChunk (row_table_builder.go:138) + subTable.build
+//           (hash_table_v2.go:107)                                   → k_table_init, k_build_insert,
+//                                                                      k_table_stats, k_table_assign,
+//                                                                      k_build_scatter_u1 / _rows
+//   probe : baseJoinProbe.SetChunkForProbe (base_join_probe.go:179) + innerJoinProbe.Probe
+//           (inner_join_probe.go:27) + append{Build,Probe}RowToChunkInternal (:589/:677)
+//                                                                    → k_probe_inner_u1 (fused fast path)
+//                                                                      k_probe_count / k_probe_write
+//
+// Data layout in HBM (B200-first, not the reference's chained row pointers):
+//   * open-addressing table of 16-byte slots {int64 key, u64 meta}, linear probing, one slot per
+//     DISTINCT key; any table size (multiply-high range reduction), one extra slot at index nslots
+//     for the key whose value equals the empty sentinel.
+//   * mode U1 (unique build keys, ≤1 eight-byte NOT NULL build payload): meta = payload.  A probe is ONE
+//     16-byte gather — no dependent pointer chase.
+//   * mode G  (anything else): meta = (offset << 28) | count into a row-major "row store" where the
+//     rows of one key are contiguous (count-then-place build, O(n) for any duplicate skew).
+#pragma once
+#include "common.cuh"
+
+namespace tg {
+
+struct __align__(16) Slot { int64_t key; unsigned long long meta; };
+
+static const uint32_t kInvalidSlot = 0xFFFFFFFFu;
+static const unsigned long long kCntMask = (1ull << 28) - 1;
+
+enum { TABLE_NONE = 0, TABLE_U1 = 1, TABLE_G = 2 };
+enum { KEY_I64 = 0, KEY_F64 = 1, KEY_F32 = 2 };
+enum { SRC_PROBE_COL = 0, SRC_BUILD_KEY = 1, SRC_BUILD_META = 2, SRC_BUILD_WORD = 3, SRC_FLAG = 4 };
+
+struct KeySpec {
+  const void* data;
+  const uint8_t* nulls;      // bitmap, nullptr = no NULLs
+  int32_t kind;              // KEY_*
+  int32_t reject_negative;   // mixed signed/unsigned key pair, this side is the signed one: a negative
+                             // value carries intFlag and can never match (codec.go:647-653)
+};
+
+struct TableView {
+  Slot* slots;
+  unsigned long long nslots;        // regular slots; slot[nslots] belongs to key == kEmptyKey
+  const unsigned long long* rows;   // row store (mode G)
+  int32_t row_words;
+  int32_t null_word;                // index of the per-row NULL mask word in the row store, -1 = none
+  int32_t mode;
+  int32_t pad;
+};
+
+#define TG_MAX_OUT 24
+struct OutSpec {
+  int32_t src;        // SRC_*
+  int32_t idx;        // probe column index | row-store word
+  int32_t elem_len;   // 4 or 8
+  int32_t null_bit;   // SRC_BUILD_WORD: bit in the null word, -1 = never NULL
+};
+struct OutCols {
+  int32_t n;
+  int32_t pad;
+  OutSpec spec[TG_MAX_OUT];
+  void* data[TG_MAX_OUT];
+  uint8_t* valid[TG_MAX_OUT];   // one byte per output row (1 = NOT NULL), nullptr when the column cannot be NULL
+};
+
+// row store build description
+struct RowSpec {
+  int32_t nwords;
+  int32_t null_word;            // -1 = none
+  int32_t col[TG_MAX_COLS];     // build column feeding word w
+  int32_t elem_len[TG_MAX_COLS];
+  int32_t null_bit[TG_MAX_COLS];
+};
+
+// join kinds as the probe kernels see them
+enum {
+  PK_INNER = 0,            // emit cnt rows per probe row (also outer join whose OUTER side is the build side)
+  PK_PROBE_OUTER = 1,      // emit max(cnt,1) rows, NULL-padded build side when unmatched
+  PK_SEMI = 2,             // probe is the left side: emit 1 row iff matched
+  PK_ANTI = 3,             // emit 1 row iff not matched
+  PK_LEFT_OUTER_SEMI = 4,  // emit 1 row + flag
+  PK_ANTI_LEFT_OUTER_SEMI = 5,
+  PK_MARK_ONLY = 6         // build is the left side of a semi/anti join: only mark used slots
+};
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool load_key(const KeySpec& ks, int64_t row, int64_t& k) {
+  if (ks.nulls && !bit_not_null(ks.nulls, row)) return false;
+  if (ks.kind == KEY_I64) {
+    k = reinterpret_cast<const int64_t*>(ks.data)[row];
+    if (ks.reject_negative && k < 0) return false;
+  } else {
+    double d = ks.kind == KEY_F64 ? reinterpret_cast<const double*>(ks.data)[row]
+                                  : (double)reinterpret_cast<const float*>(ks.data)[row];
+    if (d == 0) d = 0;   // -0 → +0 (codec.go:663-667, :676-682)
+    k = __double_as_longlong(d);
+  }
+  return true;
+}
+
+__device__ __forceinline__ Slot load_slot(const Slot* p) {
+  // one 128-bit gather
+  const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p);
+  Slot s; s.key = (int64_t)v.x; s.meta = v.y;
+  return s;
+}
+
+// lookup without insertion: returns slot index or kInvalidSlot; meta of the found slot in *meta
+__device__ __forceinline__ uint32_t table_find(const TableView& t, int64_t k, unsigned long long* meta) {
+  if (k == kEmptyKey) {
+    Slot s = load_slot(t.slots + t.nslots);
+    *meta = s.meta;
+    // the side slot is "occupied" iff a build row carried this key: mode U1 marks that in key
+    return s.key == 0 ? kInvalidSlot : (uint32_t)t.nslots;
+  }
+  unsigned long long s = slot_of(mix64((uint64_t)k), t.nslots);
+  for (;;) {
+    Slot v = load_slot(t.slots + s);
+    if (v.key == k) { *meta = v.meta; return (uint32_t)s; }
+    if (v.key == kEmptyKey) return kInvalidSlot;
+    if (++s == t.nslots) s = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// build
+// ---------------------------------------------------------------------------------------------
+__global__ void k_table_init(Slot* slots, unsigned long long n_total, unsigned long long nslots) {
+  unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (; i < n_total; i += stride) {
+    Slot s; s.key = (i == nslots) ? 0 : kEmptyKey; s.meta = 0;   // side slot: key field = occupied flag
+    *reinterpret_cast<ulonglong2*>(slots + i) = make_ulonglong2((unsigned long long)s.key, 0ull);
+  }
+}
+
+// pass 1: claim one slot per distinct key, count multiplicities, remember (slot, rank) per build row
+__global__ void __launch_bounds__(256)
+k_build_insert(KeySpec key, DevCols cols, DevFilter filt, int64_t n, Slot* slots, unsigned long long nslots,
+               uint32_t* __restrict__ row_slot, uint32_t* __restrict__ row_rank) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    int64_t k;
+    bool valid = load_key(key, i, k);
+    if (valid && filt.n) valid = eval_filter(filt, cols, i);
+    if (!valid) { row_slot[i] = kInvalidSlot; row_rank[i] = 0; continue; }
+    unsigned long long s;
+    if (k == kEmptyKey) {
+      s = nslots;
+      slots[s].key = 1;   // occupied flag (benign race: every writer stores 1)
+    } else {
+      s = slot_of(mix64((uint64_t)k), nslots);
+      for (;;) {
+        int64_t cur = *reinterpret_cast<volatile int64_t*>(&slots[s].key);
+        if (cur == k) break;
+        if (cur == kEmptyKey) {
+          unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&slots[s].key),
+                                             (unsigned long long)kEmptyKey, (unsigned long long)k);
+          if (old == (unsigned long long)kEmptyKey || old == (unsigned long long)k) break;
+        }
+        if (++s == nslots) s = 0;
+      }
+    }
+    unsigned long long rank = atomicAdd(&slots[s].meta, 1ull);
+    row_slot[i] = (uint32_t)s;
+    row_rank[i] = (uint32_t)rank;
+  }
+}
+
+// pass 2: distinct keys, largest multiplicity
+__global__ void k_table_stats(const Slot* slots, unsigned long long n_total, unsigned long long* distinct,
+                              unsigned long long* maxcnt) {
+  unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  unsigned long long d = 0, m = 0;
+  for (; i < n_total; i += stride) {
+    unsigned long long c = slots[i].meta;
+    d += c != 0;
+    m = c > m ? c : m;
+  }
+  for (int o = 16; o; o >>= 1) {
+    d += __shfl_xor_sync(0xffffffffu, d, o);
+    unsigned long long mo = __shfl_xor_sync(0xffffffffu, m, o);
+    m = mo > m ? mo : m;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (d) atomicAdd(distinct, d);
+    if (m) atomicMax(maxcnt, m);
+  }
+}
+
+// pass 3 (mode G): give every occupied slot a contiguous range of the row store
+__global__ void k_table_assign(Slot* slots, unsigned long long n_total, unsigned long long* cursor) {
+  unsigned long long base = blockIdx.x * (unsigned long long)blockDim.x;
+  unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  for (; base < n_total; base += stride) {   // warp-uniform trip count
+    unsigned long long i = base + threadIdx.x;
+    unsigned long long c = i < n_total ? slots[i].meta : 0;
+    unsigned long long incl = c;
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned long long wbase = 0;
+    if (lane == 31 && total) wbase = atomicAdd(cursor, total);
+    wbase = __shfl_sync(0xffffffffu, wbase, 31);
+    if (c) slots[i].meta = ((wbase + incl - c) << 28) | c;
+  }
+}
+
+// pass 4a (mode U1): meta = the single payload of the key
+__global__ void k_build_scatter_u1(const uint32_t* __restrict__ row_slot, const unsigned long long* __restrict__ payload,
+                                   int64_t n, Slot* slots) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    uint32_t s = row_slot[i];
+    if (s != kInvalidSlot) slots[s].meta = payload ? payload[i] : 0ull;
+  }
+}
+
+// pass 4b (mode G): column → row conversion into the key-grouped row store
+__global__ void k_build_scatter_rows(const uint32_t* __restrict__ row_slot, const uint32_t* __restrict__ row_rank,
+                                     int64_t n, const Slot* slots, DevCols cols, RowSpec rs,
+                                     unsigned long long* __restrict__ rows) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    uint32_t s = row_slot[i];
+    if (s == kInvalidSlot) continue;
+    unsigned long long pos = (slots[s].meta >> 28) + row_rank[i];
+    unsigned long long* dst = rows + pos * rs.nwords;
+    unsigned long long nullmask = 0;
+    int nw = rs.null_word >= 0 ? rs.nwords - 1 : rs.nwords;
+    for (int w = 0; w < nw; w++) {
+      int c = rs.col[w];
+      unsigned long long v;
+      if (rs.elem_len[w] == 8) v = reinterpret_cast<const unsigned long long*>(cols.data[c])[i];
+      else v = reinterpret_cast<const uint32_t*>(cols.data[c])[i];
+      if (rs.null_bit[w] >= 0 && cols.nulls[c] && !bit_not_null(cols.nulls[c], i)) nullmask |= 1ull << rs.null_bit[w];
+      dst[w] = v;
+    }
+    if (rs.null_word >= 0) dst[rs.null_word] = nullmask;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// probe — fused fast path: unique build keys (mode U1), inner join, NOT NULL 8-byte columns.
+// One pass: stream probe key (+ payload columns) with coalesced loads, one 16-byte gather per row,
+// warp-ballot compaction, one atomicAdd per CTA tile for the output cursor, coalesced column stores.
+// ---------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(256)
+k_probe_inner_u1(const int64_t* __restrict__ pkey, DevCols pcols, int64_t n, TableView t, OutCols out,
+                 unsigned long long* __restrict__ out_cursor) {
+  constexpr int BLOCK = 256;
+  constexpr int WARPS = BLOCK / 32;
+  __shared__ uint32_t s_warp_cnt[R][WARPS];
+  __shared__ unsigned long long s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t tile_rows = (int64_t)BLOCK * R;
+  const int64_t ntiles = (n + tile_rows - 1) / tile_rows;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t base = tile * tile_rows;
+    int64_t k[R];
+    Slot v[R];
+    bool m[R];
+    // issue all R independent key loads, then all R independent gathers (memory-level parallelism)
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+      int64_t i = base + (int64_t)j * BLOCK + threadIdx.x;
+      k[j] = i < n ? __ldcs(pkey + i) : kEmptyKey;
+    }
+    unsigned long long s[R];
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+      s[j] = (k[j] == kEmptyKey) ? t.nslots : slot_of(mix64((uint64_t)k[j]), t.nslots);
+      v[j] = load_slot(t.slots + s[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+      int64_t i = base + (int64_t)j * BLOCK + threadIdx.x;
+      bool in = i < n;
+      if (k[j] == kEmptyKey) {
+        m[j] = in && v[j].key != 0;
+      } else {
+        // linear probing tail: rare at the configured load factor
+        while (v[j].key != k[j] && v[j].key != kEmptyKey) {
+          if (++s[j] == t.nslots) s[j] = 0;
+          v[j] = load_slot(t.slots + s[j]);
+        }
+        m[j] = v[j].key == k[j];
+      }
+    }
+    // compaction: position of each match inside the tile
+    uint32_t pre[R];
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+      unsigned b = __ballot_sync(0xffffffffu, m[j]);
+      pre[j] = __popc(b & ((1u << lane) - 1));
+      if (lane == 0) s_warp_cnt[j][warp] = __popc(b);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t run = 0;
+#pragma unroll
+      for (int j = 0; j < R; j++)
+        for (int w = 0; w < WARPS; w++) { uint32_t c = s_warp_cnt[j][w]; s_warp_cnt[j][w] = run; run += c; }
+      s_base = run ? atomicAdd(out_cursor, (unsigned long long)run) : 0ull;
+    }
+    __syncthreads();
+    const unsigned long long obase = s_base;
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+      if (!m[j]) continue;
+      int64_t i = base + (int64_t)j * BLOCK + threadIdx.x;
+      unsigned long long o = obase + s_warp_cnt[j][warp] + pre[j];
+      for (int c = 0; c < out.n; c++) {
+        const OutSpec sp = out.spec[c];
+        unsigned long long val;
+        if (sp.src == SRC_PROBE_COL) val = __ldcs(reinterpret_cast<const unsigned long long*>(pcols.data[sp.idx]) + i);
+        else if (sp.src == SRC_BUILD_KEY) val = (unsigned long long)k[j];
+        else val = v[j].meta;
+        __stcs(reinterpret_cast<unsigned long long*>(out.data[c]) + o, val);
+      }
+    }
+    __syncthreads();   // s_warp_cnt / s_base are reused by the next tile
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// probe — general path (any join type, NULLs, filters, duplicates): count → scan → write
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_probe_count(KeySpec key, DevCols pcols, DevFilter filt, int64_t n, TableView t, int kind,
+              uint32_t* __restrict__ row_cnt, uint32_t* __restrict__ row_slot, uint8_t* slot_used) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    int64_t k;
+    bool valid = load_key(key, i, k);
+    if (valid && filt.n) valid = eval_filter(filt, pcols, i);
+    uint32_t s = kInvalidSlot;
+    unsigned long long meta = 0;
+    if (valid) s = table_find(t, k, &meta);
+    uint32_t cnt = 0;
+    if (s != kInvalidSlot) cnt = t.mode == TABLE_U1 ? 1u : (uint32_t)(meta & kCntMask);
+    bool matched = cnt > 0;
+    if (slot_used && matched) slot_used[s] = 1;
+    uint32_t c;
+    switch (kind) {
+      case PK_INNER: c = cnt; break;
+      case PK_PROBE_OUTER: c = matched ? cnt : 1u; break;
+      case PK_SEMI: c = matched ? 1u : 0u; break;
+      case PK_ANTI: c = matched ? 0u : 1u; break;
+      case PK_LEFT_OUTER_SEMI: case PK_ANTI_LEFT_OUTER_SEMI: c = 1u; break;
+      default: c = 0u; break;
+    }
+    row_cnt[i] = c;
+    row_slot[i] = matched ? s : kInvalidSlot;
+  }
+}
+
+// exclusive scan of u32 counts into u64 offsets (n+1 entries): block sums → scan of sums → rescan
+#define TG_SCAN_BLOCK 256
+#define TG_SCAN_ITEMS 8
+__global__ void __launch_bounds__(TG_SCAN_BLOCK)
+k_scan_block_sums(const uint32_t* __restrict__ in, int64_t n, unsigned long long* __restrict__ block_sums) {
+  __shared__ unsigned long long s[TG_SCAN_BLOCK / 32];
+  int64_t base = (int64_t)blockIdx.x * TG_SCAN_BLOCK * TG_SCAN_ITEMS;
+  unsigned long long sum = 0;
+#pragma unroll
+  for (int j = 0; j < TG_SCAN_ITEMS; j++) {
+    int64_t i = base + (int64_t)j * TG_SCAN_BLOCK + threadIdx.x;
+    if (i < n) sum += in[i];
+  }
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long tot = 0;
+    for (int w = 0; w < TG_SCAN_BLOCK / 32; w++) tot += s[w];
+    block_sums[blockIdx.x] = tot;
+  }
+}
+// single block: exclusive scan of block_sums in place; total written to block_sums[nblocks]
+__global__ void __launch_bounds__(1024) k_scan_sums(unsigned long long* block_sums, int64_t nblocks) {
+  __shared__ unsigned long long s_warp[32];
+  __shared__ unsigned long long s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t base = 0; base < nblocks; base += 1024) {
+    int64_t i = base + threadIdx.x;
+    unsigned long long v = i < nblocks ? block_sums[i] : 0, incl = v;
+    for (int o = 1; o < 32; o <<= 1) { unsigned long long u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned long long w = s_warp[lane], wi = w;
+      for (int o = 1; o < 32; o <<= 1) { unsigned long long u = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += u; }
+      s_warp[lane] = wi - w;
+    }
+    __syncthreads();
+    unsigned long long carry = s_carry;
+    if (i < nblocks) block_sums[i] = carry + s_warp[warp] + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = carry + s_warp[31] + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) block_sums[nblocks] = s_carry;
+}
+__global__ void __launch_bounds__(TG_SCAN_BLOCK)
+k_scan_write(const uint32_t* __restrict__ in, int64_t n, const unsigned long long* __restrict__ block_sums,
+             unsigned long long* __restrict__ out_off) {
+  // thread t owns TG_SCAN_ITEMS consecutive elements → serial scan per thread + block scan of thread sums
+  __shared__ unsigned long long s_warp[TG_SCAN_BLOCK / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int64_t base = (int64_t)blockIdx.x * TG_SCAN_BLOCK * TG_SCAN_ITEMS + (int64_t)threadIdx.x * TG_SCAN_ITEMS;
+  uint32_t v[TG_SCAN_ITEMS];
+  unsigned long long tsum = 0;
+#pragma unroll
+  for (int j = 0; j < TG_SCAN_ITEMS; j++) { v[j] = (base + j) < n ? in[base + j] : 0u; tsum += v[j]; }
+  unsigned long long incl = tsum;
+  for (int o = 1; o < 32; o <<= 1) { unsigned long long u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  unsigned long long wpre = 0;
+  for (int w = 0; w < warp; w++) wpre += s_warp[w];
+  unsigned long long run = block_sums[blockIdx.x] + wpre + incl - tsum;
+#pragma unroll
+  for (int j = 0; j < TG_SCAN_ITEMS; j++) { if (base + j < n) out_off[base + j] = run; run += v[j]; }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out_off[n] = block_sums[gridDim.x];
+}
+
+__device__ __forceinline__ void store_out(const OutCols& out, int c, unsigned long long o, unsigned long long val, bool not_null) {
+  if (out.spec[c].elem_len == 8) reinterpret_cast<unsigned long long*>(out.data[c])[o] = not_null ? val : 0ull;
+  else reinterpret_cast<uint32_t*>(out.data[c])[o] = not_null ? (uint32_t)val : 0u;
+  if (out.valid[c]) out.valid[c][o] = not_null ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_probe_write(int64_t n, const unsigned long long* __restrict__ off, const uint32_t* __restrict__ row_slot,
+              const int64_t* __restrict__ pkey_i64, KeySpec key, TableView t, DevCols pcols, OutCols out, int kind,
+              unsigned long long out_base) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    unsigned long long o0 = off[i], c = off[i + 1] - o0;
+    if (c == 0) continue;
+    o0 += out_base;
+    uint32_t s = row_slot[i];
+    bool matched = s != kInvalidSlot;
+    unsigned long long meta = matched ? t.slots[s].meta : 0ull;
+    unsigned long long roff = meta >> 28;
+    int64_t k = 0;
+    if (matched) load_key(key, i, k);
+    for (unsigned long long r = 0; r < c; r++) {
+      unsigned long long o = o0 + r;
+      const unsigned long long* brow = (matched && t.mode == TABLE_G) ? t.rows + (roff + r) * t.row_words : nullptr;
+      for (int cc = 0; cc < out.n; cc++) {
+        const OutSpec sp = out.spec[cc];
+        unsigned long long val = 0;
+        bool nn = true;
+        switch (sp.src) {
+          case SRC_PROBE_COL: {
+            const uint8_t* nb = pcols.nulls[sp.idx];
+            nn = !(nb && !bit_not_null(nb, i));
+            if (sp.elem_len == 8) val = reinterpret_cast<const unsigned long long*>(pcols.data[sp.idx])[i];
+            else val = reinterpret_cast<const uint32_t*>(pcols.data[sp.idx])[i];
+            break;
+          }
+          case SRC_BUILD_KEY: nn = matched; val = (unsigned long long)k; break;
+          case SRC_BUILD_META: nn = matched; val = meta; break;
+          case SRC_BUILD_WORD:
+            nn = matched;
+            if (matched) {
+              val = brow[sp.idx];
+              if (sp.null_bit >= 0 && ((brow[t.null_word] >> sp.null_bit) & 1ull)) nn = false;
+            }
+            break;
+          default:   // SRC_FLAG: LeftOuterSemi 1/0, AntiLeftOuterSemi 0/1
+            val = (kind == PK_ANTI_LEFT_OUTER_SEMI) ? (matched ? 0ull : 1ull) : (matched ? 1ull : 0ull);
+            break;
+        }
+        store_out(out, cc, o, val, nn);
+      }
+    }
+  }
+}
+
+// ScanRowTable (outer_join_probe.go:117, semi_join_probe.go:72): rows of the BUILD side that are
+// (un)matched, taken from the device-resident build columns; probe-side output columns become NULL.
+//   mode 0: emit build rows whose key was never matched (outer join, anti semi) — invalid-key rows included
+//   mode 1: emit build rows whose key was matched (semi join)
+__global__ void __launch_bounds__(256)
+k_build_scan_count(const uint32_t* __restrict__ row_slot, const uint8_t* __restrict__ slot_used, int64_t n, int mode,
+                   uint32_t* __restrict__ row_cnt) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    uint32_t s = row_slot[i];
+    bool used = s != kInvalidSlot && slot_used[s];
+    row_cnt[i] = (mode == 0 ? !used : used) ? 1u : 0u;
+  }
+}
+// OutSpec.src here: SRC_BUILD_WORD.idx = build column index (read from the columns), SRC_PROBE_COL → NULL
+__global__ void __launch_bounds__(256)
+k_build_scan_write(int64_t n, const unsigned long long* __restrict__ off, DevCols bcols, OutCols out,
+                   unsigned long long out_base) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    if (off[i + 1] == off[i]) continue;
+    unsigned long long o = out_base + off[i];
+    for (int cc = 0; cc < out.n; cc++) {
+      const OutSpec sp = out.spec[cc];
+      if (sp.src == SRC_PROBE_COL) { store_out(out, cc, o, 0, false); continue; }
+      const uint8_t* nb = bcols.nulls[sp.idx];
+      bool nn = !(nb && !bit_not_null(nb, i));
+      unsigned long long val = sp.elem_len == 8 ? reinterpret_cast<const unsigned long long*>(bcols.data[sp.idx])[i]
+                                                : reinterpret_cast<const uint32_t*>(bcols.data[sp.idx])[i];
+      store_out(out, cc, o, val, nn);
+    }
+  }
+}
+
+// valid bytes (1 = NOT NULL) → Column.nullBitmap bits
+__global__ void k_pack_bitmap(const uint8_t* __restrict__ valid, int64_t n, uint8_t* __restrict__ bitmap) {
+  int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t nbytes = (n + 7) / 8;
+  for (; b < nbytes; b += stride) {
+    uint8_t v = 0;
+    for (int j = 0; j < 8; j++) { int64_t r = b * 8 + j; if (r < n && valid[r]) v |= (uint8_t)(1u << j); }
+    bitmap[b] = v;
+  }
+}
+
+}  // namespace tg
