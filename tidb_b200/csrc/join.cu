@@ -121,6 +121,8 @@ struct tg_join {
 
 namespace tg {
 
+static int env_int(const char* name, int dflt) { const char* v = getenv(name); return (v && *v) ? atoi(v) : dflt; }
+
 static int grid_for(const tg_join* j, int64_t n, int block, int per_sm) {
   int64_t need = (n + block - 1) / block;
   int64_t cap = (int64_t)j->nsm * per_sm;
@@ -392,6 +394,8 @@ static int build_table(tg_join* j) {
   KeySpec ks = j->build_key;
   ks.data = bview.data[b.key_col]; ks.nulls = bview.nulls[b.key_col];
   unsigned long long nslots = (unsigned long long)((double)(n > 0 ? n : 1) / j->load_factor) + 32;
+  nslots &= ~1ull;   // even: slots are addressed as 32-byte pairs
+  const int pair_home = env_int("TG_PAIR_HOME", 1);
   if (nslots + 1 >= 0xFFFFFFFFull) return fail(TG_ERR_UNSUPPORTED, "build side too large for 32-bit slot ids");
   TG_TRY(j->table.ensure(j->device, (size_t)(nslots + 1) * sizeof(Slot)));
   TG_TRY(j->row_slot.ensure(j->device, (size_t)(n + 1) * 4));
@@ -404,7 +408,7 @@ static int build_table(tg_join* j) {
   k_table_init<<<grid_for(j, (int64_t)nslots + 1, 256, 8), 256, 0, j->stream>>>(slots, nslots + 1, nslots);
   j->stats.kernel_launches++;
   if (n > 0) {
-    k_build_insert<<<grid_for(j, n, 256, 8), 256, 0, j->stream>>>(ks, bview, b.filter, n, slots, nslots,
+    k_build_insert<<<grid_for(j, n, 256, 8), 256, 0, j->stream>>>(ks, bview, b.filter, n, slots, nslots, pair_home,
                                                                   j->row_slot.as<uint32_t>(), j->row_rank.as<uint32_t>());
     j->stats.kernel_launches++;
   }
@@ -428,7 +432,7 @@ static int build_table(tg_join* j) {
     int pc = payload[0];
     if (b.elem[pc] != 8 || j->bcols.has_nulls[pc]) u1 = false;
   }
-  j->tv = TableView{slots, nslots, nullptr, 0, -1, TABLE_NONE, 0};
+  j->tv = TableView{slots, nslots, nullptr, 0, -1, TABLE_NONE, pair_home};
   j->build_word_of_col.assign(b.ncols, -1);
   if (u1) {
     j->u1_payload_col = payload.empty() ? -1 : payload[0];
@@ -568,6 +572,70 @@ static bool fast_path_ok(const tg_join* j, const DevCols& pview) {
   return true;
 }
 
+// ---- fast-path launch tuning (env overrides are for A/B sweeps on the GPU box; defaults are the measured best) ----
+struct ProbeTuning { int variant; int R; int evict_last; int ctas_per_sm; };
+static ProbeTuning probe_tuning() {
+  ProbeTuning t;
+  t.variant = env_int("TG_PROBE_VARIANT", 1);      // 0: CTA-tile kernel (shared-memory offsets), 1: warp-autonomous kernel
+  t.R = env_int("TG_PROBE_R", 4);
+  t.evict_last = env_int("TG_PROBE_EVICT_LAST", 0);
+  t.ctas_per_sm = env_int("TG_PROBE_CTAS_PER_SM", 8);
+  if (t.ctas_per_sm < 1) t.ctas_per_sm = 1;
+  return t;
+}
+
+// classify the output columns of the fused fast path by the register that feeds them
+static bool build_fast_out(const tg_join* j, const OutCols& oc, const DevCols& pview, FastOut& fo) {
+  std::memset(&fo, 0, sizeof(fo));
+  int pcol_of[TG_FAST_MAX_PCOLS];
+  for (int c = 0; c < oc.n; c++) {
+    const OutSpec& sp = oc.spec[c];
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(oc.data[c]);
+    if (sp.src == SRC_BUILD_KEY || (sp.src == SRC_PROBE_COL && sp.idx == j->probe.key_col)) {
+      if (fo.n_key_dst >= 4) return false;
+      fo.key_dst[fo.n_key_dst++] = dst;
+    } else if (sp.src == SRC_BUILD_META) {
+      if (fo.n_meta_dst >= 2) return false;
+      fo.meta_dst[fo.n_meta_dst++] = dst;
+    } else if (sp.src == SRC_PROBE_COL) {
+      int k = -1;
+      for (int q = 0; q < fo.n_pcols; q++) if (pcol_of[q] == sp.idx) k = q;
+      if (k < 0) {
+        if (fo.n_pcols >= TG_FAST_MAX_PCOLS) return false;
+        k = fo.n_pcols++;
+        pcol_of[k] = sp.idx;
+        fo.psrc[k] = reinterpret_cast<const unsigned long long*>(pview.data[sp.idx]);
+      }
+      if (fo.n_pdst[k] >= 2) return false;
+      fo.pdst[k][fo.n_pdst[k]++] = dst;
+    } else return false;
+  }
+  return true;
+}
+
+template <int R, int NPC>
+static void launch_probe_warp_el(tg_join* j, const int64_t* pkey, int64_t n, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t) {
+  int64_t tiles = (n + 32 * R - 1) / (32 * R);
+  int64_t ctas = (tiles + 7) / 8;
+  int grid = (int)std::min<int64_t>(ctas, (int64_t)j->nsm * t.ctas_per_sm);
+  if (t.evict_last) k_probe_inner_u1_w<R, NPC, true><<<grid, 256, 0, j->stream>>>(pkey, n, j->tv, fo, cur);
+  else k_probe_inner_u1_w<R, NPC, false><<<grid, 256, 0, j->stream>>>(pkey, n, j->tv, fo, cur);
+}
+template <int R>
+static void launch_probe_warp_r(tg_join* j, const int64_t* pkey, int64_t n, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t) {
+  switch (fo.n_pcols) {
+    case 0: launch_probe_warp_el<R, 0>(j, pkey, n, fo, cur, t); break;
+    case 1: launch_probe_warp_el<R, 1>(j, pkey, n, fo, cur, t); break;
+    case 2: launch_probe_warp_el<R, 2>(j, pkey, n, fo, cur, t); break;
+    default: launch_probe_warp_el<R, 3>(j, pkey, n, fo, cur, t); break;
+  }
+}
+static void launch_probe_warp(tg_join* j, const int64_t* pkey, int64_t n, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t) {
+  if (t.R >= 8) launch_probe_warp_r<8>(j, pkey, n, fo, cur, t);
+  else if (t.R <= 2) launch_probe_warp_r<2>(j, pkey, n, fo, cur, t);
+  else launch_probe_warp_r<4>(j, pkey, n, fo, cur, t);
+}
+
 // probe `n` device-resident rows; results are appended to rb (rb.rows advanced)
 static int probe_device(tg_join* j, const DevCols& pview, int64_t n, ResultBatch& rb, bool sync_count) {
   const Side& p = j->probe;
@@ -583,10 +651,17 @@ static int probe_device(tg_join* j, const DevCols& pview, int64_t n, ResultBatch
     unsigned long long* cur = j->out_cursor.as<unsigned long long>();
     TG_CUDA(cudaMemsetAsync(cur, 0, 8, j->stream));
     if (n > 0) {
-      constexpr int R = 4;
-      int64_t tiles = (n + 256 * R - 1) / (256 * R);
-      int grid = (int)std::min<int64_t>(tiles, (int64_t)j->nsm * 8);
-      k_probe_inner_u1<R><<<grid, 256, 0, j->stream>>>(reinterpret_cast<const int64_t*>(ks.data), pview, n, j->tv, oc, cur);
+      const ProbeTuning& tune = probe_tuning();
+      FastOut fo{};
+      bool warp_ok = tune.variant != 0 && build_fast_out(j, oc, pview, fo);
+      if (warp_ok) {
+        launch_probe_warp(j, reinterpret_cast<const int64_t*>(ks.data), n, fo, cur, tune);
+      } else {
+        constexpr int R = 4;
+        int64_t tiles = (n + 256 * R - 1) / (256 * R);
+        int grid = (int)std::min<int64_t>(tiles, (int64_t)j->nsm * tune.ctas_per_sm);
+        k_probe_inner_u1<R><<<grid, 256, 0, j->stream>>>(reinterpret_cast<const int64_t*>(ks.data), pview, n, j->tv, oc, cur);
+      }
       j->stats.kernel_launches++;
     }
     if (sync_count) {
@@ -745,6 +820,12 @@ int tg_join_open(const tg_join_desc* desc, tg_join** out) {
   TG_CUDA(cudaEventCreate(&j->ev0));
   TG_CUDA(cudaEventCreate(&j->ev1));
   j->nsm = device_sm_count(j->device);
+  {
+    // Random 16-byte gathers: cap the L2 fetch granularity at one 32-byte sector.  With the default, a miss pulls
+    // ~3 sectors from HBM (ncu, profiles/r1_probe_first.md: 12.3 GB read for 6.4 GB algorithmic).
+    int gran = env_int("TG_L2_FETCH", 32);
+    if (gran == 32 || gran == 64 || gran == 128) { if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran) != cudaSuccess) cudaGetLastError(); }
+  }
   j->bstage.init(j->build.ncols); j->bcols.init(j->build.ncols);
   j->pstage.init(j->probe.ncols); j->pcols_dev.init(j->probe.ncols);
   *out = j.release();

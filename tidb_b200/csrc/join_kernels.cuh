@@ -47,8 +47,14 @@ struct TableView {
   int32_t row_words;
   int32_t null_word;                // index of the per-row NULL mask word in the row store, -1 = none
   int32_t mode;
-  int32_t pad;
+  int32_t pair_home;                // 1: a key's home is the even slot of a 32-byte pair, so that a displacement by
+                                    // one slot stays inside the DRAM/L2 sector fetched by the first gather
 };
+
+// home slot of a hash value
+__device__ __forceinline__ unsigned long long home_slot(unsigned long long h, unsigned long long nslots, int pair_home) {
+  return pair_home ? (slot_of(h, nslots >> 1) << 1) : slot_of(h, nslots);
+}
 
 #define TG_MAX_OUT 24
 struct OutSpec {
@@ -117,7 +123,7 @@ __device__ __forceinline__ uint32_t table_find(const TableView& t, int64_t k, un
     // the side slot is "occupied" iff a build row carried this key: mode U1 marks that in key
     return s.key == 0 ? kInvalidSlot : (uint32_t)t.nslots;
   }
-  unsigned long long s = slot_of(mix64((uint64_t)k), t.nslots);
+  unsigned long long s = home_slot(mix64((uint64_t)k), t.nslots, t.pair_home);
   for (;;) {
     Slot v = load_slot(t.slots + s);
     if (v.key == k) { *meta = v.meta; return (uint32_t)s; }
@@ -140,7 +146,7 @@ __global__ void k_table_init(Slot* slots, unsigned long long n_total, unsigned l
 
 // pass 1: claim one slot per distinct key, count multiplicities, remember (slot, rank) per build row
 __global__ void __launch_bounds__(256)
-k_build_insert(KeySpec key, DevCols cols, DevFilter filt, int64_t n, Slot* slots, unsigned long long nslots,
+k_build_insert(KeySpec key, DevCols cols, DevFilter filt, int64_t n, Slot* slots, unsigned long long nslots, int pair_home,
                uint32_t* __restrict__ row_slot, uint32_t* __restrict__ row_rank) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -154,7 +160,7 @@ k_build_insert(KeySpec key, DevCols cols, DevFilter filt, int64_t n, Slot* slots
       s = nslots;
       slots[s].key = 1;   // occupied flag (benign race: every writer stores 1)
     } else {
-      s = slot_of(mix64((uint64_t)k), nslots);
+      s = home_slot(mix64((uint64_t)k), nslots, pair_home);
       for (;;) {
         int64_t cur = *reinterpret_cast<volatile int64_t*>(&slots[s].key);
         if (cur == k) break;
@@ -281,7 +287,7 @@ k_probe_inner_u1(const int64_t* __restrict__ pkey, DevCols pcols, int64_t n, Tab
     unsigned long long s[R];
 #pragma unroll
     for (int j = 0; j < R; j++) {
-      s[j] = (k[j] == kEmptyKey) ? t.nslots : slot_of(mix64((uint64_t)k[j]), t.nslots);
+      s[j] = (k[j] == kEmptyKey) ? t.nslots : home_slot(mix64((uint64_t)k[j]), t.nslots, t.pair_home);
       v[j] = load_slot(t.slots + s[j]);
     }
 #pragma unroll
@@ -332,6 +338,102 @@ k_probe_inner_u1(const int64_t* __restrict__ pkey, DevCols pcols, int64_t n, Tab
       }
     }
     __syncthreads();   // s_warp_cnt / s_base are reused by the next tile
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// probe — fused fast path, warp-autonomous variant: no shared memory, no block barrier.  Each warp owns
+// tiles of 32×R rows: R coalesced key loads, the probe payload columns prefetched into registers, R
+// independent 16-byte gathers, ballot compaction, ONE atomicAdd per warp tile, coalesced column stores.
+// ---------------------------------------------------------------------------------------------
+#define TG_FAST_MAX_PCOLS 3
+struct FastOut {
+  int32_t n_pcols;                                  // distinct probe payload columns copied to the output
+  int32_t n_key_dst, n_meta_dst, pad;
+  const unsigned long long* psrc[TG_FAST_MAX_PCOLS];
+  int32_t n_pdst[TG_FAST_MAX_PCOLS]; int32_t pad2;
+  unsigned long long* pdst[TG_FAST_MAX_PCOLS][2];
+  unsigned long long* key_dst[4];                   // outputs that carry the join key (probe key and/or build key)
+  unsigned long long* meta_dst[2];                  // outputs that carry the build payload
+};
+
+__device__ __forceinline__ unsigned long long policy_evict_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ Slot load_slot_policy(const Slot* p, unsigned long long pol) {
+  unsigned long long x, y;
+  asm volatile("ld.global.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(x), "=l"(y) : "l"(p), "l"(pol));
+  Slot s; s.key = (int64_t)x; s.meta = y;
+  return s;
+}
+
+template <int R, int NPC, bool EVICT_LAST>
+__global__ void __launch_bounds__(256)
+k_probe_inner_u1_w(const int64_t* __restrict__ pkey, int64_t n, TableView t, FastOut out,
+                   unsigned long long* __restrict__ out_cursor) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t tile_rows = 32 * R;
+  const int64_t ntiles = (n + tile_rows - 1) / tile_rows;
+  unsigned long long pol = 0;
+  if (EVICT_LAST) pol = policy_evict_last();
+  for (int64_t tile = warp_id; tile < ntiles; tile += warps_total) {
+    const int64_t base = tile * tile_rows;
+    int64_t k[R];
+    unsigned long long pv[R][NPC > 0 ? NPC : 1];
+    Slot v[R];
+    unsigned long long s[R];
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+      int64_t i = base + j * 32 + lane;
+      k[j] = i < n ? __ldcs(pkey + i) : kEmptyKey;
+    }
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+      s[j] = (k[j] == kEmptyKey) ? t.nslots : home_slot(mix64((uint64_t)k[j]), t.nslots, t.pair_home);
+      v[j] = EVICT_LAST ? load_slot_policy(t.slots + s[j], pol) : load_slot(t.slots + s[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+      int64_t i = base + j * 32 + lane;
+#pragma unroll
+      for (int c = 0; c < NPC; c++) pv[j][c] = i < n ? __ldcs(out.psrc[c] + i) : 0ull;
+    }
+    unsigned bal[R];
+    uint32_t total = 0;
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+      int64_t i = base + j * 32 + lane;
+      bool m;
+      if (k[j] == kEmptyKey) m = (i < n) && v[j].key != 0;
+      else {
+        while (v[j].key != k[j] && v[j].key != kEmptyKey) {
+          if (++s[j] == t.nslots) s[j] = 0;
+          v[j] = load_slot(t.slots + s[j]);
+        }
+        m = v[j].key == k[j];
+      }
+      bal[j] = __ballot_sync(0xffffffffu, m);
+      total += __popc(bal[j]);
+    }
+    unsigned long long wbase = 0;
+    if (lane == 0 && total) wbase = atomicAdd(out_cursor, (unsigned long long)total);
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+      if ((bal[j] >> lane) & 1u) {
+        unsigned long long o = wbase + __popc(bal[j] & ((1u << lane) - 1));
+        for (int d = 0; d < out.n_key_dst; d++) __stcs(out.key_dst[d] + o, (unsigned long long)k[j]);
+        for (int d = 0; d < out.n_meta_dst; d++) __stcs(out.meta_dst[d] + o, v[j].meta);
+#pragma unroll
+        for (int c = 0; c < NPC; c++)
+          for (int d = 0; d < out.n_pdst[c]; d++) __stcs(out.pdst[c][d] + o, pv[j][c]);
+      }
+      wbase += __popc(bal[j]);
+    }
   }
 }
 

@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""A/B sweep of the fused probe kernel's launch parameters on one B200 (config 2 shape).
+Each line of gpurun_out/sweep_probe.jsonl is one (table layout, kernel variant) point, timed with CUDA events
+over `--steps` launches after 2 warm-ups.  Not a bench: use bench.py for reported numbers."""
+import argparse, itertools, json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from bench import gen_local, make_plan
+from tidb_b200.device import DeviceJoin
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--build-rows", type=int, default=10_000_000)
+ap.add_argument("--probe-rows", type=int, default=100_000_000)
+ap.add_argument("--steps", type=int, default=5)
+ap.add_argument("--lf", default="0.5")
+ap.add_argument("--pair", default="1")
+ap.add_argument("--l2", default="32")
+ap.add_argument("--variant", default="0,1")
+ap.add_argument("--R", default="4")
+ap.add_argument("--evict", default="0")
+ap.add_argument("--ctas", default="8")
+ap.add_argument("--out", default="gpurun_out/sweep_probe.jsonl")
+a = ap.parse_args()
+L = lambda s, f: [f(x) for x in s.split(",")]
+dev = torch.device("cuda", 0)
+stream = torch.cuda.Stream(device=dev)
+with torch.cuda.stream(stream):
+    bk, bv, pk, pv = gen_local(torch, dev, 0, 1, a.build_rows, a.probe_rows)
+stream.synchronize()
+os.makedirs(os.path.dirname(a.out), exist_ok=True)
+fout = open(a.out, "a")
+for lf, pair, l2 in itertools.product(L(a.lf, float), L(a.pair, int), L(a.l2, int)):
+    os.environ["TG_PAIR_HOME"] = str(pair); os.environ["TG_L2_FETCH"] = str(l2)
+    plan = make_plan(0, stream.cuda_stream); plan.load_factor = lf
+    j = DeviceJoin(plan)
+    with torch.cuda.stream(stream):
+        j.build([bk, bv])
+    bs = j.stats()
+    for variant, R, ev, ctas in itertools.product(L(a.variant, int), L(a.R, int), L(a.evict, int), L(a.ctas, int)):
+        if variant == 0 and (R != L(a.R, int)[0] or ev != L(a.evict, int)[0]):
+            continue
+        os.environ.update(TG_PROBE_VARIANT=str(variant), TG_PROBE_R=str(R), TG_PROBE_EVICT_LAST=str(ev), TG_PROBE_CTAS_PER_SM=str(ctas))
+        with torch.cuda.stream(stream):
+            rows, _, _ = j.probe([pk, pv], sync=True)
+            assert rows == a.probe_rows, rows
+            j.probe([pk, pv], sync=False)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(a.steps):
+                j.probe([pk, pv], sync=False)
+            e1.record(stream)
+        stream.synchronize()
+        ms = e0.elapsed_time(e1) / a.steps
+        rec = dict(lf=lf, pair=pair, l2=l2, variant=variant, R=R, evict_last=ev, ctas=ctas, ms=ms, grows=a.probe_rows / ms / 1e6,
+                   frac=64 * a.probe_rows / (ms * 1e-3) / 1e9 / 6575.1, slots=bs.table_slots, build_ms=bs.build_ms)
+        print(json.dumps(rec)); fout.write(json.dumps(rec) + "\n"); fout.flush()
+    j.close()
