@@ -205,3 +205,32 @@ def test_partial_match_and_stats():
     n, ocols = O.OracleJoin(plan, 8).run([build], probe.split(1 << 16))
     got = [np.concatenate([c.columns[i].data for c in chunks]) for i in range(4)]
     assert np.array_equal(columns_sorted(ocols), columns_sorted([(g, np.zeros(len(g), dtype=bool)) for g in got]))
+
+
+@pytest.mark.parametrize("env", [dict(TG_PROBE_TMA="1", TG_PROBE_PARTITION="1"), dict(TG_PROBE_TMA="0", TG_PROBE_PARTITION="1"),
+                                 dict(TG_PROBE_TMA="1", TG_PROBE_PARTITION="0"), dict(TG_PROBE_VARIANT="0")])
+def test_fused_probe_variants_forced(env, monkeypatch):
+    # every launch variant of the fused fast path (TMA-fed ring, L2 partition pass, warp kernel, CTA-tile kernel) must
+    # give the same multiset; odd sizes exercise the tail tiles; PART_MIN_MB=0 forces the partition pass on a small table
+    for k, v in dict(env, TG_PROBE_PART_MIN_MB="0").items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(17)
+    nb, npr = 300_001, 2_500_003
+    bk = rng.permutation(nb).astype(np.int64) * 2654435761 - (1 << 40)
+    bk[5] = -(1 << 63)                       # the sentinel-valued key
+    build = Chunk([Column(bk), Column(np.arange(nb, dtype=np.int64) * 3)])
+    pick = rng.integers(0, int(nb * 1.25), npr)
+    pk = np.where(pick < nb, bk[np.minimum(pick, nb - 1)], pick.astype(np.int64) * 7 + 1)   # ~80 % match
+    probe = Chunk([Column(pk), Column(np.arange(npr, dtype=np.int64))])
+    plan = JoinPlan(abi.JOIN_INNER, [INT_NN, INT_NN], [INT_NN, INT_NN], [0], [0])
+    e = HashJoinExec(plan, MockDataSource(plan.left_types, [probe]), MockDataSource(plan.right_types, [build]))
+    chunks = drain(e, 1 << 22)
+    got = [np.concatenate([c.columns[i].data for c in chunks]) for i in range(4)]
+    order = np.argsort(bk); sb = bk[order]
+    pos = np.searchsorted(sb, pk); pos[pos >= nb] = nb - 1
+    hit = sb[pos] == pk
+    assert len(got[0]) == int(hit.sum())
+    assert np.array_equal(np.sort(got[1]), np.nonzero(hit)[0])                       # each matching probe row exactly once
+    assert np.array_equal(got[0], pk[got[1]]) and np.array_equal(got[2], got[0])     # keys travel with their row
+    exp_pay = (order[pos] * 3)[got[1]]
+    assert np.array_equal(got[3], exp_pay)                                           # and with the right build payload

@@ -5,6 +5,7 @@
 #include <deque>
 #include <algorithm>
 #include "join_kernels.cuh"
+#include "partition_kernels.cuh"
 
 namespace tg {
 
@@ -107,6 +108,8 @@ struct tg_join {
   HostStage pstage;
   ColStore pcols_dev;
   DevBuf tmp_cnt, tmp_slot, tmp_off, tmp_sums, out_cursor;
+  DevBuf part_scratch;                               // counts | cursors | offsets of the L2 partition pass
+  std::unique_ptr<DevBuf> part_cols[1 + TG_FAST_MAX_PCOLS];   // partitioned copies of the probe key and payload columns
   std::vector<std::unique_ptr<DevBuf>> tmp_valid;
   std::deque<std::unique_ptr<ResultBatch>> results;
   std::unique_ptr<ResultBatch> dev_result;      // tg_join_probe_dev output (reused across calls)
@@ -573,7 +576,7 @@ static bool fast_path_ok(const tg_join* j, const DevCols& pview) {
 }
 
 // ---- fast-path launch tuning (env overrides are for A/B sweeps on the GPU box; defaults are the measured best) ----
-struct ProbeTuning { int variant; int R; int evict_last; int ctas_per_sm; };
+struct ProbeTuning { int variant; int R; int evict_last; int ctas_per_sm; int partition; int parts; int part_min_mb; int tma; int stages; int tma_ctas; };
 static ProbeTuning probe_tuning() {
   ProbeTuning t;
   t.variant = env_int("TG_PROBE_VARIANT", 1);      // 0: CTA-tile kernel (shared-memory offsets), 1: warp-autonomous kernel
@@ -581,6 +584,12 @@ static ProbeTuning probe_tuning() {
   t.evict_last = env_int("TG_PROBE_EVICT_LAST", 0);
   t.ctas_per_sm = env_int("TG_PROBE_CTAS_PER_SM", 8);
   if (t.ctas_per_sm < 1) t.ctas_per_sm = 1;
+  t.partition = env_int("TG_PROBE_PARTITION", 1);   // split big probes into L2-sized partitions first
+  t.parts = env_int("TG_PROBE_PARTS", 0);           // 0 = auto: table slices of <= 32 MB
+  t.part_min_mb = env_int("TG_PROBE_PART_MIN_MB", 64);
+  t.tma = env_int("TG_PROBE_TMA", 1);               // TMA-fed kernels (cp.async.bulk ring) for the streamed inputs
+  t.stages = env_int("TG_PROBE_STAGES", 4);
+  t.tma_ctas = env_int("TG_PROBE_TMA_CTAS", 3);
   return t;
 }
 
@@ -611,6 +620,57 @@ static bool build_fast_out(const tg_join* j, const OutCols& oc, const DevCols& p
     } else return false;
   }
   return true;
+}
+
+template <int NPC, int STAGES>
+static int launch_probe_tma_s(tg_join* j, const int64_t* pkey, int64_t ntiles, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t) {
+  size_t smem = (size_t)STAGES * (1 + NPC) * TG_PROBE_TILE * 8 + STAGES * 8 + 16;
+  int grid = (int)std::min<int64_t>(ntiles, (int64_t)j->nsm * t.tma_ctas);
+  if (t.evict_last) {
+    TG_CUDA(cudaFuncSetAttribute(k_probe_inner_u1_tma<NPC, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_probe_inner_u1_tma<NPC, STAGES, true><<<grid, 256, smem, j->stream>>>(pkey, ntiles, j->tv, fo, cur);
+  } else {
+    TG_CUDA(cudaFuncSetAttribute(k_probe_inner_u1_tma<NPC, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_probe_inner_u1_tma<NPC, STAGES, false><<<grid, 256, smem, j->stream>>>(pkey, ntiles, j->tv, fo, cur);
+  }
+  return TG_OK;
+}
+template <int NPC>
+static int launch_probe_tma_n(tg_join* j, const int64_t* pkey, int64_t ntiles, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t) {
+  if (t.stages <= 2) return launch_probe_tma_s<NPC, 2>(j, pkey, ntiles, fo, cur, t);
+  if (t.stages == 3) return launch_probe_tma_s<NPC, 3>(j, pkey, ntiles, fo, cur, t);
+  if (t.stages >= 6 && NPC <= 1) return launch_probe_tma_s<NPC, 6>(j, pkey, ntiles, fo, cur, t);
+  return launch_probe_tma_s<NPC, 4>(j, pkey, ntiles, fo, cur, t);
+}
+static int launch_probe_tma(tg_join* j, const int64_t* pkey, int64_t ntiles, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t) {
+  switch (fo.n_pcols) {
+    case 0: return launch_probe_tma_n<0>(j, pkey, ntiles, fo, cur, t);
+    case 1: return launch_probe_tma_n<1>(j, pkey, ntiles, fo, cur, t);
+    case 2: return launch_probe_tma_n<2>(j, pkey, ntiles, fo, cur, t);
+    default: return launch_probe_tma_n<3>(j, pkey, ntiles, fo, cur, t);
+  }
+}
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// L2 partition pass with the TMA-fed scatter: full 2048-row tiles by k_partition_scatter_tma, tail by k_partition_scatter
+template <int NC>
+static int launch_scatter_tma(tg_join* j, int64_t n, PartDst& d, unsigned long long* cursors) {
+  int64_t ntiles = n / PT_TILE;
+  if (ntiles > 0) {
+    size_t smem = (size_t)2 * NC * PT_TILE * 8 + PT_TILE * 8 + 2 * 8 + 16;
+    TG_CUDA(cudaFuncSetAttribute(k_partition_scatter_tma<true, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = (int)std::min<int64_t>(ntiles, (int64_t)j->nsm * 2);
+    k_partition_scatter_tma<true, NC><<<grid, PT_BLOCK, smem, j->stream>>>(ntiles, d, cursors);
+    j->stats.kernel_launches++;
+  }
+  int64_t done = ntiles * PT_TILE;
+  if (done < n) {
+    PartDst tail = d;
+    for (int c = 0; c < NC; c++) tail.src[c] = reinterpret_cast<const unsigned long long*>(d.src[c]) + done;
+    k_partition_scatter<true><<<1, PT_BLOCK, 0, j->stream>>>(reinterpret_cast<const long long*>(tail.src[0]), nullptr, n - done, tail, cursors);
+    j->stats.kernel_launches++;
+  }
+  return TG_OK;
 }
 
 template <int R, int NPC>
@@ -655,7 +715,67 @@ static int probe_device(tg_join* j, const DevCols& pview, int64_t n, ResultBatch
       FastOut fo{};
       bool warp_ok = tune.variant != 0 && build_fast_out(j, oc, pview, fo);
       if (warp_ok) {
-        launch_probe_warp(j, reinterpret_cast<const int64_t*>(ks.data), n, fo, cur, tune);
+        const int64_t* pkey = reinterpret_cast<const int64_t*>(ks.data);
+        size_t table_bytes = (size_t)j->tv.nslots * sizeof(Slot);
+        if (tune.partition && n >= (1ll << 20) && table_bytes > ((size_t)tune.part_min_mb << 20)) {
+          // L2 partition pass: regroup the probe rows by the TOP hash bits.  slot = mulhi(hash, nslots) is monotone
+          // in the hash, so partition p only touches the contiguous table slice [p/P, (p+1)/P) — 20-32 MB that stay
+          // L2 resident while the fused probe kernel sweeps the partition.  Trades 32 B/row of extra streaming
+          // traffic for ~100 B/row of random HBM traffic (ncu: profiles/r1_probe_first.md).
+          int P = tune.parts > 0 ? tune.parts : (int)((table_bytes + (32u << 20) - 1) / (32u << 20));
+          if (P > TG_MAX_PARTS) P = TG_MAX_PARTS;
+          if (P >= 2) {
+            int nc = 1 + fo.n_pcols;
+            for (int c = 0; c < nc; c++) {
+              if (!j->part_cols[c]) j->part_cols[c].reset(new DevBuf());
+              TG_TRY(j->part_cols[c]->ensure(j->device, (size_t)n * 8 + 64));
+            }
+            TG_TRY(j->part_scratch.ensure(j->device, (size_t)TG_MAX_PARTS * 8 * 3 + 64));
+            unsigned long long* counts = j->part_scratch.as<unsigned long long>();
+            unsigned long long* cursors = counts + TG_MAX_PARTS;
+            long long* offs = reinterpret_cast<long long*>(cursors + TG_MAX_PARTS);
+            TG_CUDA(cudaMemsetAsync(counts, 0, (size_t)TG_MAX_PARTS * 8 * 3 + 8, j->stream));
+            const long long* k64 = reinterpret_cast<const long long*>(pkey);
+            if (tune.tma && aligned16(k64)) k_partition_count4<true><<<grid_for(j, (n + 7) / 8, 256, 8), 256, 0, j->stream>>>(k64, n, (uint32_t)P, counts);
+            else k_partition_count<true><<<grid_for(j, n, 256, 8), 256, 0, j->stream>>>(k64, nullptr, n, (uint32_t)P, counts);
+            k_partition_offsets<<<1, 32, 0, j->stream>>>(counts, (uint32_t)P, offs, cursors);
+            PartDst d{};
+            d.nparts = P; d.ncols = nc;
+            d.src[0] = pkey;
+            for (int c = 0; c < fo.n_pcols; c++) d.src[1 + c] = fo.psrc[c];
+            for (int c = 0; c < nc; c++) for (int q = 0; q < P; q++) d.dst[q][c] = j->part_cols[c]->p;
+            d.dst_base = offs;
+            bool src_aligned = true;
+            for (int c = 0; c < nc; c++) src_aligned = src_aligned && aligned16(d.src[c]);
+            if (tune.tma && src_aligned) {
+              switch (nc) {
+                case 1: TG_TRY(launch_scatter_tma<1>(j, n, d, cursors)); break;
+                case 2: TG_TRY(launch_scatter_tma<2>(j, n, d, cursors)); break;
+                case 3: TG_TRY(launch_scatter_tma<3>(j, n, d, cursors)); break;
+                default: TG_TRY(launch_scatter_tma<4>(j, n, d, cursors)); break;
+              }
+              j->stats.kernel_launches += 2;
+            } else {
+              int64_t tiles = (n + PT_TILE - 1) / PT_TILE;
+              int pg = (int)std::min<int64_t>(tiles, (int64_t)j->nsm * 4);
+              k_partition_scatter<true><<<pg, PT_BLOCK, 0, j->stream>>>(k64, nullptr, n, d, cursors);
+              j->stats.kernel_launches += 3;
+            }
+            pkey = j->part_cols[0]->as<int64_t>();
+            for (int c = 0; c < fo.n_pcols; c++) fo.psrc[c] = j->part_cols[1 + c]->as<unsigned long long>();
+          }
+        }
+        bool tma_ok = tune.tma && aligned16(pkey);
+        for (int c = 0; c < fo.n_pcols; c++) tma_ok = tma_ok && aligned16(fo.psrc[c]);
+        int64_t full_tiles = tma_ok ? n / TG_PROBE_TILE : 0;
+        if (full_tiles > 0) TG_TRY(launch_probe_tma(j, pkey, full_tiles, fo, cur, tune));
+        int64_t done = full_tiles * TG_PROBE_TILE;
+        if (done < n) {
+          FastOut tail = fo;
+          for (int c = 0; c < fo.n_pcols; c++) tail.psrc[c] = fo.psrc[c] + done;
+          launch_probe_warp(j, pkey + done, n - done, tail, cur, tune);
+          if (full_tiles > 0) j->stats.kernel_launches++;
+        }
       } else {
         constexpr int R = 4;
         int64_t tiles = (n + 256 * R - 1) / (256 * R);
@@ -821,9 +941,10 @@ int tg_join_open(const tg_join_desc* desc, tg_join** out) {
   TG_CUDA(cudaEventCreate(&j->ev1));
   j->nsm = device_sm_count(j->device);
   {
-    // Random 16-byte gathers: cap the L2 fetch granularity at one 32-byte sector.  With the default, a miss pulls
-    // ~3 sectors from HBM (ncu, profiles/r1_probe_first.md: 12.3 GB read for 6.4 GB algorithmic).
-    int gran = env_int("TG_L2_FETCH", 32);
+    // L2 fetch granularity (cudaLimitMaxL2FetchGranularity): left at the device default.  Measured (tools/sweep_probe.py,
+    // profiles/r1_sweep.md): capping it at 32 B cuts the HBM bytes of the random gathers but makes the unpartitioned probe
+    // SLOWER (the gathers are bound by DRAM access rate, not bytes); TG_L2_FETCH={32,64,128} overrides for experiments.
+    int gran = env_int("TG_L2_FETCH", 0);
     if (gran == 32 || gran == 64 || gran == 128) { if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran) != cudaSuccess) cudaGetLastError(); }
   }
   j->bstage.init(j->build.ncols); j->bcols.init(j->build.ncols);

@@ -20,6 +20,7 @@
 //     rows of one key are contiguous (count-then-place build, O(n) for any duplicate skew).
 #pragma once
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace tg {
 
@@ -413,6 +414,98 @@ k_probe_inner_u1_w(const int64_t* __restrict__ pkey, int64_t n, TableView t, Fas
         while (v[j].key != k[j] && v[j].key != kEmptyKey) {
           if (++s[j] == t.nslots) s[j] = 0;
           v[j] = load_slot(t.slots + s[j]);
+        }
+        m = v[j].key == k[j];
+      }
+      bal[j] = __ballot_sync(0xffffffffu, m);
+      total += __popc(bal[j]);
+    }
+    unsigned long long wbase = 0;
+    if (lane == 0 && total) wbase = atomicAdd(out_cursor, (unsigned long long)total);
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+      if ((bal[j] >> lane) & 1u) {
+        unsigned long long o = wbase + __popc(bal[j] & ((1u << lane) - 1));
+        for (int d = 0; d < out.n_key_dst; d++) __stcs(out.key_dst[d] + o, (unsigned long long)k[j]);
+        for (int d = 0; d < out.n_meta_dst; d++) __stcs(out.meta_dst[d] + o, v[j].meta);
+#pragma unroll
+        for (int c = 0; c < NPC; c++)
+          for (int d = 0; d < out.n_pdst[c]; d++) __stcs(out.pdst[c][d] + o, pv[j][c]);
+      }
+      wbase += __popc(bal[j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// probe — fused fast path, TMA-fed: the streamed inputs (probe key + payload columns) arrive in shared memory
+// through a STAGES-deep ring of 1024-row tiles filled by cp.async.bulk (one elected thread, mbarrier completion),
+// so the only LSU traffic left is the random 16-byte table gathers and the output stores.  Full tiles only; the
+// tail (< 1024 rows) is finished by k_probe_inner_u1_w on the same output cursor.
+// ---------------------------------------------------------------------------------------------
+#define TG_PROBE_TILE 1024
+template <int NPC, int STAGES, bool EVICT_LAST>
+__global__ void __launch_bounds__(256)
+k_probe_inner_u1_tma(const int64_t* __restrict__ pkey, int64_t ntiles, TableView t, FastOut out,
+                     unsigned long long* __restrict__ out_cursor) {
+  constexpr int T = TG_PROBE_TILE, R = T / 256, COLS = 1 + NPC;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned long long* ring = reinterpret_cast<unsigned long long*>(smem_raw);          // [STAGES][COLS][T]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * COLS * T * 8);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const unsigned long long pol_stream = l2_policy_evict_first();
+  unsigned long long pol_table = 0;
+  if (EVICT_LAST) pol_table = l2_policy_evict_last();
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](int64_t it) {
+    int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
+    if (tile >= ntiles) return;
+    int s = (int)(it % STAGES);
+    unsigned long long* st = ring + (size_t)s * COLS * T;
+    mbar_arrive_expect_tx(&full[s], (uint32_t)(COLS * T * 8));
+    bulk_g2s(st, pkey + tile * T, T * 8, &full[s], pol_stream);
+#pragma unroll
+    for (int c = 0; c < NPC; c++) bulk_g2s(st + (size_t)(1 + c) * T, out.psrc[c] + tile * T, T * 8, &full[s], pol_stream);
+  };
+  if (tid == 0) for (int it = 0; it < STAGES; it++) issue(it);
+  for (int64_t it = 0;; it++) {
+    const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
+    if (tile >= ntiles) break;
+    const int s = (int)(it % STAGES);
+    mbar_wait(&full[s], (uint32_t)((it / STAGES) & 1));
+    const unsigned long long* st = ring + (size_t)s * COLS * T;
+    int64_t k[R];
+    unsigned long long pv[R][NPC > 0 ? NPC : 1];
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+      k[j] = (int64_t)st[j * 256 + tid];
+#pragma unroll
+      for (int c = 0; c < NPC; c++) pv[j][c] = st[(size_t)(1 + c) * T + j * 256 + tid];
+    }
+    __syncthreads();                 // the whole CTA has drained stage s into registers
+    if (tid == 0) issue(it + STAGES);
+    Slot v[R];
+    unsigned long long sl[R];
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+      sl[j] = (k[j] == kEmptyKey) ? t.nslots : home_slot(mix64((uint64_t)k[j]), t.nslots, t.pair_home);
+      v[j] = EVICT_LAST ? load_slot_policy(t.slots + sl[j], pol_table) : load_slot(t.slots + sl[j]);
+    }
+    unsigned bal[R];
+    uint32_t total = 0;
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+      bool m;
+      if (k[j] == kEmptyKey) m = v[j].key != 0;
+      else {
+        while (v[j].key != k[j] && v[j].key != kEmptyKey) {
+          if (++sl[j] == t.nslots) sl[j] = 0;
+          v[j] = load_slot(t.slots + sl[j]);
         }
         m = v[j].key == k[j];
       }

@@ -1,0 +1,264 @@
+// partition_kernels.cuh — histogram + shared-memory-regrouped scatter by key hash (see partition.cu for the
+// reference mapping).  Used twice: across GPUs (low hash bits) and, inside one GPU, to split a large probe side into
+// L2-sized partitions (high hash bits) before the fused probe kernel (join.cu).
+#pragma once
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace tg {
+
+#define TG_MAX_PARTS 16
+#define TG_PART_MAX_COLS 8
+#define PT_BLOCK 256
+#define PT_ITEMS 8
+#define PT_TILE (PT_BLOCK * PT_ITEMS)
+
+struct PartDst {
+  int32_t nparts, ncols;
+  const void* src[TG_PART_MAX_COLS];
+  void* dst[TG_MAX_PARTS][TG_PART_MAX_COLS];   // column base per destination
+  // row offset inside the destination buffers where this launch starts writing, per destination
+  const long long* dst_base;                   // device array [nparts]
+};
+
+// HIGH = false: destination GPU, low 32 hash bits (disjoint from the slot bits).
+// HIGH = true : local L2 partition, the TOP hash bits — the table slot is mulhi(h, nslots), monotone in h, so
+//               partition p owns the contiguous slot range [p*nslots/P, (p+1)*nslots/P).
+template <bool HIGH>
+__device__ __forceinline__ uint32_t row_part(const long long* key, const uint8_t* nulls, int64_t i, uint32_t nparts) {
+  uint64_t h = (nulls && !bit_not_null(nulls, i)) ? mix64((uint64_t)i)    // NULL keys never join: spread them
+                                                   : mix64((uint64_t)__ldcs(key + i));
+  return HIGH ? (uint32_t)__umul64hi(h, (uint64_t)nparts) : part_of(h, nparts);
+}
+
+template <bool HIGH>
+__global__ void __launch_bounds__(256)
+k_partition_count(const long long* __restrict__ key, const uint8_t* __restrict__ nulls, int64_t n, uint32_t nparts,
+                  unsigned long long* __restrict__ counts) {
+  __shared__ unsigned long long s_cnt[TG_MAX_PARTS];
+  if (threadIdx.x < TG_MAX_PARTS) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  unsigned int local[TG_MAX_PARTS];
+#pragma unroll
+  for (int p = 0; p < TG_MAX_PARTS; p++) local[p] = 0;
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    uint32_t p = row_part<HIGH>(key, nulls, i, nparts);
+#pragma unroll
+    for (int q = 0; q < TG_MAX_PARTS; q++) local[q] += (p == (uint32_t)q);
+  }
+#pragma unroll
+  for (int p = 0; p < TG_MAX_PARTS; p++) {
+    unsigned int v = local[p];
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt[p], (unsigned long long)v);
+  }
+  __syncthreads();
+  if (threadIdx.x < nparts && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], s_cnt[threadIdx.x]);
+}
+
+// exclusive prefix of counts → part_offsets[nparts+1]; also seeds the scatter cursors
+static __global__ void k_partition_offsets(const unsigned long long* counts, uint32_t nparts, long long* part_offsets,
+                                    unsigned long long* cursors) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    long long run = 0;
+    for (uint32_t p = 0; p < nparts; p++) { part_offsets[p] = run; cursors[p] = 0; run += (long long)counts[p]; }
+    part_offsets[nparts] = run;
+  }
+}
+
+template <bool HIGH>
+__global__ void __launch_bounds__(PT_BLOCK)
+k_partition_scatter(const long long* __restrict__ key, const uint8_t* __restrict__ nulls, int64_t n, PartDst d,
+                    unsigned long long* __restrict__ cursors) {
+  __shared__ unsigned long long s_val[PT_TILE];
+  __shared__ uint32_t s_cnt[TG_MAX_PARTS], s_off[TG_MAX_PARTS + 1];
+  __shared__ unsigned long long s_gbase[TG_MAX_PARTS];
+  const int lane = threadIdx.x & 31;
+  const uint32_t P = (uint32_t)d.nparts;
+  const int64_t ntiles = (n + PT_TILE - 1) / PT_TILE;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t base = tile * PT_TILE;
+    if (threadIdx.x < TG_MAX_PARTS) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    // phase 1: destination of every row + rank inside (tile, destination), warp-aggregated
+    uint32_t part[PT_ITEMS], rank[PT_ITEMS];
+#pragma unroll
+    for (int j = 0; j < PT_ITEMS; j++) {
+      int64_t i = base + (int64_t)j * PT_BLOCK + threadIdx.x;
+      bool in = i < n;
+      uint32_t p = in ? row_part<HIGH>(key, nulls, i, P) : 0xffffffffu;
+      unsigned peers = __match_any_sync(0xffffffffu, p);
+      uint32_t r = 0;
+      if (in) {
+        int leader = __ffs(peers) - 1;
+        uint32_t wbase = 0;
+        if (lane == leader) wbase = atomicAdd(&s_cnt[p], (uint32_t)__popc(peers));
+        wbase = __shfl_sync(peers, wbase, leader);
+        r = wbase + __popc(peers & ((1u << lane) - 1));
+      }
+      part[j] = p; rank[j] = r;
+    }
+    __syncthreads();
+    // phase 2: reserve a contiguous run per destination in the global cursors
+    if (threadIdx.x == 0) {
+      uint32_t run = 0;
+      for (uint32_t p = 0; p < P; p++) { s_off[p] = run; run += s_cnt[p]; }
+      s_off[P] = run;
+    }
+    if (threadIdx.x < P) {
+      uint32_t c = s_cnt[threadIdx.x];
+      s_gbase[threadIdx.x] = (c ? atomicAdd(&cursors[threadIdx.x], (unsigned long long)c) : 0ull) + (unsigned long long)d.dst_base[threadIdx.x];
+    }
+    __syncthreads();
+    const uint32_t tile_rows = s_off[P];
+    // phase 3: per column, regroup through shared memory and write coalesced runs
+    for (int c = 0; c < d.ncols; c++) {
+      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(d.src[c]);
+#pragma unroll
+      for (int j = 0; j < PT_ITEMS; j++) {
+        int64_t i = base + (int64_t)j * PT_BLOCK + threadIdx.x;
+        if (i < n) s_val[s_off[part[j]] + rank[j]] = __ldcs(src + i);
+      }
+      __syncthreads();
+      for (uint32_t sidx = threadIdx.x; sidx < tile_rows; sidx += PT_BLOCK) {
+        uint32_t p = 0;
+        while (sidx >= s_off[p + 1]) p++;   // ≤ nparts steps
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(d.dst[p][c]);
+        dst[s_gbase[p] + (sidx - s_off[p])] = s_val[sidx];
+      }
+      __syncthreads();
+    }
+  }
+}
+
+
+// TMA-fed variant of k_partition_scatter for 8-byte columns: the source tiles (key = column 0 plus NC-1 more columns)
+// arrive in shared memory through a 2-stage cp.async.bulk ring; destinations are regrouped through one 16 KB
+// shared buffer and written as coalesced runs.  Full 2048-row tiles only; the tail goes through k_partition_scatter.
+template <bool HIGH, int NC>
+__global__ void __launch_bounds__(PT_BLOCK)
+k_partition_scatter_tma(int64_t ntiles, PartDst d, unsigned long long* __restrict__ cursors) {
+  constexpr int STAGES = 2;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned long long* ring = reinterpret_cast<unsigned long long*>(smem_raw);                  // [STAGES][NC][PT_TILE]
+  unsigned long long* s_val = ring + (size_t)STAGES * NC * PT_TILE;                            // [PT_TILE]
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_val + PT_TILE);
+  __shared__ uint32_t s_cnt[TG_MAX_PARTS], s_off[TG_MAX_PARTS + 1];
+  __shared__ unsigned long long s_gbase[TG_MAX_PARTS];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t P = (uint32_t)d.nparts;
+  const unsigned long long pol = l2_policy_evict_first();
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](int64_t it) {
+    int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
+    if (tile >= ntiles) return;
+    int s = (int)(it % STAGES);
+    mbar_arrive_expect_tx(&full[s], (uint32_t)(NC * PT_TILE * 8));
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+      bulk_g2s(ring + ((size_t)s * NC + c) * PT_TILE, reinterpret_cast<const unsigned long long*>(d.src[c]) + tile * PT_TILE,
+               PT_TILE * 8, &full[s], pol);
+  };
+  if (tid == 0) for (int it = 0; it < STAGES; it++) issue(it);
+  for (int64_t it = 0;; it++) {
+    const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
+    if (tile >= ntiles) break;
+    const int s = (int)(it % STAGES);
+    if (tid < TG_MAX_PARTS) s_cnt[tid] = 0;
+    mbar_wait(&full[s], (uint32_t)((it / STAGES) & 1));
+    __syncthreads();
+    const unsigned long long* in = ring + (size_t)s * NC * PT_TILE;
+    uint32_t part[PT_ITEMS], rank[PT_ITEMS];
+#pragma unroll
+    for (int j = 0; j < PT_ITEMS; j++) {
+      uint64_t h = mix64((uint64_t)in[j * PT_BLOCK + tid]);
+      uint32_t p = HIGH ? (uint32_t)__umul64hi(h, (uint64_t)P) : part_of(h, P);
+      unsigned peers = __match_any_sync(0xffffffffu, p);
+      int leader = __ffs(peers) - 1;
+      uint32_t wbase = 0;
+      if (lane == leader) wbase = atomicAdd(&s_cnt[p], (uint32_t)__popc(peers));
+      wbase = __shfl_sync(peers, wbase, leader);
+      part[j] = p;
+      rank[j] = wbase + __popc(peers & ((1u << lane) - 1));
+    }
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t run = 0;
+      for (uint32_t p = 0; p < P; p++) { s_off[p] = run; run += s_cnt[p]; }
+      s_off[P] = run;
+    }
+    if (tid < (int)P) {
+      uint32_t c = s_cnt[tid];
+      s_gbase[tid] = (c ? atomicAdd(&cursors[tid], (unsigned long long)c) : 0ull) + (unsigned long long)d.dst_base[tid];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+#pragma unroll
+      for (int j = 0; j < PT_ITEMS; j++) s_val[s_off[part[j]] + rank[j]] = in[(size_t)c * PT_TILE + j * PT_BLOCK + tid];
+      __syncthreads();
+      if (c == NC - 1 && tid == 0) issue(it + STAGES);   // every column of stage s has been drained
+      for (uint32_t sidx = tid; sidx < PT_TILE; sidx += PT_BLOCK) {
+        uint32_t p = 0;
+        while (sidx >= s_off[p + 1]) p++;
+        reinterpret_cast<unsigned long long*>(d.dst[p][c])[s_gbase[p] + (sidx - s_off[p])] = s_val[sidx];
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// 4 rows per thread per iteration, all loads issued before use
+template <bool HIGH>
+__global__ void __launch_bounds__(256)
+k_partition_count4(const long long* __restrict__ key, int64_t n, uint32_t nparts, unsigned long long* __restrict__ counts) {
+  __shared__ unsigned long long s_cnt[TG_MAX_PARTS];
+  if (threadIdx.x < TG_MAX_PARTS) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  unsigned int local[TG_MAX_PARTS];
+#pragma unroll
+  for (int p = 0; p < TG_MAX_PARTS; p++) local[p] = 0;
+  const int64_t n2 = n >> 1;   // pairs, loaded as 128-bit
+  const ulonglong2* k2 = reinterpret_cast<const ulonglong2*>(key);
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n2; i += 4 * stride) {
+    ulonglong2 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      int64_t q = i + u * stride;
+      v[u] = q < n2 ? __ldcs(k2 + q) : make_ulonglong2(0ull, 0ull);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (i + u * stride >= n2) continue;
+      uint64_t h0 = mix64(v[u].x), h1 = mix64(v[u].y);
+      uint32_t p0 = HIGH ? (uint32_t)__umul64hi(h0, (uint64_t)nparts) : part_of(h0, nparts);
+      uint32_t p1 = HIGH ? (uint32_t)__umul64hi(h1, (uint64_t)nparts) : part_of(h1, nparts);
+#pragma unroll
+      for (int q = 0; q < TG_MAX_PARTS; q++) local[q] += (p0 == (uint32_t)q) + (p1 == (uint32_t)q);
+    }
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    uint64_t h = mix64((uint64_t)key[n - 1]);
+    uint32_t p = HIGH ? (uint32_t)__umul64hi(h, (uint64_t)nparts) : part_of(h, nparts);
+#pragma unroll
+    for (int q = 0; q < TG_MAX_PARTS; q++) local[q] += (p == (uint32_t)q);
+  }
+#pragma unroll
+  for (int p = 0; p < TG_MAX_PARTS; p++) {
+    unsigned int v = local[p];
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt[p], (unsigned long long)v);
+  }
+  __syncthreads();
+  if (threadIdx.x < nparts && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], s_cnt[threadIdx.x]);
+}
+
+}  // namespace tg
