@@ -33,8 +33,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Every lane performs its own acquire, then the warp reconverges: try_wait may release lanes of one warp at
+// different times, and the CTA-wide __syncthreads() that follows in the kernels is an ALIGNED barrier — executing it
+// with a diverged warp is undefined (seen on B200: the barrier released early and the stage was refilled under
+// lanes that had not read it yet).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {}
+  __syncwarp();
 }
 
 __device__ __forceinline__ unsigned long long l2_policy_evict_first() {
