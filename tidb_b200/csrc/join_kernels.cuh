@@ -487,15 +487,24 @@ k_probe_inner_u1_tma(const int64_t* __restrict__ pkey, int64_t ntiles, TableView
 #pragma unroll
       for (int c = 0; c < NPC; c++) pv[j][c] = st[(size_t)(1 + c) * T + j * 256 + tid];
     }
-    __syncthreads();                 // the whole CTA has drained stage s into registers
-    if (tid == 0) issue(it + STAGES);
+    // The shared-memory loads above must have RETURNED before the CTA barrier: BAR.SYNC does not wait for outstanding
+    // LDS, and on a busy LSU (other warps' uncoalesced gathers queue for microseconds) the refill issued right after
+    // the barrier can land first.  Consuming every loaded value (hash of the keys, XOR of the payloads) before the
+    // barrier makes the scoreboard wait for them.
     Slot v[R];
     unsigned long long sl[R];
+    unsigned long long dep = 0;
 #pragma unroll
     for (int j = 0; j < R; j++) {
       sl[j] = (k[j] == kEmptyKey) ? t.nslots : home_slot(mix64((uint64_t)k[j]), t.nslots, t.pair_home);
-      v[j] = EVICT_LAST ? load_slot_policy(t.slots + sl[j], pol_table) : load_slot(t.slots + sl[j]);
+#pragma unroll
+      for (int c = 0; c < NPC; c++) dep ^= pv[j][c];
     }
+    if (NPC > 0 && dep == 0x9E3779B97F4A7C15ull && sl[0] == ~0ull) out_cursor[1] = dep;   // never true; keeps `dep` alive
+    __syncthreads();                 // the whole CTA has drained stage s into registers
+    if (tid == 0) issue(it + STAGES);
+#pragma unroll
+    for (int j = 0; j < R; j++) v[j] = EVICT_LAST ? load_slot_policy(t.slots + sl[j], pol_table) : load_slot(t.slots + sl[j]);
     unsigned bal[R];
     uint32_t total = 0;
 #pragma unroll
