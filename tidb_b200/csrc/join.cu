@@ -584,10 +584,10 @@ static ProbeTuning probe_tuning() {
   t.evict_last = env_int("TG_PROBE_EVICT_LAST", 0);
   t.ctas_per_sm = env_int("TG_PROBE_CTAS_PER_SM", 8);
   if (t.ctas_per_sm < 1) t.ctas_per_sm = 1;
-  t.partition = env_int("TG_PROBE_PARTITION", 1);   // split big probes into L2-sized partitions first
+  t.partition = env_int("TG_PROBE_PARTITION", 0);   // split big probes into L2-sized partitions first
   t.parts = env_int("TG_PROBE_PARTS", 0);           // 0 = auto: table slices of <= 32 MB
   t.part_min_mb = env_int("TG_PROBE_PART_MIN_MB", 64);
-  t.tma = env_int("TG_PROBE_TMA", 1);               // TMA-fed kernels (cp.async.bulk ring) for the streamed inputs
+  t.tma = env_int("TG_PROBE_TMA", 0);               // TMA-fed kernels (cp.async.bulk ring) for the streamed inputs
   t.stages = env_int("TG_PROBE_STAGES", 4);
   t.tma_ctas = env_int("TG_PROBE_TMA_CTAS", 3);
   return t;
