@@ -211,32 +211,18 @@ def run_gpu(args):
         torch.cuda.synchronize(dev)
 
     # ---- build side (untimed): repartition by key hash when N > 1, then build the local table ---------
-    def exchange(key, cols):
-        """key-hash repartition of `cols` (list of int64 tensors, key first) to their owner ranks"""
-        nonlocal launches_extra
-        n = key.numel()
-        dst = [torch.empty_like(c) for c in cols]
-        offs = torch.zeros(world + 1, dtype=torch.int64, device=dev)
-        src_p = (C.c_void_p * len(cols))(*[c.data_ptr() for c in cols])
-        dst_p = (C.c_void_p * len(cols))(*[c.data_ptr() for c in dst])
-        abi.check(lib.tg_partition_by_key(local, C.c_void_p(key.data_ptr()), None, C.c_int64(n), world, len(cols), src_p, dst_p,
-                                          C.c_void_p(offs.data_ptr()), C.c_void_p(stream.cuda_stream)))
-        launches_extra += 3
-        send = torch.diff(offs)
-        recv = torch.empty_like(send)
-        dist.all_to_all_single(recv, send)
-        send_l, recv_l = send.tolist(), recv.tolist()
-        out = []
-        for c in dst:
-            r = torch.empty(sum(recv_l), dtype=c.dtype, device=dev)
-            dist.all_to_all_single(r, c, recv_l, send_l)
-            out.append(r)
-        return out
+    xch_b = xch_p = None
+    if world > 1:
+        from tidb_b200.parallel import KeyExchange
+        with torch.cuda.stream(stream):
+            # receive capacity: expected rows + 2 % (uniform hash; a skewed key set would need a count-then-allocate round)
+            xch_b = KeyExchange(rank, world, local, stream, 2, int(nb * 1.02) + 4096, args.exchange)
+            xch_p = KeyExchange(rank, world, local, stream, 2, int(npb * 1.02) + 4096, args.exchange)
 
     join = DeviceJoin(plan)
     with torch.cuda.stream(stream):
         if world > 1:
-            lbk, lbv = exchange(bk, [bk, bv])
+            lbk, lbv = xch_b.exchange(bk, [bk, bv])
         else:
             lbk, lbv = bk, bv
         join.build([lbk, lbv])
@@ -245,7 +231,7 @@ def run_gpu(args):
     # ---- one step ------------------------------------------------------------------------------------------
     def step(sync: bool):
         if world > 1:
-            lpk, lpv = exchange(pk, [pk, pv])
+            lpk, lpv = xch_p.exchange(pk, [pk, pv])
         else:
             lpk, lpv = pk, pv
         rows, cols, _ = join.probe([lpk, lpv], sync=sync)
@@ -286,7 +272,7 @@ def run_gpu(args):
     # ---- timed region: value (device resident) ----------------------------------------------------------------
     sampler = ClockSampler(local)
     l0 = join.stats().kernel_launches
-    lx0 = launches_extra
+    lx0 = xch_p.launches if xch_p else 0
     barrier()
     if rank == 0:
         sampler.start()
@@ -304,6 +290,7 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
+    launches_extra = (xch_p.launches if xch_p else 0)
     launches = (join.stats().kernel_launches - l0) + (launches_extra - lx0)
     value = npb * world / (ms_step * 1e-3)
 
@@ -341,7 +328,7 @@ def run_gpu(args):
             "config": {"workload": f"hash join {npb}x{nb} int64 keys per GPU, 8-byte payload, 100% match, output 4 columns (BASELINE configs[1])",
                        "l2": "inputs larger than L2 (1.6 GB probe columns + 3.2 GB output + %.0f MB table per step vs 126 MB L2)" % (bstats.table_slots * 16 / 1e6),
                        "table": {"slots": bstats.table_slots, "mode": bstats.table_mode, "distinct_keys": bstats.distinct_keys, "build_ms": bstats.build_ms},
-                       "exchange": "none" if world == 1 else "tg_partition_by_key + NCCL all_to_all_single per column"},
+                       "exchange": "none" if world == 1 else ("k_partition_scatter storing into peer receive buffers over NVLink (tg_partition_exchange), counts all-gathered" if args.exchange == "p2p" else "tg_partition_by_key + NCCL all_to_all_single per column")},
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
         }
         if roof:
@@ -351,6 +338,8 @@ def run_gpu(args):
         print(json.dumps(line))
     join.close()
     if world > 1:
+        xch_b.close(); xch_p.close()
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -449,6 +438,7 @@ def main():
     ap.add_argument("--cpu-sample-rows", type=int, default=8_000_000)
     ap.add_argument("--ref-sample-rows", type=int, default=8_000_000)
     ap.add_argument("--e2e-chunk-rows", type=int, default=4 << 20)
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--ncu-traffic-bytes", type=float, default=None, help="dram bytes per launch from the committed ncu capture")

@@ -1,0 +1,94 @@
+"""N > 1 host logic on CPU: world_size-2 gloo processes run the key-hash exchange (tidb_b200/parallel.py, same
+bookkeeping as the NVLink path) and shard-local joins with the oracle; the union of the shard results must equal the
+single-process join bit-exactly, and every row must land on the rank the C partition function names."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle_lib as O
+    from nested_loop import columns_sorted
+    from tidb_b200 import abi
+    from tidb_b200.chunk import Chunk, Column
+    from tidb_b200.parallel import exchange_by_key_host, partition_of_keys_np, recv_bases
+    from tidb_b200.plan import FieldType, JoinPlan
+    lib = abi.load_lib()
+    INT = FieldType(abi.TYPE_LONGLONG, abi.FLAG_NOT_NULL)
+    nb, npr = 5000, 20000
+    rng = np.random.default_rng(100 + rank)
+    ids = rng.permutation(nb).astype(np.int64) + rank * nb
+    bk, bv = ids * np.int64(-7046029254386353131), ids * 7
+    pid = rng.integers(0, nb * world, npr).astype(np.int64)
+    pk, pv = pid * np.int64(-7046029254386353131), np.arange(npr, dtype=np.int64) + rank * npr
+
+    def all_to_all(pieces):
+        gathered = [None] * world
+        dist.all_gather_object(gathered, pieces)
+        return [gathered[src][rank] for src in range(world)]
+
+    lbk, lbv = exchange_by_key_host(bk, [bk, bv], world, all_to_all)
+    lpk, lpv = exchange_by_key_host(pk, [pk, pv], world, all_to_all)
+    # every received key belongs here, according to the C function the device kernels share
+    assert all(lib.tg_partition_of_key(int(k), world) == rank for k in lbk[:500])
+    assert np.all(partition_of_keys_np(lpk, world) == rank)
+    # count-matrix bookkeeping used by the NVLink path: bases are the exclusive prefix over source ranks
+    cnt = np.bincount(partition_of_keys_np(pk, world), minlength=world)
+    mats = [None] * world
+    dist.all_gather_object(mats, cnt)
+    mat = np.stack(mats)
+    base, nrecv = recv_bases(mat, rank)
+    assert nrecv == len(lpk) and np.array_equal(base, mat[:rank].sum(axis=0))
+    plan = JoinPlan(abi.JOIN_INNER, [INT, INT], [INT, INT], [0], [0])
+    n, cols = O.OracleJoin(plan, 2).run([Chunk([Column(lbk), Column(lbv)])], Chunk([Column(lpk), Column(lpv)]).split(1024))
+    shard = [c[0] for c in cols]
+    allparts = [None] * world
+    dist.all_gather_object(allparts, (shard, (bk, bv, pk, pv)))
+    if rank == 0:
+        got = [np.concatenate([p[0][i] for p in allparts]) for i in range(4)]
+        gbk = np.concatenate([p[1][0] for p in allparts]); gbv = np.concatenate([p[1][1] for p in allparts])
+        gpk = np.concatenate([p[1][2] for p in allparts]); gpv = np.concatenate([p[1][3] for p in allparts])
+        n1, c1 = O.OracleJoin(plan, 2).run([Chunk([Column(gbk), Column(gbv)])], Chunk([Column(gpk), Column(gpv)]).split(1024))
+        ok = n1 == len(got[0]) == npr * world and np.array_equal(
+            columns_sorted(c1), columns_sorted([(g, np.zeros(len(g), dtype=bool)) for g in got]))
+        q.put(bool(ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_partitioned_join_gloo():
+    from tidb_b200 import build
+    build.build()
+    import oracle_lib
+    oracle_lib.build_oracle()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0, f"rank exited with {p.exitcode}"
+    assert q.get(timeout=5) is True
+
+
+def test_partition_mirror_matches_c_function():
+    from tidb_b200 import abi, build
+    from tidb_b200.parallel import partition_of_keys_np
+    build.build()
+    lib = abi.load_lib()
+    rng = np.random.default_rng(9)
+    keys = np.concatenate([rng.integers(-(1 << 63), (1 << 63) - 1, 3000, dtype=np.int64), np.arange(-50, 50, dtype=np.int64)])
+    for nparts in (1, 2, 3, 8, 16):
+        exp = np.array([lib.tg_partition_of_key(int(k), nparts) for k in keys])
+        assert np.array_equal(partition_of_keys_np(keys, nparts), exp)

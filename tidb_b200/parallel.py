@@ -1,0 +1,178 @@
+"""Key-hash repartition across GPUs: the one exchange step of the partitioned hash join / aggregation.
+
+Reference analogue: the MPP ExchangeSender with ExchangeType HashPartition that the planner emits for TiFlash
+(pkg/planner/core/operator/physicalop/physical_exchange_sender.go:115; Q3 plan in
+planner/core/casetest/tpch/testdata/tpch_suite_out.json:99-123) and, in process,
+partitionHashSplitter.split (pkg/executor/shuffle.go:450).  One process per GPU (torch.distributed).
+
+Two data paths, same partition function (tg_partition_of_key = low 32 bits of mix64(key), disjoint from the table
+slot bits):
+  * "nccl": k_partition_scatter into local per-destination regions, then all_to_all_single per column;
+  * "p2p" : tg_partition_exchange — the scatter kernel stores each destination's runs straight into the peer's
+            receive buffer over NVLink (buffers shared with cudaIpc handles), i.e. the repartition and its
+            all-to-all are ONE kernel; only the 8×8 count matrix goes through a collective.
+The host-side bookkeeping (counts → send/recv splits → bases) is shared with the CPU/gloo tests.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, List, Sequence, Tuple
+
+import numpy as np
+
+_M1 = np.uint64(0xFF51AFD7ED558CCD)
+_M2 = np.uint64(0xC4CEB9FE1A85EC53)
+
+
+def mix64_np(k: np.ndarray) -> np.ndarray:
+    """numpy mirror of tg::mix64 (csrc/common.cuh)"""
+    k = k.astype(np.uint64, copy=True)
+    with np.errstate(over="ignore"):
+        k ^= k >> np.uint64(33); k *= _M1
+        k ^= k >> np.uint64(33); k *= _M2
+        k ^= k >> np.uint64(33)
+    return k
+
+
+def partition_of_keys_np(keys: np.ndarray, nparts: int) -> np.ndarray:
+    """numpy mirror of tg_partition_of_key: destination rank of every key"""
+    h = mix64_np(keys.view(np.uint64) if keys.dtype != np.uint64 else keys)
+    return (((h & np.uint64(0xFFFFFFFF)) * np.uint64(nparts)) >> np.uint64(32)).astype(np.int64)
+
+
+def recv_bases(count_matrix: np.ndarray, rank: int) -> Tuple[np.ndarray, int]:
+    """count_matrix[src, dst] = rows src sends to dst.
+    -> (base[dst] = first row of `rank`'s region inside dst's receive buffer, rows this rank receives)"""
+    base = count_matrix[:rank, :].sum(axis=0).astype(np.int64)
+    return base, int(count_matrix[:, rank].sum())
+
+
+def exchange_by_key_host(keys: np.ndarray, cols: Sequence[np.ndarray], world: int,
+                         all_to_all: Callable[[List[np.ndarray]], List[np.ndarray]]) -> List[np.ndarray]:
+    """CPU rendering of the exchange (gloo tests): split rows by destination, hand the per-destination pieces to
+    `all_to_all`, concatenate what arrives.  Same function, same bookkeeping as the device path."""
+    dest = partition_of_keys_np(keys, world)
+    order = np.argsort(dest, kind="stable")
+    counts = np.bincount(dest, minlength=world)
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    out = []
+    for c in cols:
+        cs = c[order]
+        pieces = [np.ascontiguousarray(cs[offs[d]:offs[d + 1]]) for d in range(world)]
+        out.append(np.concatenate(all_to_all(pieces)))
+    return out
+
+
+class KeyExchange:
+    """Device-side exchange for `ncols` 8-byte columns (key first) on one rank."""
+
+    def __init__(self, rank: int, world: int, device: int, stream, ncols: int, capacity_rows: int, mode: str = "p2p"):
+        import torch
+        import torch.distributed as dist
+        from . import abi
+        self.torch, self.dist, self.abi = torch, dist, abi
+        self.lib = abi.load_lib()
+        self.rank, self.world, self.device, self.stream, self.ncols = rank, world, device, stream, ncols
+        self.mode = mode
+        self.dev = torch.device("cuda", device)
+        self.capacity = int(capacity_rows)
+        self.launches = 0
+        self.counts = torch.zeros(world, dtype=torch.int64, device=self.dev)
+        self.count_mat = torch.zeros(world * world, dtype=torch.int64, device=self.dev)
+        self.base_dev = torch.zeros(world, dtype=torch.int64, device=self.dev)
+        if mode == "p2p":
+            self._alloc_symmetric()
+        else:
+            self.scratch = [torch.empty(0, dtype=torch.int64, device=self.dev) for _ in range(ncols)]
+            self.offs = torch.zeros(world + 1, dtype=torch.int64, device=self.dev)
+
+    # ---- p2p: symmetric receive buffers, IPC-mapped on every peer ------------------------------------------
+    def _alloc_symmetric(self):
+        lib, abi = self.lib, self.abi
+        self.recv_ptrs = []
+        handles = []
+        for _ in range(self.ncols):
+            p = C.c_void_p()
+            abi.check(lib.tg_dev_alloc(self.device, C.c_size_t(self.capacity * 8), C.byref(p)))
+            self.recv_ptrs.append(p.value)
+            h = (C.c_uint8 * 64)()
+            abi.check(lib.tg_ipc_export(self.device, p, h))
+            handles.append(bytes(h))
+        gathered = [None] * self.world
+        self.dist.all_gather_object(gathered, handles)
+        # peer_ptrs[p][c] = address, in THIS process, of column c's receive buffer on rank p
+        self.peer_ptrs = []
+        for p in range(self.world):
+            row = []
+            for c in range(self.ncols):
+                if p == self.rank:
+                    row.append(self.recv_ptrs[c])
+                else:
+                    mp = C.c_void_p()
+                    hb = (C.c_uint8 * 64).from_buffer_copy(gathered[p][c])
+                    abi.check(lib.tg_ipc_open(self.device, hb, C.byref(mp)))
+                    row.append(mp.value)
+            self.peer_ptrs.append(row)
+        flat = [self.peer_ptrs[p][c] for p in range(self.world) for c in range(self.ncols)]
+        self.peer_arr = (C.c_void_p * len(flat))(*flat)
+
+    def _view(self, ptr: int, n: int):
+        class _A:
+            pass
+        a = _A()
+        a.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+        return self.torch.as_tensor(a, device=self.dev)
+
+    def exchange(self, key, cols):
+        """cols[0] must be the key column.  -> list of received columns (torch int64 tensors on this device)"""
+        torch, dist, lib, abi = self.torch, self.dist, self.lib, self.abi
+        n = key.numel()
+        st = C.c_void_p(self.stream.cuda_stream)
+        if self.mode == "nccl":
+            dst = []
+            for i, c in enumerate(cols):
+                if self.scratch[i].numel() < n:
+                    self.scratch[i] = torch.empty(n, dtype=torch.int64, device=self.dev)
+                dst.append(self.scratch[i][:n])
+            src_p = (C.c_void_p * len(cols))(*[c.data_ptr() for c in cols])
+            dst_p = (C.c_void_p * len(cols))(*[c.data_ptr() for c in dst])
+            abi.check(lib.tg_partition_by_key(self.device, C.c_void_p(key.data_ptr()), None, C.c_int64(n), self.world, len(cols),
+                                              src_p, dst_p, C.c_void_p(self.offs.data_ptr()), st))
+            self.launches += 3
+            send = torch.diff(self.offs)
+            recv = torch.empty_like(send)
+            dist.all_to_all_single(recv, send)
+            send_l, recv_l = send.tolist(), recv.tolist()
+            out = []
+            for c in dst:
+                r = torch.empty(sum(recv_l), dtype=torch.int64, device=self.dev)
+                dist.all_to_all_single(r, c, recv_l, send_l)
+                out.append(r)
+            return out
+        # p2p: counts → all-gather → bases → one scatter kernel that writes into the peers
+        abi.check(lib.tg_partition_count(self.device, C.c_void_p(key.data_ptr()), C.c_int64(n), self.world,
+                                         C.c_void_p(self.counts.data_ptr()), st))
+        dist.all_gather_into_tensor(self.count_mat, self.counts)
+        mat = self.count_mat.cpu().numpy().reshape(self.world, self.world)
+        base, nrecv = recv_bases(mat, self.rank)
+        if int(mat.sum(axis=0).max()) > self.capacity:
+            raise RuntimeError("receive buffer capacity exceeded: re-create KeyExchange with a larger capacity_rows")
+        self.base_dev.copy_(torch.from_numpy(base))
+        dist.barrier()   # every peer is done reading what the previous exchange delivered into its receive buffers
+        src_p = (C.c_void_p * len(cols))(*[c.data_ptr() for c in cols])
+        abi.check(lib.tg_partition_exchange(self.device, C.c_void_p(key.data_ptr()), C.c_int64(n), self.world, len(cols), src_p,
+                                            self.peer_arr, C.c_void_p(self.counts.data_ptr()), C.c_void_p(self.base_dev.data_ptr()), st))
+        self.launches += 2
+        dist.barrier()   # all peers' stores into my receive buffers have completed (kernel end + barrier)
+        return [self._view(self.recv_ptrs[c], nrecv) for c in range(len(cols))]
+
+    def close(self):
+        if self.mode == "p2p":
+            for p in range(self.world):
+                if p == self.rank:
+                    continue
+                for c in range(self.ncols):
+                    self.lib.tg_ipc_close(self.device, C.c_void_p(self.peer_ptrs[p][c]))
+            for ptr in self.recv_ptrs:
+                self.lib.tg_dev_free(self.device, C.c_void_p(ptr))
+            self.recv_ptrs = []
