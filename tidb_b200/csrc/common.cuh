@@ -112,9 +112,29 @@ struct PinBuf {
 };
 
 // ---- hashing --------------------------------------------------------------------------------------
-// The reference hashes the serialised key with FNV-1 64 (join/row_table_builder.go:103).  The hash only
-// selects a bucket, never a result, so the GPU uses a cheaper 64-bit finaliser (murmur3 fmix64) and
-// maps it to a slot with a multiply-high ("fastrange"), which permits non-power-of-two tables.
+// The reference hashes the serialised key with FNV-1 64 (join/row_table_builder.go:103).  The hash only selects a
+// bucket / partition, never a result, so the GPU is free to use something cheaper.  These kernels turned out to be
+// instruction-bound (profiles/r1_partitioned_*): murmur's 64-bit finaliser plus a 64-bit multiply-high cost ~40 SASS
+// instructions per row.  hash64 is one xor-fold and ONE 64-bit multiply (Fibonacci hashing, ~5 instructions); every
+// range reduction is a 32-bit multiply-high:
+//   slot   = mulhi32(hi32(h), nslots)      table slot, monotone in hi32(h)   (tables are limited to < 2^32 slots)
+//   lpart  = mulhi32(hi32(h), P)           L2 partition = same top bits, so partition p owns a contiguous slot range
+//   gpart  = mulhi32(remix(lo32,hi32), N)  destination GPU, from bits the slot does not use (the reference splits
+//                                          top bits / low bits the same way: hash_join_v2.go:306 vs hash_table_v2.go:46)
+__host__ __device__ __forceinline__ uint64_t hash64(uint64_t k) {
+  k ^= k >> 32;
+  return k * 0x9E3779B97F4A7C15ULL;
+}
+__host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
+__host__ __device__ __forceinline__ uint32_t slot32(uint64_t h, uint32_t nslots) { return mulhi32((uint32_t)(h >> 32), nslots); }
+__host__ __device__ __forceinline__ uint32_t part_of(uint64_t h, uint32_t nparts) {
+  uint32_t g = (uint32_t)h ^ ((uint32_t)(h >> 32) * 0x85EBCA6Bu);
+  g *= 0xC2B2AE35u;
+  g ^= g >> 16;
+  return mulhi32(g, nparts);
+}
+// kept for the aggregation table (64-bit slot counts are never needed there either, but its keys are group ids that
+// deserve a stronger mix: low-cardinality integer ranges)
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t k) {
   k ^= k >> 33; k *= 0xff51afd7ed558ccdULL;
   k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL;
@@ -124,11 +144,6 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t k) {
 #ifdef __CUDACC__
 __device__ __forceinline__ uint64_t slot_of(uint64_t h, uint64_t nslots) { return __umul64hi(h, nslots); }
 #endif
-// destination rank for the multi-GPU exchange: low 32 hash bits (the slot uses the high bits, like the
-// reference's top-bits partition vs low-bits slot split, hash_join_v2.go:306 vs hash_table_v2.go:46)
-__host__ __device__ __forceinline__ uint32_t part_of(uint64_t h, uint32_t nparts) {
-  return (uint32_t)(((h & 0xffffffffull) * (uint64_t)nparts) >> 32);
-}
 
 static const int64_t kEmptyKey = INT64_MIN;   // sentinel of an unoccupied slot; the key value itself
                                               // lives in a dedicated side slot (see join.cu)

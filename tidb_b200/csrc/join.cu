@@ -657,7 +657,7 @@ template <int NC>
 static int launch_scatter_tma(tg_join* j, int64_t n, PartDst& d, unsigned long long* cursors) {
   int64_t ntiles = n / PT_TILE;
   if (ntiles > 0) {
-    size_t smem = (size_t)2 * NC * PT_TILE * 8 + PT_TILE * 8 + 2 * 8 + 16;
+    size_t smem = (size_t)2 * NC * PT_TILE * 8 + 2 * PT_TILE * 8 + 2 * 8 + 16;
     TG_CUDA(cudaFuncSetAttribute(k_partition_scatter_tma<true, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (int)std::min<int64_t>(ntiles, (int64_t)j->nsm * 2);
     k_partition_scatter_tma<true, NC><<<grid, PT_BLOCK, smem, j->stream>>>(ntiles, d, cursors);

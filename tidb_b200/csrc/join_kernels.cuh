@@ -54,7 +54,7 @@ struct TableView {
 
 // home slot of a hash value
 __device__ __forceinline__ unsigned long long home_slot(unsigned long long h, unsigned long long nslots, int pair_home) {
-  return pair_home ? (slot_of(h, nslots >> 1) << 1) : slot_of(h, nslots);
+  return pair_home ? ((unsigned long long)slot32(h, (uint32_t)(nslots >> 1)) << 1) : (unsigned long long)slot32(h, (uint32_t)nslots);
 }
 
 #define TG_MAX_OUT 24
@@ -116,6 +116,13 @@ __device__ __forceinline__ Slot load_slot(const Slot* p) {
   return s;
 }
 
+// both slots of a 32-byte home pair with ONE 256-bit load (LDG.E.256, sm_100+); p must be 32-byte aligned
+__device__ __forceinline__ void load_pair(const Slot* p, Slot& a, Slot& b) {
+  unsigned long long x0, x1, x2, x3;
+  asm volatile("ld.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(x0), "=l"(x1), "=l"(x2), "=l"(x3) : "l"(p));
+  a.key = (int64_t)x0; a.meta = x1; b.key = (int64_t)x2; b.meta = x3;
+}
+
 // lookup without insertion: returns slot index or kInvalidSlot; meta of the found slot in *meta
 __device__ __forceinline__ uint32_t table_find(const TableView& t, int64_t k, unsigned long long* meta) {
   if (k == kEmptyKey) {
@@ -124,7 +131,7 @@ __device__ __forceinline__ uint32_t table_find(const TableView& t, int64_t k, un
     // the side slot is "occupied" iff a build row carried this key: mode U1 marks that in key
     return s.key == 0 ? kInvalidSlot : (uint32_t)t.nslots;
   }
-  unsigned long long s = home_slot(mix64((uint64_t)k), t.nslots, t.pair_home);
+  unsigned long long s = home_slot(hash64((uint64_t)k), t.nslots, t.pair_home);
   for (;;) {
     Slot v = load_slot(t.slots + s);
     if (v.key == k) { *meta = v.meta; return (uint32_t)s; }
@@ -161,7 +168,7 @@ k_build_insert(KeySpec key, DevCols cols, DevFilter filt, int64_t n, Slot* slots
       s = nslots;
       slots[s].key = 1;   // occupied flag (benign race: every writer stores 1)
     } else {
-      s = home_slot(mix64((uint64_t)k), nslots, pair_home);
+      s = home_slot(hash64((uint64_t)k), nslots, pair_home);
       for (;;) {
         int64_t cur = *reinterpret_cast<volatile int64_t*>(&slots[s].key);
         if (cur == k) break;
@@ -288,7 +295,7 @@ k_probe_inner_u1(const int64_t* __restrict__ pkey, DevCols pcols, int64_t n, Tab
     unsigned long long s[R];
 #pragma unroll
     for (int j = 0; j < R; j++) {
-      s[j] = (k[j] == kEmptyKey) ? t.nslots : home_slot(mix64((uint64_t)k[j]), t.nslots, t.pair_home);
+      s[j] = (k[j] == kEmptyKey) ? t.nslots : home_slot(hash64((uint64_t)k[j]), t.nslots, t.pair_home);
       v[j] = load_slot(t.slots + s[j]);
     }
 #pragma unroll
@@ -394,7 +401,7 @@ k_probe_inner_u1_w(const int64_t* __restrict__ pkey, int64_t n, TableView t, Fas
     }
 #pragma unroll
     for (int j = 0; j < R; j++) {
-      s[j] = (k[j] == kEmptyKey) ? t.nslots : home_slot(mix64((uint64_t)k[j]), t.nslots, t.pair_home);
+      s[j] = (k[j] == kEmptyKey) ? t.nslots : home_slot(hash64((uint64_t)k[j]), t.nslots, t.pair_home);
       v[j] = EVICT_LAST ? load_slot_policy(t.slots + s[j], pol) : load_slot(t.slots + s[j]);
     }
 #pragma unroll
@@ -496,22 +503,38 @@ k_probe_inner_u1_tma(const int64_t* __restrict__ pkey, int64_t ntiles, TableView
     unsigned long long dep = 0;
 #pragma unroll
     for (int j = 0; j < R; j++) {
-      sl[j] = (k[j] == kEmptyKey) ? t.nslots : home_slot(mix64((uint64_t)k[j]), t.nslots, t.pair_home);
+      sl[j] = (k[j] == kEmptyKey) ? t.nslots : home_slot(hash64((uint64_t)k[j]), t.nslots, t.pair_home);
 #pragma unroll
       for (int c = 0; c < NPC; c++) dep ^= pv[j][c];
     }
     if (NPC > 0 && dep == 0x9E3779B97F4A7C15ull && sl[0] == ~0ull) out_cursor[1] = dep;   // never true; keeps `dep` alive
     __syncthreads();                 // the whole CTA has drained stage s into registers
     if (tid == 0) issue(it + STAGES);
+    Slot w[R];                       // second slot of the home pair (pair_home tables)
+    if (t.pair_home) {
 #pragma unroll
-    for (int j = 0; j < R; j++) v[j] = EVICT_LAST ? load_slot_policy(t.slots + sl[j], pol_table) : load_slot(t.slots + sl[j]);
+      for (int j = 0; j < R; j++) {
+        if (k[j] == kEmptyKey) { v[j] = load_slot(t.slots + sl[j]); w[j].key = kEmptyKey; w[j].meta = 0; }
+        else load_pair(t.slots + sl[j], v[j], w[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < R; j++) { v[j] = EVICT_LAST ? load_slot_policy(t.slots + sl[j], pol_table) : load_slot(t.slots + sl[j]); w[j].key = kEmptyKey; w[j].meta = 0; }
+    }
     unsigned bal[R];
     uint32_t total = 0;
 #pragma unroll
     for (int j = 0; j < R; j++) {
       bool m;
       if (k[j] == kEmptyKey) m = v[j].key != 0;
+      else if (v[j].key == k[j]) m = true;
+      else if (t.pair_home && w[j].key == k[j]) { v[j] = w[j]; m = true; }
+      else if (v[j].key == kEmptyKey || (t.pair_home && w[j].key == kEmptyKey)) m = false;
       else {
+        // both home slots hold other keys: continue the linear probe behind them (rare at the configured load factor)
+        sl[j] += t.pair_home ? 2 : 1;
+        if (sl[j] >= t.nslots) sl[j] = 0;
+        v[j] = load_slot(t.slots + sl[j]);
         while (v[j].key != k[j] && v[j].key != kEmptyKey) {
           if (++sl[j] == t.nslots) sl[j] = 0;
           v[j] = load_slot(t.slots + sl[j]);

@@ -30,7 +30,7 @@ using namespace tg;
 
 extern "C" {
 
-int32_t tg_partition_of_key(int64_t key, int32_t nparts) { return (int32_t)part_of(mix64((uint64_t)key), (uint32_t)nparts); }
+int32_t tg_partition_of_key(int64_t key, int32_t nparts) { return (int32_t)part_of(hash64((uint64_t)key), (uint32_t)nparts); }
 
 int tg_partition_count(int device, const int64_t* key_dev, int64_t rows, int32_t nparts, int64_t* part_counts_dev, void* stream) {
   TG_TRY(check_parts(nparts, 1));

@@ -26,9 +26,9 @@ struct PartDst {
 //               partition p owns the contiguous slot range [p*nslots/P, (p+1)*nslots/P).
 template <bool HIGH>
 __device__ __forceinline__ uint32_t row_part(const long long* key, const uint8_t* nulls, int64_t i, uint32_t nparts) {
-  uint64_t h = (nulls && !bit_not_null(nulls, i)) ? mix64((uint64_t)i)    // NULL keys never join: spread them
-                                                   : mix64((uint64_t)__ldcs(key + i));
-  return HIGH ? (uint32_t)__umul64hi(h, (uint64_t)nparts) : part_of(h, nparts);
+  uint64_t h = (nulls && !bit_not_null(nulls, i)) ? hash64((uint64_t)i)    // NULL keys never join: spread them
+                                                   : hash64((uint64_t)__ldcs(key + i));
+  return HIGH ? mulhi32((uint32_t)(h >> 32), nparts) : part_of(h, nparts);
 }
 
 template <bool HIGH>
@@ -134,18 +134,20 @@ k_partition_scatter(const long long* __restrict__ key, const uint8_t* __restrict
 }
 
 
-// TMA-fed variant of k_partition_scatter for 8-byte columns: the source tiles (key = column 0 plus NC-1 more columns)
-// arrive in shared memory through a 2-stage cp.async.bulk ring; destinations are regrouped through one 16 KB
-// shared buffer and written as coalesced runs.  Full 2048-row tiles only; the tail goes through k_partition_scatter.
+// TMA-fed scatter for 8-byte columns, no NULL keys: the source tiles (key = column 0 plus NC-1 more columns) arrive in
+// shared memory through a 2-stage cp.async.bulk ring.  Each row's destination (partition, global position) is computed
+// ONCE, parked next to its tile slot, and reused for every column; columns are regrouped through one 16 KB buffer and
+// written as coalesced runs.  Full 2048-row tiles only; the tail goes through k_partition_scatter.
 template <bool HIGH, int NC>
 __global__ void __launch_bounds__(PT_BLOCK)
 k_partition_scatter_tma(int64_t ntiles, PartDst d, unsigned long long* __restrict__ cursors) {
   constexpr int STAGES = 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned long long* ring = reinterpret_cast<unsigned long long*>(smem_raw);                  // [STAGES][NC][PT_TILE]
-  unsigned long long* s_val = ring + (size_t)STAGES * NC * PT_TILE;                            // [PT_TILE]
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_val + PT_TILE);
-  __shared__ uint32_t s_cnt[TG_MAX_PARTS], s_off[TG_MAX_PARTS + 1];
+  unsigned long long* s_val = ring + (size_t)STAGES * NC * PT_TILE;                            // [PT_TILE] regrouped values
+  unsigned long long* s_pos = s_val + PT_TILE;                                                 // [PT_TILE] part<<58 | global row
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_pos + PT_TILE);
+  __shared__ uint32_t s_cnt[TG_MAX_PARTS], s_off[TG_MAX_PARTS];
   __shared__ unsigned long long s_gbase[TG_MAX_PARTS];
   const int tid = threadIdx.x, lane = tid & 31;
   const uint32_t P = (uint32_t)d.nparts;
@@ -174,47 +176,59 @@ k_partition_scatter_tma(int64_t ntiles, PartDst d, unsigned long long* __restric
     mbar_wait(&full[s], (uint32_t)((it / STAGES) & 1));
     __syncthreads();
     const unsigned long long* in = ring + (size_t)s * NC * PT_TILE;
-    uint32_t part[PT_ITEMS], rank[PT_ITEMS];
+    unsigned long long key[PT_ITEMS];
+    uint32_t pr[PT_ITEMS];   // part << 16 | rank inside (tile, part)
 #pragma unroll
     for (int j = 0; j < PT_ITEMS; j++) {
-      uint64_t h = mix64((uint64_t)in[j * PT_BLOCK + tid]);
-      uint32_t p = HIGH ? (uint32_t)__umul64hi(h, (uint64_t)P) : part_of(h, P);
+      key[j] = in[j * PT_BLOCK + tid];
+      uint64_t h = hash64(key[j]);
+      uint32_t p = HIGH ? mulhi32((uint32_t)(h >> 32), P) : part_of(h, P);
       unsigned peers = __match_any_sync(0xffffffffu, p);
       int leader = __ffs(peers) - 1;
       uint32_t wbase = 0;
       if (lane == leader) wbase = atomicAdd(&s_cnt[p], (uint32_t)__popc(peers));
       wbase = __shfl_sync(peers, wbase, leader);
-      part[j] = p;
-      rank[j] = wbase + __popc(peers & ((1u << lane) - 1));
+      pr[j] = (p << 16) | (wbase + __popc(peers & ((1u << lane) - 1)));
     }
     __syncthreads();
-    if (tid == 0) {
-      uint32_t run = 0;
-      for (uint32_t p = 0; p < P; p++) { s_off[p] = run; run += s_cnt[p]; }
-      s_off[P] = run;
+    if (tid < 32) {   // exclusive scan of the P counts by one warp + one global reservation per destination
+      uint32_t c = tid < (int)P ? s_cnt[tid] : 0, incl = c;
+      for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+      if (tid < (int)P) {
+        s_off[tid] = incl - c;
+        s_gbase[tid] = (c ? atomicAdd(&cursors[tid], (unsigned long long)c) : 0ull) + (unsigned long long)d.dst_base[tid];
+      }
     }
-    if (tid < (int)P) {
-      uint32_t c = s_cnt[tid];
-      s_gbase[tid] = (c ? atomicAdd(&cursors[tid], (unsigned long long)c) : 0ull) + (unsigned long long)d.dst_base[tid];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PT_ITEMS; j++) {
+      uint32_t p = pr[j] >> 16, r = pr[j] & 0xffffu;
+      uint32_t slot = s_off[p] + r;
+      pr[j] = slot;
+      s_pos[slot] = ((unsigned long long)p << 58) | (s_gbase[p] + r);
+      s_val[slot] = key[j];
     }
     __syncthreads();
 #pragma unroll
     for (int c = 0; c < NC; c++) {
+      if (c > 0) {
 #pragma unroll
-      for (int j = 0; j < PT_ITEMS; j++) s_val[s_off[part[j]] + rank[j]] = in[(size_t)c * PT_TILE + j * PT_BLOCK + tid];
-      __syncthreads();
-      if (c == NC - 1 && tid == 0) issue(it + STAGES);   // every column of stage s has been drained
-      for (uint32_t sidx = tid; sidx < PT_TILE; sidx += PT_BLOCK) {
-        uint32_t p = 0;
-        while (sidx >= s_off[p + 1]) p++;
-        reinterpret_cast<unsigned long long*>(d.dst[p][c])[s_gbase[p] + (sidx - s_off[p])] = s_val[sidx];
+        for (int j = 0; j < PT_ITEMS; j++) s_val[pr[j]] = in[(size_t)c * PT_TILE + j * PT_BLOCK + tid];
+        __syncthreads();
+      }
+      if (c == NC - 1 && tid == 0) issue(it + STAGES);   // every column of stage s has been drained (values consumed by STS)
+#pragma unroll
+      for (int j = 0; j < PT_ITEMS; j++) {
+        uint32_t sidx = j * PT_BLOCK + tid;
+        unsigned long long pos = s_pos[sidx];
+        reinterpret_cast<unsigned long long*>(d.dst[pos >> 58][c])[pos & ((1ull << 58) - 1)] = s_val[sidx];
       }
       __syncthreads();
     }
   }
 }
 
-// 4 rows per thread per iteration, all loads issued before use
+// histogram of destinations: 128-bit loads, 4 in flight per thread, counts packed 8 x 8 bit in two 64-bit registers
 template <bool HIGH>
 __global__ void __launch_bounds__(256)
 k_partition_count4(const long long* __restrict__ key, int64_t n, uint32_t nparts, unsigned long long* __restrict__ counts) {
@@ -224,33 +238,40 @@ k_partition_count4(const long long* __restrict__ key, int64_t n, uint32_t nparts
   unsigned int local[TG_MAX_PARTS];
 #pragma unroll
   for (int p = 0; p < TG_MAX_PARTS; p++) local[p] = 0;
+  unsigned long long a0 = 0, a1 = 0;
+  int pending = 0;
+  auto add = [&](uint64_t k) {
+    uint64_t h = hash64(k);
+    uint32_t p = HIGH ? mulhi32((uint32_t)(h >> 32), nparts) : part_of(h, nparts);
+    unsigned long long inc = 1ull << ((p & 7u) << 3);
+    a0 += (p < 8u) ? inc : 0ull;
+    a1 += (p < 8u) ? 0ull : inc;
+  };
+  auto flush = [&]() {
+#pragma unroll
+    for (int q = 0; q < 8; q++) { local[q] += (unsigned int)((a0 >> (8 * q)) & 0xffu); local[8 + q] += (unsigned int)((a1 >> (8 * q)) & 0xffu); }
+    a0 = a1 = 0; pending = 0;
+  };
   const int64_t n2 = n >> 1;   // pairs, loaded as 128-bit
   const ulonglong2* k2 = reinterpret_cast<const ulonglong2*>(key);
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n2; i += 4 * stride) {
     ulonglong2 v[4];
+    bool ok[4];
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       int64_t q = i + u * stride;
-      v[u] = q < n2 ? __ldcs(k2 + q) : make_ulonglong2(0ull, 0ull);
+      ok[u] = q < n2;
+      v[u] = ok[u] ? __ldcs(k2 + q) : make_ulonglong2(0ull, 0ull);
     }
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      if (i + u * stride >= n2) continue;
-      uint64_t h0 = mix64(v[u].x), h1 = mix64(v[u].y);
-      uint32_t p0 = HIGH ? (uint32_t)__umul64hi(h0, (uint64_t)nparts) : part_of(h0, nparts);
-      uint32_t p1 = HIGH ? (uint32_t)__umul64hi(h1, (uint64_t)nparts) : part_of(h1, nparts);
-#pragma unroll
-      for (int q = 0; q < TG_MAX_PARTS; q++) local[q] += (p0 == (uint32_t)q) + (p1 == (uint32_t)q);
-    }
+    for (int u = 0; u < 4; u++) if (ok[u]) { add(v[u].x); add(v[u].y); }
+    pending += 8;
+    if (pending > 240) flush();
   }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-    uint64_t h = mix64((uint64_t)key[n - 1]);
-    uint32_t p = HIGH ? (uint32_t)__umul64hi(h, (uint64_t)nparts) : part_of(h, nparts);
-#pragma unroll
-    for (int q = 0; q < TG_MAX_PARTS; q++) local[q] += (p == (uint32_t)q);
-  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) add((uint64_t)key[n - 1]);
+  flush();
 #pragma unroll
   for (int p = 0; p < TG_MAX_PARTS; p++) {
     unsigned int v = local[p];

@@ -20,24 +20,28 @@ from typing import Callable, List, Sequence, Tuple
 
 import numpy as np
 
-_M1 = np.uint64(0xFF51AFD7ED558CCD)
-_M2 = np.uint64(0xC4CEB9FE1A85EC53)
+_C64 = np.uint64(0x9E3779B97F4A7C15)
 
 
-def mix64_np(k: np.ndarray) -> np.ndarray:
-    """numpy mirror of tg::mix64 (csrc/common.cuh)"""
+def hash64_np(k: np.ndarray) -> np.ndarray:
+    """numpy mirror of tg::hash64 (csrc/common.cuh): xor-fold + one 64-bit multiply"""
     k = k.astype(np.uint64, copy=True)
     with np.errstate(over="ignore"):
-        k ^= k >> np.uint64(33); k *= _M1
-        k ^= k >> np.uint64(33); k *= _M2
-        k ^= k >> np.uint64(33)
+        k ^= k >> np.uint64(32)
+        k *= _C64
     return k
 
 
 def partition_of_keys_np(keys: np.ndarray, nparts: int) -> np.ndarray:
-    """numpy mirror of tg_partition_of_key: destination rank of every key"""
-    h = mix64_np(keys.view(np.uint64) if keys.dtype != np.uint64 else keys)
-    return (((h & np.uint64(0xFFFFFFFF)) * np.uint64(nparts)) >> np.uint64(32)).astype(np.int64)
+    """numpy mirror of tg_partition_of_key (tg::part_of): destination rank of every key"""
+    h = hash64_np(keys.view(np.uint64) if keys.dtype != np.uint64 else keys)
+    lo = (h & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    hi = (h >> np.uint64(32)).astype(np.uint32)
+    with np.errstate(over="ignore"):
+        g = lo ^ (hi * np.uint32(0x85EBCA6B))
+        g = g * np.uint32(0xC2B2AE35)
+        g ^= g >> np.uint32(16)
+    return ((g.astype(np.uint64) * np.uint64(nparts)) >> np.uint64(32)).astype(np.int64)
 
 
 def recv_bases(count_matrix: np.ndarray, rank: int) -> Tuple[np.ndarray, int]:
