@@ -593,7 +593,8 @@ static ProbeTuning probe_tuning() {
   return t;
 }
 
-// classify the output columns of the fused fast path by the register that feeds them
+// classify the output columns of the fused fast path by the register that feeds them; false = shape not covered by
+// the templated kernels (the CTA-tile kernel handles it)
 static bool build_fast_out(const tg_join* j, const OutCols& oc, const DevCols& pview, FastOut& fo) {
   std::memset(&fo, 0, sizeof(fo));
   int pcol_of[TG_FAST_MAX_PCOLS];
@@ -601,54 +602,66 @@ static bool build_fast_out(const tg_join* j, const OutCols& oc, const DevCols& p
     const OutSpec& sp = oc.spec[c];
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(oc.data[c]);
     if (sp.src == SRC_BUILD_KEY || (sp.src == SRC_PROBE_COL && sp.idx == j->probe.key_col)) {
-      if (fo.n_key_dst >= 4) return false;
+      if (fo.n_key_dst >= TG_FAST_MAX_KEYDST) return false;
       fo.key_dst[fo.n_key_dst++] = dst;
     } else if (sp.src == SRC_BUILD_META) {
-      if (fo.n_meta_dst >= 2) return false;
+      if (fo.n_meta_dst >= TG_FAST_MAX_METADST) return false;
       fo.meta_dst[fo.n_meta_dst++] = dst;
     } else if (sp.src == SRC_PROBE_COL) {
-      int k = -1;
-      for (int q = 0; q < fo.n_pcols; q++) if (pcol_of[q] == sp.idx) k = q;
-      if (k < 0) {
-        if (fo.n_pcols >= TG_FAST_MAX_PCOLS) return false;
-        k = fo.n_pcols++;
-        pcol_of[k] = sp.idx;
-        fo.psrc[k] = reinterpret_cast<const unsigned long long*>(pview.data[sp.idx]);
-      }
-      if (fo.n_pdst[k] >= 2) return false;
-      fo.pdst[k][fo.n_pdst[k]++] = dst;
+      for (int q = 0; q < fo.n_pcols; q++) if (pcol_of[q] == sp.idx) return false;   // same column twice
+      if (fo.n_pcols >= TG_FAST_MAX_PCOLS) return false;
+      int k = fo.n_pcols++;
+      pcol_of[k] = sp.idx;
+      fo.psrc[k] = reinterpret_cast<const unsigned long long*>(pview.data[sp.idx]);
+      fo.pdst[k] = dst;
     } else return false;
   }
   return true;
 }
 
-template <int NPC, int STAGES>
-static int launch_probe_tma_s(tg_join* j, const int64_t* pkey, int64_t ntiles, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t) {
-  size_t smem = (size_t)STAGES * (1 + NPC) * TG_PROBE_TILE * 8 + STAGES * 8 + 16;
-  int grid = (int)std::min<int64_t>(ntiles, (int64_t)j->nsm * t.tma_ctas);
-  if (t.evict_last) {
-    TG_CUDA(cudaFuncSetAttribute(k_probe_inner_u1_tma<NPC, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_probe_inner_u1_tma<NPC, STAGES, true><<<grid, 256, smem, j->stream>>>(pkey, ntiles, j->tv, fo, cur);
-  } else {
-    TG_CUDA(cudaFuncSetAttribute(k_probe_inner_u1_tma<NPC, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_probe_inner_u1_tma<NPC, STAGES, false><<<grid, 256, smem, j->stream>>>(pkey, ntiles, j->tv, fo, cur);
-  }
-  return TG_OK;
+// (NPC, NKD, NMD) dispatch
+template <template <int, int, int> class F, typename... A>
+static int dispatch_shape(const FastOut& fo, A&&... a) {
+#define TG_SHAPE(P, K, M) if (fo.n_pcols == P && fo.n_key_dst == K && fo.n_meta_dst == M) return F<P, K, M>::run(a...);
+#define TG_SHAPE_KM(P) TG_SHAPE(P, 0, 0) TG_SHAPE(P, 0, 1) TG_SHAPE(P, 1, 0) TG_SHAPE(P, 1, 1) TG_SHAPE(P, 2, 0) TG_SHAPE(P, 2, 1)
+  TG_SHAPE_KM(0) TG_SHAPE_KM(1) TG_SHAPE_KM(2) TG_SHAPE_KM(3)
+#undef TG_SHAPE_KM
+#undef TG_SHAPE
+  return fail(TG_ERR_CUDA, "internal: fused probe shape not instantiated");
 }
-template <int NPC>
-static int launch_probe_tma_n(tg_join* j, const int64_t* pkey, int64_t ntiles, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t) {
-  if (t.stages <= 2) return launch_probe_tma_s<NPC, 2>(j, pkey, ntiles, fo, cur, t);
-  if (t.stages == 3) return launch_probe_tma_s<NPC, 3>(j, pkey, ntiles, fo, cur, t);
-  if (t.stages >= 6 && NPC <= 1) return launch_probe_tma_s<NPC, 6>(j, pkey, ntiles, fo, cur, t);
-  return launch_probe_tma_s<NPC, 4>(j, pkey, ntiles, fo, cur, t);
+
+template <int NPC, int NKD, int NMD>
+struct LaunchWarp {
+  static int run(tg_join* j, const int64_t* pkey, int64_t n, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t) {
+    constexpr int R = 4;
+    int64_t tiles = (n + 32 * R - 1) / (32 * R);
+    int64_t ctas = (tiles + 7) / 8;
+    int grid = (int)std::min<int64_t>(ctas, (int64_t)j->nsm * t.ctas_per_sm);
+    k_probe_inner_u1_w<R, NPC, NKD, NMD><<<grid, 256, 0, j->stream>>>(pkey, n, j->tv, fo, cur);
+    return TG_OK;
+  }
+};
+template <int NPC, int NKD, int NMD>
+struct LaunchTma {
+  static int run(tg_join* j, const int64_t* pkey, int64_t ntiles, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t) {
+    int grid = (int)std::min<int64_t>(ntiles, (int64_t)j->nsm * t.tma_ctas);
+    if (t.stages >= 4) {
+      size_t smem = (size_t)4 * (1 + NPC) * TG_PROBE_TILE * 8 + 4 * 8 + 16;
+      TG_CUDA(cudaFuncSetAttribute(k_probe_inner_u1_tma<NPC, NKD, NMD, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_probe_inner_u1_tma<NPC, NKD, NMD, 4><<<grid, 256, smem, j->stream>>>(pkey, ntiles, j->tv, fo, cur);
+    } else {
+      size_t smem = (size_t)2 * (1 + NPC) * TG_PROBE_TILE * 8 + 2 * 8 + 16;
+      TG_CUDA(cudaFuncSetAttribute(k_probe_inner_u1_tma<NPC, NKD, NMD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_probe_inner_u1_tma<NPC, NKD, NMD, 2><<<grid, 256, smem, j->stream>>>(pkey, ntiles, j->tv, fo, cur);
+    }
+    return TG_OK;
+  }
+};
+static int launch_probe_warp(tg_join* j, const int64_t* pkey, int64_t n, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t) {
+  return dispatch_shape<LaunchWarp>(fo, j, pkey, n, fo, cur, t);
 }
 static int launch_probe_tma(tg_join* j, const int64_t* pkey, int64_t ntiles, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t) {
-  switch (fo.n_pcols) {
-    case 0: return launch_probe_tma_n<0>(j, pkey, ntiles, fo, cur, t);
-    case 1: return launch_probe_tma_n<1>(j, pkey, ntiles, fo, cur, t);
-    case 2: return launch_probe_tma_n<2>(j, pkey, ntiles, fo, cur, t);
-    default: return launch_probe_tma_n<3>(j, pkey, ntiles, fo, cur, t);
-  }
+  return dispatch_shape<LaunchTma>(fo, j, pkey, ntiles, fo, cur, t);
 }
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -671,29 +684,6 @@ static int launch_scatter_tma(tg_join* j, int64_t n, PartDst& d, unsigned long l
     j->stats.kernel_launches++;
   }
   return TG_OK;
-}
-
-template <int R, int NPC>
-static void launch_probe_warp_el(tg_join* j, const int64_t* pkey, int64_t n, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t) {
-  int64_t tiles = (n + 32 * R - 1) / (32 * R);
-  int64_t ctas = (tiles + 7) / 8;
-  int grid = (int)std::min<int64_t>(ctas, (int64_t)j->nsm * t.ctas_per_sm);
-  if (t.evict_last) k_probe_inner_u1_w<R, NPC, true><<<grid, 256, 0, j->stream>>>(pkey, n, j->tv, fo, cur);
-  else k_probe_inner_u1_w<R, NPC, false><<<grid, 256, 0, j->stream>>>(pkey, n, j->tv, fo, cur);
-}
-template <int R>
-static void launch_probe_warp_r(tg_join* j, const int64_t* pkey, int64_t n, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t) {
-  switch (fo.n_pcols) {
-    case 0: launch_probe_warp_el<R, 0>(j, pkey, n, fo, cur, t); break;
-    case 1: launch_probe_warp_el<R, 1>(j, pkey, n, fo, cur, t); break;
-    case 2: launch_probe_warp_el<R, 2>(j, pkey, n, fo, cur, t); break;
-    default: launch_probe_warp_el<R, 3>(j, pkey, n, fo, cur, t); break;
-  }
-}
-static void launch_probe_warp(tg_join* j, const int64_t* pkey, int64_t n, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t) {
-  if (t.R >= 8) launch_probe_warp_r<8>(j, pkey, n, fo, cur, t);
-  else if (t.R <= 2) launch_probe_warp_r<2>(j, pkey, n, fo, cur, t);
-  else launch_probe_warp_r<4>(j, pkey, n, fo, cur, t);
 }
 
 // probe `n` device-resident rows; results are appended to rb (rb.rows advanced)
@@ -773,7 +763,7 @@ static int probe_device(tg_join* j, const DevCols& pview, int64_t n, ResultBatch
         if (done < n) {
           FastOut tail = fo;
           for (int c = 0; c < fo.n_pcols; c++) tail.psrc[c] = fo.psrc[c] + done;
-          launch_probe_warp(j, pkey + done, n - done, tail, cur, tune);
+          TG_TRY(launch_probe_warp(j, pkey + done, n - done, tail, cur, tune));
           if (full_tiles > 0) j->stats.kernel_launches++;
         }
       } else {

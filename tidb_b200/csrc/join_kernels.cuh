@@ -350,19 +350,20 @@ k_probe_inner_u1(const int64_t* __restrict__ pkey, DevCols pcols, int64_t n, Tab
 }
 
 // ---------------------------------------------------------------------------------------------
-// probe — fused fast path, warp-autonomous variant: no shared memory, no block barrier.  Each warp owns
-// tiles of 32×R rows: R coalesced key loads, the probe payload columns prefetched into registers, R
-// independent 16-byte gathers, ballot compaction, ONE atomicAdd per warp tile, coalesced column stores.
+// probe — fused fast path, warp-autonomous and TMA-fed variants.
+// The output shape is a template parameter (NPC probe payload columns, NKD outputs fed by the join key, NMD outputs
+// fed by the build payload): with run-time destination counts ptxas unrolled the store loops into ~360 predicated
+// STG + 350 LDC per kernel (886 M warp instructions for 100 M rows, profiles/r1_partitioned_tma_launches.csv).
 // ---------------------------------------------------------------------------------------------
 #define TG_FAST_MAX_PCOLS 3
+#define TG_FAST_MAX_KEYDST 2
+#define TG_FAST_MAX_METADST 1
 struct FastOut {
-  int32_t n_pcols;                                  // distinct probe payload columns copied to the output
-  int32_t n_key_dst, n_meta_dst, pad;
+  int32_t n_pcols, n_key_dst, n_meta_dst, pad;
   const unsigned long long* psrc[TG_FAST_MAX_PCOLS];
-  int32_t n_pdst[TG_FAST_MAX_PCOLS]; int32_t pad2;
-  unsigned long long* pdst[TG_FAST_MAX_PCOLS][2];
-  unsigned long long* key_dst[4];                   // outputs that carry the join key (probe key and/or build key)
-  unsigned long long* meta_dst[2];                  // outputs that carry the build payload
+  unsigned long long* pdst[TG_FAST_MAX_PCOLS];       // exactly one destination per probe payload column
+  unsigned long long* key_dst[TG_FAST_MAX_KEYDST];   // outputs that carry the join key (probe key and/or build key)
+  unsigned long long* meta_dst[TG_FAST_MAX_METADST]; // output that carries the build payload
 };
 
 __device__ __forceinline__ unsigned long long policy_evict_last() {
@@ -377,7 +378,68 @@ __device__ __forceinline__ Slot load_slot_policy(const Slot* p, unsigned long lo
   return s;
 }
 
-template <int R, int NPC, bool EVICT_LAST>
+// R rows per lane, keys (and prefetched payload) already in registers: gather, resolve, compact, store.
+// `in[j]` = row j of this lane exists (tail tiles).
+template <int R, int NPC, int NKD, int NMD>
+__device__ __forceinline__ void probe_rows_u1(const int64_t (&k)[R], const unsigned long long (&pv)[R][NPC > 0 ? NPC : 1],
+                                              const unsigned long long (&sl0)[R], const bool (&in)[R], const TableView& t,
+                                              const FastOut& out, unsigned long long* __restrict__ out_cursor, int lane) {
+  Slot v[R], w[R];
+  unsigned long long sl[R];
+  if (t.pair_home) {
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+      sl[j] = sl0[j];
+      if (k[j] == kEmptyKey) { v[j] = load_slot(t.slots + sl[j]); w[j].key = kEmptyKey; w[j].meta = 0; }
+      else load_pair(t.slots + sl[j], v[j], w[j]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < R; j++) { sl[j] = sl0[j]; v[j] = load_slot(t.slots + sl[j]); w[j].key = kEmptyKey; w[j].meta = 0; }
+  }
+  unsigned bal[R];
+  uint32_t total = 0;
+#pragma unroll
+  for (int j = 0; j < R; j++) {
+    bool m;
+    if (k[j] == kEmptyKey) m = in[j] && v[j].key != 0;
+    else if (v[j].key == k[j]) m = true;
+    else if (t.pair_home && w[j].key == k[j]) { v[j] = w[j]; m = true; }
+    else if (v[j].key == kEmptyKey || (t.pair_home && w[j].key == kEmptyKey)) m = false;
+    else {
+      // the home slots hold other keys: continue the linear probe behind them (rare at the configured load factor)
+      sl[j] += t.pair_home ? 2 : 1;
+      if (sl[j] >= t.nslots) sl[j] = 0;
+      v[j] = load_slot(t.slots + sl[j]);
+      while (v[j].key != k[j] && v[j].key != kEmptyKey) {
+        if (++sl[j] == t.nslots) sl[j] = 0;
+        v[j] = load_slot(t.slots + sl[j]);
+      }
+      m = v[j].key == k[j];
+    }
+    bal[j] = __ballot_sync(0xffffffffu, m);
+    total += __popc(bal[j]);
+  }
+  unsigned long long wbase = 0;
+  if (lane == 0 && total) wbase = atomicAdd(out_cursor, (unsigned long long)total);
+  wbase = __shfl_sync(0xffffffffu, wbase, 0);
+#pragma unroll
+  for (int j = 0; j < R; j++) {
+    if ((bal[j] >> lane) & 1u) {
+      const unsigned long long o = wbase + __popc(bal[j] & ((1u << lane) - 1));
+#pragma unroll
+      for (int d = 0; d < NKD; d++) __stcs(out.key_dst[d] + o, (unsigned long long)k[j]);
+#pragma unroll
+      for (int d = 0; d < NMD; d++) __stcs(out.meta_dst[d] + o, v[j].meta);
+#pragma unroll
+      for (int c = 0; c < NPC; c++) __stcs(out.pdst[c] + o, pv[j][c]);
+    }
+    wbase += __popc(bal[j]);
+  }
+}
+
+// warp-autonomous: no shared memory, no block barrier; each warp owns tiles of 32×R rows
+template <int R, int NPC, int NKD, int NMD>
 __global__ void __launch_bounds__(256)
 k_probe_inner_u1_w(const int64_t* __restrict__ pkey, int64_t n, TableView t, FastOut out,
                    unsigned long long* __restrict__ out_cursor) {
@@ -386,73 +448,34 @@ k_probe_inner_u1_w(const int64_t* __restrict__ pkey, int64_t n, TableView t, Fas
   const int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t tile_rows = 32 * R;
   const int64_t ntiles = (n + tile_rows - 1) / tile_rows;
-  unsigned long long pol = 0;
-  if (EVICT_LAST) pol = policy_evict_last();
   for (int64_t tile = warp_id; tile < ntiles; tile += warps_total) {
     const int64_t base = tile * tile_rows;
     int64_t k[R];
     unsigned long long pv[R][NPC > 0 ? NPC : 1];
-    Slot v[R];
-    unsigned long long s[R];
+    unsigned long long sl[R];
+    bool in[R];
 #pragma unroll
     for (int j = 0; j < R; j++) {
       int64_t i = base + j * 32 + lane;
-      k[j] = i < n ? __ldcs(pkey + i) : kEmptyKey;
-    }
-#pragma unroll
-    for (int j = 0; j < R; j++) {
-      s[j] = (k[j] == kEmptyKey) ? t.nslots : home_slot(hash64((uint64_t)k[j]), t.nslots, t.pair_home);
-      v[j] = EVICT_LAST ? load_slot_policy(t.slots + s[j], pol) : load_slot(t.slots + s[j]);
+      in[j] = i < n;
+      k[j] = in[j] ? __ldcs(pkey + i) : kEmptyKey;
     }
 #pragma unroll
     for (int j = 0; j < R; j++) {
       int64_t i = base + j * 32 + lane;
+      sl[j] = (k[j] == kEmptyKey) ? t.nslots : home_slot(hash64((uint64_t)k[j]), t.nslots, t.pair_home);
 #pragma unroll
-      for (int c = 0; c < NPC; c++) pv[j][c] = i < n ? __ldcs(out.psrc[c] + i) : 0ull;
+      for (int c = 0; c < NPC; c++) pv[j][c] = in[j] ? __ldcs(out.psrc[c] + i) : 0ull;
     }
-    unsigned bal[R];
-    uint32_t total = 0;
-#pragma unroll
-    for (int j = 0; j < R; j++) {
-      int64_t i = base + j * 32 + lane;
-      bool m;
-      if (k[j] == kEmptyKey) m = (i < n) && v[j].key != 0;
-      else {
-        while (v[j].key != k[j] && v[j].key != kEmptyKey) {
-          if (++s[j] == t.nslots) s[j] = 0;
-          v[j] = load_slot(t.slots + s[j]);
-        }
-        m = v[j].key == k[j];
-      }
-      bal[j] = __ballot_sync(0xffffffffu, m);
-      total += __popc(bal[j]);
-    }
-    unsigned long long wbase = 0;
-    if (lane == 0 && total) wbase = atomicAdd(out_cursor, (unsigned long long)total);
-    wbase = __shfl_sync(0xffffffffu, wbase, 0);
-#pragma unroll
-    for (int j = 0; j < R; j++) {
-      if ((bal[j] >> lane) & 1u) {
-        unsigned long long o = wbase + __popc(bal[j] & ((1u << lane) - 1));
-        for (int d = 0; d < out.n_key_dst; d++) __stcs(out.key_dst[d] + o, (unsigned long long)k[j]);
-        for (int d = 0; d < out.n_meta_dst; d++) __stcs(out.meta_dst[d] + o, v[j].meta);
-#pragma unroll
-        for (int c = 0; c < NPC; c++)
-          for (int d = 0; d < out.n_pdst[c]; d++) __stcs(out.pdst[c][d] + o, pv[j][c]);
-      }
-      wbase += __popc(bal[j]);
-    }
+    probe_rows_u1<R, NPC, NKD, NMD>(k, pv, sl, in, t, out, out_cursor, lane);
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// probe — fused fast path, TMA-fed: the streamed inputs (probe key + payload columns) arrive in shared memory
-// through a STAGES-deep ring of 1024-row tiles filled by cp.async.bulk (one elected thread, mbarrier completion),
-// so the only LSU traffic left is the random 16-byte table gathers and the output stores.  Full tiles only; the
-// tail (< 1024 rows) is finished by k_probe_inner_u1_w on the same output cursor.
-// ---------------------------------------------------------------------------------------------
+// TMA-fed: the streamed inputs (probe key + payload columns) arrive in shared memory through a STAGES-deep ring of
+// 1024-row tiles filled by cp.async.bulk (one elected thread, mbarrier completion).  Full tiles only; the tail
+// (< 1024 rows) is finished by k_probe_inner_u1_w on the same output cursor.
 #define TG_PROBE_TILE 1024
-template <int NPC, int STAGES, bool EVICT_LAST>
+template <int NPC, int NKD, int NMD, int STAGES>
 __global__ void __launch_bounds__(256)
 k_probe_inner_u1_tma(const int64_t* __restrict__ pkey, int64_t ntiles, TableView t, FastOut out,
                      unsigned long long* __restrict__ out_cursor) {
@@ -462,8 +485,6 @@ k_probe_inner_u1_tma(const int64_t* __restrict__ pkey, int64_t ntiles, TableView
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * COLS * T * 8);
   const int tid = threadIdx.x, lane = tid & 31;
   const unsigned long long pol_stream = l2_policy_evict_first();
-  unsigned long long pol_table = 0;
-  if (EVICT_LAST) pol_table = l2_policy_evict_last();
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
     mbar_fence_init();
@@ -488,8 +509,12 @@ k_probe_inner_u1_tma(const int64_t* __restrict__ pkey, int64_t ntiles, TableView
     const unsigned long long* st = ring + (size_t)s * COLS * T;
     int64_t k[R];
     unsigned long long pv[R][NPC > 0 ? NPC : 1];
+    unsigned long long sl[R];
+    bool in[R];
+    unsigned long long dep = 0;
 #pragma unroll
     for (int j = 0; j < R; j++) {
+      in[j] = true;
       k[j] = (int64_t)st[j * 256 + tid];
 #pragma unroll
       for (int c = 0; c < NPC; c++) pv[j][c] = st[(size_t)(1 + c) * T + j * 256 + tid];
@@ -498,9 +523,6 @@ k_probe_inner_u1_tma(const int64_t* __restrict__ pkey, int64_t ntiles, TableView
     // LDS, and on a busy LSU (other warps' uncoalesced gathers queue for microseconds) the refill issued right after
     // the barrier can land first.  Consuming every loaded value (hash of the keys, XOR of the payloads) before the
     // barrier makes the scoreboard wait for them.
-    Slot v[R];
-    unsigned long long sl[R];
-    unsigned long long dep = 0;
 #pragma unroll
     for (int j = 0; j < R; j++) {
       sl[j] = (k[j] == kEmptyKey) ? t.nslots : home_slot(hash64((uint64_t)k[j]), t.nslots, t.pair_home);
@@ -510,55 +532,7 @@ k_probe_inner_u1_tma(const int64_t* __restrict__ pkey, int64_t ntiles, TableView
     if (NPC > 0 && dep == 0x9E3779B97F4A7C15ull && sl[0] == ~0ull) out_cursor[1] = dep;   // never true; keeps `dep` alive
     __syncthreads();                 // the whole CTA has drained stage s into registers
     if (tid == 0) issue(it + STAGES);
-    Slot w[R];                       // second slot of the home pair (pair_home tables)
-    if (t.pair_home) {
-#pragma unroll
-      for (int j = 0; j < R; j++) {
-        if (k[j] == kEmptyKey) { v[j] = load_slot(t.slots + sl[j]); w[j].key = kEmptyKey; w[j].meta = 0; }
-        else load_pair(t.slots + sl[j], v[j], w[j]);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < R; j++) { v[j] = EVICT_LAST ? load_slot_policy(t.slots + sl[j], pol_table) : load_slot(t.slots + sl[j]); w[j].key = kEmptyKey; w[j].meta = 0; }
-    }
-    unsigned bal[R];
-    uint32_t total = 0;
-#pragma unroll
-    for (int j = 0; j < R; j++) {
-      bool m;
-      if (k[j] == kEmptyKey) m = v[j].key != 0;
-      else if (v[j].key == k[j]) m = true;
-      else if (t.pair_home && w[j].key == k[j]) { v[j] = w[j]; m = true; }
-      else if (v[j].key == kEmptyKey || (t.pair_home && w[j].key == kEmptyKey)) m = false;
-      else {
-        // both home slots hold other keys: continue the linear probe behind them (rare at the configured load factor)
-        sl[j] += t.pair_home ? 2 : 1;
-        if (sl[j] >= t.nslots) sl[j] = 0;
-        v[j] = load_slot(t.slots + sl[j]);
-        while (v[j].key != k[j] && v[j].key != kEmptyKey) {
-          if (++sl[j] == t.nslots) sl[j] = 0;
-          v[j] = load_slot(t.slots + sl[j]);
-        }
-        m = v[j].key == k[j];
-      }
-      bal[j] = __ballot_sync(0xffffffffu, m);
-      total += __popc(bal[j]);
-    }
-    unsigned long long wbase = 0;
-    if (lane == 0 && total) wbase = atomicAdd(out_cursor, (unsigned long long)total);
-    wbase = __shfl_sync(0xffffffffu, wbase, 0);
-#pragma unroll
-    for (int j = 0; j < R; j++) {
-      if ((bal[j] >> lane) & 1u) {
-        unsigned long long o = wbase + __popc(bal[j] & ((1u << lane) - 1));
-        for (int d = 0; d < out.n_key_dst; d++) __stcs(out.key_dst[d] + o, (unsigned long long)k[j]);
-        for (int d = 0; d < out.n_meta_dst; d++) __stcs(out.meta_dst[d] + o, v[j].meta);
-#pragma unroll
-        for (int c = 0; c < NPC; c++)
-          for (int d = 0; d < out.n_pdst[c]; d++) __stcs(out.pdst[c][d] + o, pv[j][c]);
-      }
-      wbase += __popc(bal[j]);
-    }
+    probe_rows_u1<R, NPC, NKD, NMD>(k, pv, sl, in, t, out, out_cursor, lane);
   }
 }
 
