@@ -576,7 +576,7 @@ static bool fast_path_ok(const tg_join* j, const DevCols& pview) {
 }
 
 // ---- fast-path launch tuning (env overrides are for A/B sweeps on the GPU box; defaults are the measured best) ----
-struct ProbeTuning { int variant; int R; int evict_last; int ctas_per_sm; int partition; int parts; int part_min_mb; int tma; int stages; int tma_ctas; };
+struct ProbeTuning { int variant; int R; int evict_last; int ctas_per_sm; int partition; int parts; int part_min_mb; int tma; int stages; int tma_ctas; int cta_agg; };
 static ProbeTuning probe_tuning() {
   ProbeTuning t;
   t.variant = env_int("TG_PROBE_VARIANT", 1);      // 0: CTA-tile kernel (shared-memory offsets), 1: warp-autonomous kernel
@@ -590,6 +590,7 @@ static ProbeTuning probe_tuning() {
   t.tma = env_int("TG_PROBE_TMA", 0);               // TMA-fed kernels (cp.async.bulk ring) for the streamed inputs
   t.stages = env_int("TG_PROBE_STAGES", 4);
   t.tma_ctas = env_int("TG_PROBE_TMA_CTAS", 3);
+  t.cta_agg = env_int("TG_PROBE_CTA_AGG", 1);        // one output-cursor atomic per CTA tile (TMA kernel)
   return t;
 }
 
@@ -647,12 +648,16 @@ struct LaunchTma {
     int grid = (int)std::min<int64_t>(ntiles, (int64_t)j->nsm * t.tma_ctas);
     if (t.stages >= 4) {
       size_t smem = (size_t)4 * (1 + NPC) * TG_PROBE_TILE * 8 + 4 * 8 + 16;
-      TG_CUDA(cudaFuncSetAttribute(k_probe_inner_u1_tma<NPC, NKD, NMD, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_probe_inner_u1_tma<NPC, NKD, NMD, 4><<<grid, 256, smem, j->stream>>>(pkey, ntiles, j->tv, fo, cur);
+      TG_CUDA(cudaFuncSetAttribute(k_probe_inner_u1_tma<NPC, NKD, NMD, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_probe_inner_u1_tma<NPC, NKD, NMD, 4, false><<<grid, 256, smem, j->stream>>>(pkey, ntiles, j->tv, fo, cur);
+    } else if (t.cta_agg) {
+      size_t smem = (size_t)2 * (1 + NPC) * TG_PROBE_TILE * 8 + 2 * 8 + 16;
+      TG_CUDA(cudaFuncSetAttribute(k_probe_inner_u1_tma<NPC, NKD, NMD, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_probe_inner_u1_tma<NPC, NKD, NMD, 2, true><<<grid, 256, smem, j->stream>>>(pkey, ntiles, j->tv, fo, cur);
     } else {
       size_t smem = (size_t)2 * (1 + NPC) * TG_PROBE_TILE * 8 + 2 * 8 + 16;
-      TG_CUDA(cudaFuncSetAttribute(k_probe_inner_u1_tma<NPC, NKD, NMD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_probe_inner_u1_tma<NPC, NKD, NMD, 2><<<grid, 256, smem, j->stream>>>(pkey, ntiles, j->tv, fo, cur);
+      TG_CUDA(cudaFuncSetAttribute(k_probe_inner_u1_tma<NPC, NKD, NMD, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_probe_inner_u1_tma<NPC, NKD, NMD, 2, false><<<grid, 256, smem, j->stream>>>(pkey, ntiles, j->tv, fo, cur);
     }
     return TG_OK;
   }

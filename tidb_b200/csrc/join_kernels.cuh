@@ -380,7 +380,7 @@ __device__ __forceinline__ Slot load_slot_policy(const Slot* p, unsigned long lo
 
 // R rows per lane, keys (and prefetched payload) already in registers: gather, resolve, compact, store.
 // `in[j]` = row j of this lane exists (tail tiles).
-template <int R, int NPC, int NKD, int NMD>
+template <int R, int NPC, int NKD, int NMD, bool CTA_AGG>
 __device__ __forceinline__ void probe_rows_u1(const int64_t (&k)[R], const unsigned long long (&pv)[R][NPC > 0 ? NPC : 1],
                                               const unsigned long long (&sl0)[R], const bool (&in)[R], const TableView& t,
                                               const FastOut& out, unsigned long long* __restrict__ out_cursor, int lane) {
@@ -421,8 +421,27 @@ __device__ __forceinline__ void probe_rows_u1(const int64_t (&k)[R], const unsig
     total += __popc(bal[j]);
   }
   unsigned long long wbase = 0;
-  if (lane == 0 && total) wbase = atomicAdd(out_cursor, (unsigned long long)total);
-  wbase = __shfl_sync(0xffffffffu, wbase, 0);
+  if (CTA_AGG) {
+    // one atomic per CTA tile instead of one per warp: every atomic of a launch hits the SAME address and the L2
+    // serialises them (781 K per 100 M rows with per-warp reservation)
+    __shared__ uint32_t s_wtot[8];
+    __shared__ unsigned long long s_cta_base;
+    const int warp = threadIdx.x >> 5;
+    if (lane == 0) s_wtot[warp] = total;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t sum = 0;
+#pragma unroll
+      for (int q = 0; q < 8; q++) sum += s_wtot[q];
+      s_cta_base = sum ? atomicAdd(out_cursor, (unsigned long long)sum) : 0ull;
+    }
+    __syncthreads();
+    wbase = s_cta_base;
+    for (int q = 0; q < warp; q++) wbase += s_wtot[q];
+  } else {
+    if (lane == 0 && total) wbase = atomicAdd(out_cursor, (unsigned long long)total);
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+  }
 #pragma unroll
   for (int j = 0; j < R; j++) {
     if ((bal[j] >> lane) & 1u) {
@@ -467,7 +486,7 @@ k_probe_inner_u1_w(const int64_t* __restrict__ pkey, int64_t n, TableView t, Fas
 #pragma unroll
       for (int c = 0; c < NPC; c++) pv[j][c] = in[j] ? __ldcs(out.psrc[c] + i) : 0ull;
     }
-    probe_rows_u1<R, NPC, NKD, NMD>(k, pv, sl, in, t, out, out_cursor, lane);
+    probe_rows_u1<R, NPC, NKD, NMD, false>(k, pv, sl, in, t, out, out_cursor, lane);
   }
 }
 
@@ -475,7 +494,7 @@ k_probe_inner_u1_w(const int64_t* __restrict__ pkey, int64_t n, TableView t, Fas
 // 1024-row tiles filled by cp.async.bulk (one elected thread, mbarrier completion).  Full tiles only; the tail
 // (< 1024 rows) is finished by k_probe_inner_u1_w on the same output cursor.
 #define TG_PROBE_TILE 1024
-template <int NPC, int NKD, int NMD, int STAGES>
+template <int NPC, int NKD, int NMD, int STAGES, bool CTA_AGG>
 __global__ void __launch_bounds__(256)
 k_probe_inner_u1_tma(const int64_t* __restrict__ pkey, int64_t ntiles, TableView t, FastOut out,
                      unsigned long long* __restrict__ out_cursor) {
@@ -532,7 +551,7 @@ k_probe_inner_u1_tma(const int64_t* __restrict__ pkey, int64_t ntiles, TableView
     if (NPC > 0 && dep == 0x9E3779B97F4A7C15ull && sl[0] == ~0ull) out_cursor[1] = dep;   // never true; keeps `dep` alive
     __syncthreads();                 // the whole CTA has drained stage s into registers
     if (tid == 0) issue(it + STAGES);
-    probe_rows_u1<R, NPC, NKD, NMD>(k, pv, sl, in, t, out, out_cursor, lane);
+    probe_rows_u1<R, NPC, NKD, NMD, CTA_AGG>(k, pv, sl, in, t, out, out_cursor, lane);
   }
 }
 
