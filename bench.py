@@ -300,7 +300,7 @@ def run_gpu(args):
         achieved = BYTES_PER_PROBE_ROW * npb / (ms_step * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": args.ncu_traffic_bytes, "peak_source": peak_src,
-                "kernel": "k_probe_inner_u1<4>", "algorithmic_bytes_per_launch": BYTES_PER_PROBE_ROW * npb,
+                "kernel": "k_probe_inner_u1_w<4,1,2,1>", "algorithmic_bytes_per_launch": BYTES_PER_PROBE_ROW * npb,
                 "read_only_frac": 32 * npb / (ms_step * 1e-3) / 1e9 / hbm_peak}
 
     # ---- e2e: host buffers through tg_join_probe_push / tg_join_next (N = 1 path; per rank at N > 1) ---------

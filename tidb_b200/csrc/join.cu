@@ -252,7 +252,7 @@ static int setup(tg_join* j, const tg_join_desc* d) {
   j->n_out = (int)j->out_elem.size();
   if (j->n_out > TG_MAX_OUT) return fail(TG_ERR_UNSUPPORTED, "too many output columns");
   j->device = d->device;
-  j->load_factor = (d->load_factor > 0.05 && d->load_factor <= 0.95) ? d->load_factor : 0.5;
+  j->load_factor = (d->load_factor > 0.05 && d->load_factor <= 0.95) ? d->load_factor : 0.4;   // measured best (profiles/r1_sweep_probe.jsonl)
   return TG_OK;
 }
 
