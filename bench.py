@@ -296,10 +296,16 @@ def run_gpu(args):
 
     # kernel-only duration for the roofline at N = 1 (the step IS the probe kernel + an 8-byte memset)
     roof = None
+    traffic = args.ncu_traffic_bytes
+    if traffic is None:
+        try:   # per-launch DRAM bytes of the committed ncu --set full capture of this kernel
+            traffic = float(json.load(open(os.path.join(ROOT, "profiles", "r1_probe_final_traffic.json")))["dram_bytes_per_launch"])
+        except Exception:
+            traffic = None
     if world == 1:
         achieved = BYTES_PER_PROBE_ROW * npb / (ms_step * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": args.ncu_traffic_bytes, "peak_source": peak_src,
+                "traffic": traffic, "peak_source": peak_src,
                 "kernel": "k_probe_inner_u1_w<4,1,2,1>", "algorithmic_bytes_per_launch": BYTES_PER_PROBE_ROW * npb,
                 "read_only_frac": 32 * npb / (ms_step * 1e-3) / 1e9 / hbm_peak}
 
