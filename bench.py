@@ -396,17 +396,34 @@ def run_e2e(args, lib, abi, torch, dev, local, rank, world, bk, bv, pk, pv, barr
     mch = abi.TgMutChunk(); mch.ncols = 4; mch.cols = C.cast(mc, C.POINTER(abi.TgMutColumn)); mch.capacity_rows = chunk_rows
 
     def one_pass():
-        """a fresh probe of the whole probe side: push every chunk, drain Next between pushes"""
+        """a fresh probe of the whole probe side.  Two host threads, like the reference's probe fetcher goroutine and
+        the consumer of joinResultCh: one pushes the pinned probe chunks (H2D + kernels), the other sits in
+        tg_join_next_wait and receives the joined columns (D2H) — PCIe runs full duplex."""
+        err = []
+
+        def pusher():
+            try:
+                for lo in range(0, npb, chunk_rows):
+                    ck = host_chunk(hp, lo, min(chunk_rows, npb - lo))
+                    abi.check(lib.tg_join_probe_push(h, C.byref(ck)))
+                abi.check(lib.tg_join_probe_finish(h))
+            except Exception as e:   # noqa: BLE001
+                err.append(e)
+                lib.tg_join_probe_finish(h)
+
+        th = threading.Thread(target=pusher)
+        th.start()
         got = 0
         n = C.c_int64(0)
-        for lo in range(0, npb, chunk_rows):
-            ck = host_chunk(hp, lo, min(chunk_rows, npb - lo))
-            abi.check(lib.tg_join_probe_push(h, C.byref(ck)))
-            while True:
-                abi.check(lib.tg_join_next(h, C.byref(mch), C.c_int64(chunk_rows), C.byref(n)))
-                if n.value == 0:
-                    break
-                got += n.value
+        while True:
+            abi.check(lib.tg_join_next_wait(h, C.byref(mch), C.c_int64(chunk_rows), C.byref(n)))
+            if n.value == 0:
+                break
+            got += n.value
+        th.join()
+        if err:
+            raise err[0]
+        abi.check(lib.tg_join_probe_rewind(h))
         return got
 
     for _ in range(max(1, args.warmup // 2)):
@@ -431,8 +448,7 @@ def run_e2e(args, lib, abi, torch, dev, local, rank, world, bk, bv, pk, pv, barr
     sec_step = float(tt.item()) / steps
     return {"value": npb * world / sec_step, "unit": "rows/s", "h2d_bytes_per_step": 16 * npb, "d2h_bytes_per_step": 32 * npb,
             "ms_per_step": sec_step * 1e3, "steps": steps, "chunk_rows": chunk_rows,
-            "path": "tg_join_probe_push(host pinned chunk) -> kernels -> tg_join_next(host pinned buffers); per rank its own shard, no exchange"
-                    if world > 1 else "tg_join_probe_push(host pinned chunk) -> kernels -> tg_join_next(host pinned buffers)",
+            "path": "thread A: tg_join_probe_push(host pinned 4M-row chunks) -> kernels; thread B: tg_join_next_wait -> D2H into host pinned buffers",
             "timing": "host wall clock around the passes, device synchronised on both sides (host work is part of the path)"}
 
 

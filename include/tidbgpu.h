@@ -211,6 +211,13 @@ int tg_join_probe_finish(tg_join* j);
 /* HashJoinV2Exec.Next (hash_join_v2.go:1161): fill at most min(max_rows, out->capacity_rows)
  * joined rows; *nrows == 0 means EOF (only after tg_join_probe_finish).                       */
 int tg_join_next(tg_join* j, tg_mut_chunk* out, int64_t max_rows, int64_t* nrows);
+/* Same, but blocks until rows are available or the probe side is finished (then 0 = EOF).  One thread may sit in
+ * tg_join_next_wait while another pushes probe chunks — the reference's probe fetcher goroutine vs the consumer of
+ * joinResultCh (hash_join_v2.go:840, :1176); results are copied on their own stream, so D2H overlaps the next H2D. */
+int tg_join_next_wait(tg_join* j, tg_mut_chunk* out, int64_t max_rows, int64_t* nrows);
+/* Start another probe pass against the SAME built table (results not yet fetched are dropped).  Mirrors re-execution
+ * of the probe side under Apply with a cached build side; not available for joins that scan the build side. */
+int tg_join_probe_rewind(tg_join* j);
 /* HashJoinV2Exec.Close (hash_join_v2.go:647); idempotent                                     */
 int tg_join_close(tg_join* j);
 

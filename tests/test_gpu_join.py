@@ -234,3 +234,52 @@ def test_fused_probe_variants_forced(env, monkeypatch):
     assert np.array_equal(got[0], pk[got[1]]) and np.array_equal(got[2], got[0])     # keys travel with their row
     exp_pay = (order[pos] * 3)[got[1]]
     assert np.array_equal(got[3], exp_pay)                                           # and with the right build payload
+
+
+def test_concurrent_push_and_next_wait_and_rewind():
+    # one thread pushes probe chunks while another blocks in tg_join_next_wait (the reference's probe fetcher goroutine vs
+    # the consumer of joinResultCh, hash_join_v2.go:840/:1176); then a second pass after tg_join_probe_rewind
+    import threading
+    from tidb_b200.chunk import MutChunk
+    lib = abi.load_lib()
+    build, probe = _config1(150_000, 3_000_000)
+    plan = JoinPlan(abi.JOIN_INNER, [INT_NN, INT_NN], [INT_NN, INT_NN], [0], [0])
+    desc, keep = plan.to_struct()
+    h = C.c_void_p()
+    abi.check(lib.tg_join_open(C.byref(desc), C.byref(h)))
+    bs = build.to_struct()
+    abi.check(lib.tg_join_build_push(h, C.byref(bs)))
+    abi.check(lib.tg_join_build_finish(h))
+    chunks = probe.split(1 << 18)
+    for _pass in range(2):
+        errs = []
+
+        def pusher():
+            try:
+                for c in chunks:
+                    cs = c.to_struct()
+                    abi.check(lib.tg_join_probe_push(h, C.byref(cs)))
+                abi.check(lib.tg_join_probe_finish(h))
+            except Exception as e:   # noqa: BLE001
+                errs.append(e)
+                lib.tg_join_probe_finish(h)
+
+        th = threading.Thread(target=pusher)
+        th.start()
+        out = MutChunk([8, 8, 8, 8], 1 << 18)
+        rows, parts = 0, [[], [], [], []]
+        n = C.c_int64(0)
+        while True:
+            abi.check(lib.tg_join_next_wait(h, C.byref(out.struct), C.c_int64(1 << 18), C.byref(n)))
+            if n.value == 0:
+                break
+            rows += n.value
+            for i, (v, _) in enumerate(out.columns(n.value)):
+                parts[i].append(v)
+        th.join()
+        assert not errs, errs
+        assert rows == 3_000_000
+        got = [np.concatenate(p) for p in parts]
+        assert np.array_equal(np.sort(got[1]), np.arange(3_000_000)) and np.array_equal(got[3], got[0] * 7)
+        abi.check(lib.tg_join_probe_rewind(h))
+    lib.tg_join_close(h)

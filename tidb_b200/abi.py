@@ -105,7 +105,7 @@ EXPORTED_SYMBOLS = [
     "tg_host_alloc", "tg_host_free", "tg_dev_alloc", "tg_dev_free", "tg_memcpy_h2d", "tg_memcpy_d2h",
     "tg_device_synchronize",
     "tg_join_supported", "tg_join_open", "tg_join_build_push", "tg_join_build_push_dev",
-    "tg_join_build_finish", "tg_join_probe_push", "tg_join_probe_finish", "tg_join_next",
+    "tg_join_build_finish", "tg_join_probe_push", "tg_join_probe_finish", "tg_join_next", "tg_join_next_wait", "tg_join_probe_rewind",
     "tg_join_close", "tg_join_probe_dev", "tg_join_get_stats",
     "tg_agg_supported", "tg_agg_open", "tg_agg_push", "tg_agg_push_dev", "tg_agg_finish",
     "tg_agg_next", "tg_agg_close", "tg_agg_result_dev", "tg_agg_get_stats",

@@ -4,6 +4,7 @@
 #include <memory>
 #include <deque>
 #include <algorithm>
+#include <condition_variable>
 #include "join_kernels.cuh"
 #include "partition_kernels.cuh"
 
@@ -72,10 +73,13 @@ struct ResultBatch {
 using namespace tg;
 
 struct tg_join {
-  std::mutex mu;
+  std::mutex mu;                     // build / probe-input side (one pushing thread)
+  std::mutex res_mu;                 // result queue (one pulling thread may run concurrently with the pusher, like the
+  std::condition_variable res_cv;    //   reference's probe fetcher vs joinResultCh consumer, hash_join_v2.go:840 / :1176)
   std::atomic<bool> closed{false};
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t d2h_stream = nullptr; // tg_join_next copies results on its own stream: D2H overlaps the next H2D + probe
   bool own_stream = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int nsm = 148;
@@ -112,8 +116,10 @@ struct tg_join {
   std::unique_ptr<DevBuf> part_cols[1 + TG_FAST_MAX_PCOLS];   // partitioned copies of the probe key and payload columns
   std::vector<std::unique_ptr<DevBuf>> tmp_valid;
   std::deque<std::unique_ptr<ResultBatch>> results;
+  std::vector<std::unique_ptr<ResultBatch>> free_batches;   // recycled (cudaFree would synchronise the whole device)
   std::unique_ptr<ResultBatch> dev_result;      // tg_join_probe_dev output (reused across calls)
-  bool probe_finished = false;
+  std::atomic<bool> probe_finished{false};
+  std::atomic<int64_t> d2h_bytes{0};
   // small-Next window
   PinBuf win;
   int64_t win_lo = 0, win_hi = 0;
@@ -702,7 +708,7 @@ static int probe_device(tg_join* j, const DevCols& pview, int64_t n, ResultBatch
     TG_TRY(ensure_result(j, rb, rb.rows + n, rb.rows > 0, rb.rows));
     OutCols oc{};
     fill_outspec_probe(j, oc);
-    for (int c = 0; c < j->n_out; c++) { oc.data[c] = rb.cols[c]->as<uint8_t>() + (size_t)rb.rows * 8; oc.valid[c] = nullptr; rb.bitmaps[c]->release(); }
+    for (int c = 0; c < j->n_out; c++) { oc.data[c] = rb.cols[c]->as<uint8_t>() + (size_t)rb.rows * 8; oc.valid[c] = nullptr; if (rb.bitmaps[c]->p) rb.bitmaps[c]->release(); }
     unsigned long long* cur = j->out_cursor.as<unsigned long long>();
     TG_CUDA(cudaMemsetAsync(cur, 0, 8, j->stream));
     if (n > 0) {
@@ -885,10 +891,27 @@ static int scan_build_side(tg_join* j, ResultBatch& rb) {
   return TG_OK;
 }
 
+static std::unique_ptr<ResultBatch> new_batch(tg_join* j) {
+  std::lock_guard<std::mutex> lk(j->res_mu);
+  if (!j->free_batches.empty()) {
+    std::unique_ptr<ResultBatch> rb = std::move(j->free_batches.back());
+    j->free_batches.pop_back();
+    rb->rows = 0; rb->consumed = 0;
+    return rb;
+  }
+  return std::unique_ptr<ResultBatch>(new ResultBatch());
+}
+
+static void queue_result(tg_join* j, std::unique_ptr<ResultBatch> rb) {
+  if (rb->rows <= 0) { std::lock_guard<std::mutex> lk(j->res_mu); j->free_batches.push_back(std::move(rb)); return; }
+  { std::lock_guard<std::mutex> lk(j->res_mu); j->results.push_back(std::move(rb)); }
+  j->res_cv.notify_all();
+}
+
 static int flush_probe_stage(tg_join* j) {
   if (j->pstage.rows == 0) return TG_OK;
   TG_TRY(stage_to_device(j, j->pstage, j->probe, j->pcols_dev));
-  std::unique_ptr<ResultBatch> rb(new ResultBatch());
+  std::unique_ptr<ResultBatch> rb = new_batch(j);
   DevCols pview = j->pcols_dev.view(j->probe);
   TG_CUDA(cudaEventRecord(j->ev0, j->stream));
   TG_TRY(probe_device(j, pview, j->pstage.rows, *rb, true));
@@ -896,7 +919,7 @@ static int flush_probe_stage(tg_join* j) {
   TG_CUDA(cudaStreamSynchronize(j->stream));
   float ms = 0; cudaEventElapsedTime(&ms, j->ev0, j->ev1); j->stats.probe_ms += ms;
   j->pstage.reset();
-  if (rb->rows > 0) j->results.push_back(std::move(rb));
+  queue_result(j, std::move(rb));
   return TG_OK;
 }
 
@@ -934,6 +957,7 @@ int tg_join_open(const tg_join_desc* desc, tg_join** out) {
   else { TG_CUDA(cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking)); j->own_stream = true; }
   TG_CUDA(cudaEventCreate(&j->ev0));
   TG_CUDA(cudaEventCreate(&j->ev1));
+  TG_CUDA(cudaStreamCreateWithFlags(&j->d2h_stream, cudaStreamNonBlocking));
   j->nsm = device_sm_count(j->device);
   {
     // L2 fetch granularity (cudaLimitMaxL2FetchGranularity): left at the device default.  Measured (tools/sweep_probe.py,
@@ -976,21 +1000,21 @@ int tg_join_build_finish(tg_join* j) {
 int tg_join_probe_push(tg_join* j, const tg_chunk* chk) {
   TG_LOCK(j);
   if (!j->built) return fail(TG_ERR_STATE, "probe_push before build_finish");
-  if (j->probe_finished) return fail(TG_ERR_STATE, "probe_push after probe_finish");
+  if (j->probe_finished.load()) return fail(TG_ERR_STATE, "probe_push after probe_finish");
   TG_TRY(validate_chunk(j->probe, chk));
   int64_t n = chunk_logical_rows(chk);
   if (n == 0) return TG_OK;
   if (!chk->sel && n >= kDirectPushRows) {
     TG_TRY(flush_probe_stage(j));
     TG_TRY(chunk_to_device(j, chk, j->probe, j->pcols_dev));
-    std::unique_ptr<ResultBatch> rb(new ResultBatch());
+    std::unique_ptr<ResultBatch> rb = new_batch(j);
     DevCols pview = j->pcols_dev.view(j->probe);
     TG_CUDA(cudaEventRecord(j->ev0, j->stream));
     TG_TRY(probe_device(j, pview, n, *rb, true));
     TG_CUDA(cudaEventRecord(j->ev1, j->stream));
     TG_CUDA(cudaStreamSynchronize(j->stream));
     float ms = 0; cudaEventElapsedTime(&ms, j->ev0, j->ev1); j->stats.probe_ms += ms;
-    if (rb->rows > 0) j->results.push_back(std::move(rb));
+    queue_result(j, std::move(rb));
     return TG_OK;
   }
   TG_TRY(stage_append(j->pstage, j->probe, chk));
@@ -1001,28 +1025,40 @@ int tg_join_probe_push(tg_join* j, const tg_chunk* chk) {
 int tg_join_probe_finish(tg_join* j) {
   TG_LOCK(j);
   if (!j->built) return fail(TG_ERR_STATE, "probe_finish before build_finish");
-  if (j->probe_finished) return TG_OK;
+  if (j->probe_finished.load()) return TG_OK;
   TG_TRY(flush_probe_stage(j));
   if (j->need_scan) {
-    std::unique_ptr<ResultBatch> rb(new ResultBatch());
+    std::unique_ptr<ResultBatch> rb = new_batch(j);
     TG_TRY(scan_build_side(j, *rb));
-    if (rb->rows > 0) j->results.push_back(std::move(rb));
+    queue_result(j, std::move(rb));
   }
-  j->probe_finished = true;
+  { std::lock_guard<std::mutex> lk(j->res_mu); j->probe_finished.store(true); }
+  j->res_cv.notify_all();
   return TG_OK;
 }
 
-int tg_join_next(tg_join* j, tg_mut_chunk* out, int64_t max_rows, int64_t* nrows) {
-  TG_LOCK(j);
+static int join_next_impl(tg_join* j, tg_mut_chunk* out, int64_t max_rows, int64_t* nrows, bool wait) {
+  if (!j) return fail(TG_ERR_INVALID, "handle is NULL");
+  if (j->closed.load()) return fail(TG_ERR_CANCELLED, "handle is closed");
   if (!out || !nrows) return fail(TG_ERR_INVALID, "out / nrows is NULL");
   *nrows = 0;
   if (out->ncols != j->n_out) return fail(TG_ERR_INVALID, "output chunk column count does not match the join schema");
   for (int c = 0; c < j->n_out; c++) if (out->cols[c].elem_len != j->out_elem[c]) return fail(TG_ERR_INVALID, "output column elem_len mismatch");
-  while (!j->results.empty() && j->results.front()->consumed >= j->results.front()->rows) {
-    if (j->win_batch == j->results.front().get()) { j->win_batch = nullptr; j->win_lo = j->win_hi = 0; }
-    j->results.pop_front();
+  std::unique_lock<std::mutex> lock__(j->res_mu);
+  tg::DeviceGuard guard__(j->device);
+  if (!guard__.ok) return fail(TG_ERR_CUDA, "cudaSetDevice failed (no usable CUDA device)");
+  for (;;) {
+    while (!j->results.empty() && j->results.front()->consumed >= j->results.front()->rows) {
+      if (j->win_batch == j->results.front().get()) { j->win_batch = nullptr; j->win_lo = j->win_hi = 0; }
+      j->free_batches.push_back(std::move(j->results.front()));
+      j->results.pop_front();
+    }
+    if (!j->results.empty()) break;
+    if (!wait || j->probe_finished.load()) return TG_OK;   // 0 rows: EOF iff probe_finish was called, else "push more"
+    j->res_cv.wait(lock__);
+    if (j->closed.load()) return fail(TG_ERR_CANCELLED, "handle is closed");
   }
-  if (j->results.empty()) return TG_OK;   // EOF iff probe_finish was called, else "push more"
+  cudaStream_t cstream = j->d2h_stream;
   ResultBatch& rb = *j->results.front();
   int64_t want = std::min<int64_t>(std::min<int64_t>(max_rows, out->capacity_rows), rb.rows - rb.consumed);
   if (want <= 0) return TG_OK;
@@ -1039,8 +1075,8 @@ int tg_join_next(tg_join* j, tg_mut_chunk* out, int64_t max_rows, int64_t* nrows
   if (want >= 64 * 1024) {
     for (int c = 0; c < j->n_out; c++) {
       size_t el = j->out_elem[c];
-      TG_CUDA(cudaMemcpyAsync(out->cols[c].data, rb.cols[c]->as<uint8_t>() + (size_t)lo * el, (size_t)want * el, cudaMemcpyDeviceToHost, j->stream));
-      j->stats.d2h_bytes += (int64_t)want * el;
+      TG_CUDA(cudaMemcpyAsync(out->cols[c].data, rb.cols[c]->as<uint8_t>() + (size_t)lo * el, (size_t)want * el, cudaMemcpyDeviceToHost, cstream));
+      j->d2h_bytes += (int64_t)want * el;
     }
   } else {
     // serve from a pinned window of up to kNextWindowRows rows fetched with one copy per column
@@ -1050,11 +1086,11 @@ int tg_join_next(tg_join* j, tg_mut_chunk* out, int64_t max_rows, int64_t* nrows
       size_t offb = 0;
       for (int c = 0; c < j->n_out; c++) {
         size_t el = j->out_elem[c];
-        TG_CUDA(cudaMemcpyAsync(j->win.p + offb, rb.cols[c]->as<uint8_t>() + (size_t)lo * el, (size_t)wn * el, cudaMemcpyDeviceToHost, j->stream));
-        j->stats.d2h_bytes += (int64_t)wn * el;
+        TG_CUDA(cudaMemcpyAsync(j->win.p + offb, rb.cols[c]->as<uint8_t>() + (size_t)lo * el, (size_t)wn * el, cudaMemcpyDeviceToHost, cstream));
+        j->d2h_bytes += (int64_t)wn * el;
         offb += (size_t)wn * el;
       }
-      TG_CUDA(cudaStreamSynchronize(j->stream));
+      TG_CUDA(cudaStreamSynchronize(cstream));
       j->win_batch = &rb; j->win_lo = lo; j->win_hi = lo + wn;
     }
     int64_t wn = j->win_hi - j->win_lo;
@@ -1069,20 +1105,35 @@ int tg_join_next(tg_join* j, tg_mut_chunk* out, int64_t max_rows, int64_t* nrows
     size_t nb = (size_t)((want + 7) / 8);
     if (rb.bitmaps[c]->p) {
       if (!out->cols[c].null_bitmap) return fail(TG_ERR_INVALID, "output column can be NULL but the caller passed no null bitmap");
-      TG_CUDA(cudaMemcpyAsync(out->cols[c].null_bitmap, rb.bitmaps[c]->as<uint8_t>() + lo / 8, nb, cudaMemcpyDeviceToHost, j->stream));
-      j->stats.d2h_bytes += nb;
+      TG_CUDA(cudaMemcpyAsync(out->cols[c].null_bitmap, rb.bitmaps[c]->as<uint8_t>() + lo / 8, nb, cudaMemcpyDeviceToHost, cstream));
+      j->d2h_bytes += nb;
     } else if (out->cols[c].null_bitmap) {
       std::memset(out->cols[c].null_bitmap, 0xff, nb);
       if (want & 7) out->cols[c].null_bitmap[nb - 1] = (uint8_t)((1u << (want & 7)) - 1);
     }
   }
-  TG_CUDA(cudaStreamSynchronize(j->stream));
+  TG_CUDA(cudaStreamSynchronize(cstream));
   // mask the tail bits of copied bitmaps (Column.nullBitmap keeps unused bits zero)
   if (want & 7) for (int c = 0; c < j->n_out; c++) if (rb.bitmaps[c]->p) out->cols[c].null_bitmap[(want >> 3)] &= (uint8_t)((1u << (want & 7)) - 1);
   rb.consumed += want;
   *nrows = want;
   return TG_OK;
 }
+
+int tg_join_probe_rewind(tg_join* j) {
+  TG_LOCK(j);
+  if (!j->built) return fail(TG_ERR_STATE, "rewind before build_finish");
+  if (j->need_scan) return fail(TG_ERR_UNSUPPORTED, "joins that scan the build side afterwards cannot be re-probed (used flags accumulate)");
+  j->pstage.reset();
+  std::lock_guard<std::mutex> lk(j->res_mu);
+  while (!j->results.empty()) { j->free_batches.push_back(std::move(j->results.front())); j->results.pop_front(); }
+  j->win_batch = nullptr; j->win_lo = j->win_hi = 0;
+  j->probe_finished.store(false);
+  return TG_OK;
+}
+
+int tg_join_next(tg_join* j, tg_mut_chunk* out, int64_t max_rows, int64_t* nrows) { return join_next_impl(j, out, max_rows, nrows, false); }
+int tg_join_next_wait(tg_join* j, tg_mut_chunk* out, int64_t max_rows, int64_t* nrows) { return join_next_impl(j, out, max_rows, nrows, true); }
 
 int tg_join_probe_dev(tg_join* j, const tg_chunk* dev_chk, int64_t* out_rows, void** out_cols, void** out_nulls) {
   TG_LOCK(j);
@@ -1112,6 +1163,7 @@ int tg_join_get_stats(tg_join* j, tg_join_stats* out) {
   if (!out) return fail(TG_ERR_INVALID, "out is NULL");
   TG_CUDA(cudaStreamSynchronize(j->stream));
   *out = j->stats;
+  out->d2h_bytes = j->d2h_bytes.load();
   return TG_OK;
 }
 
@@ -1119,11 +1171,16 @@ int tg_join_close(tg_join* j) {
   if (!j) return TG_OK;
   bool was = j->closed.exchange(true);
   if (was) return TG_OK;
+  j->res_cv.notify_all();
   {
-    std::lock_guard<std::mutex> lock(j->mu);   // waits for an in-flight call; later calls see `closed`
+    // waits for an in-flight push and an in-flight next; later calls see `closed`
+    std::lock_guard<std::mutex> lock(j->mu);
+    std::lock_guard<std::mutex> rlock(j->res_mu);
     DeviceGuard g(j->device);
     if (j->stream) cudaStreamSynchronize(j->stream);
+    if (j->d2h_stream) { cudaStreamSynchronize(j->d2h_stream); cudaStreamDestroy(j->d2h_stream); }
     j->results.clear();
+    j->free_batches.clear();
     j->dev_result.reset();
     if (j->ev0) cudaEventDestroy(j->ev0);
     if (j->ev1) cudaEventDestroy(j->ev1);
