@@ -213,6 +213,140 @@ k_agg_update_nogroup(DevCols cols, int64_t n, AggTable t, AggSpec spec) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Two-phase path for low-cardinality GROUP BY (the reference's own benchmark uses NDV 1000, benchmark_test.go:224): the
+// same partial → final split as HashAggPartialWorker / HashAggFinalWorker (agg_hash_partial_worker.go:256,
+// agg_hash_final_worker.go:73), with a CTA playing the partial worker.  Each CTA aggregates its rows into a
+// shared-memory table (AGG_LOCAL_SLOTS slots + the NULL and sentinel groups); rows whose new key does not fit are
+// deferred to the global kernel.  At the end the CTA emits its partial results, and k_agg_merge folds them into the
+// global table (MergePartialResult semantics) with the usual grow-and-retry protocol.
+// ---------------------------------------------------------------------------------------------------------------
+#define AGG_LOCAL_SLOTS 1024
+#define AGG_LOCAL_MAX_FILL 512
+#define AGG_LOCAL_MAX_STATES 4
+struct AggPartials {   // columnar partial results, capacity = gridDim.x * (AGG_LOCAL_MAX_FILL + 2)
+  long long* keys;
+  unsigned char* kind;                 // 0 regular key, 1 NULL group, 2 sentinel-valued key
+  unsigned long long* rows;
+  unsigned long long* state[AGG_LOCAL_MAX_STATES];
+  unsigned long long* count;           // number of tuples emitted
+};
+
+__global__ void __launch_bounds__(256)
+k_agg_update_local(GroupKey gk, DevCols cols, int64_t row_lo, int64_t row_hi, AggSpec spec, int nstates, AggPartials out,
+                   uint32_t* deferred, unsigned long long* n_deferred) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NT = AGG_LOCAL_SLOTS + 2;
+  AggTable lt;
+  lt.nslots = AGG_LOCAL_SLOTS;
+  lt.keys = reinterpret_cast<long long*>(smem_raw);
+  lt.rows = reinterpret_cast<unsigned long long*>(smem_raw) + NT;
+  for (int s = 0; s < nstates; s++) lt.state[s] = reinterpret_cast<unsigned long long*>(smem_raw) + (size_t)NT * (2 + s);
+  __shared__ unsigned int s_fill;
+  for (int i = threadIdx.x; i < NT; i += blockDim.x) {
+    lt.keys[i] = kEmptyKey; lt.rows[i] = 0;
+    for (int k = 0; k < spec.n; k++) {
+      const AggFuncDev& f = spec.f[k];
+      if (f.s0 >= 0) lt.state[f.s0][i] = f.name == TG_AGG_MIN ? ~0ull : 0ull;
+      if (f.s1 >= 0) lt.state[f.s1][i] = 0;
+    }
+  }
+  if (threadIdx.x == 0) s_fill = 0;
+  __syncthreads();
+  unsigned long long my_deferred = 0;
+  for (int64_t i = row_lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < row_hi; i += (int64_t)gridDim.x * blockDim.x) {
+    unsigned long long s;
+    bool is_null = gk.nulls && !bit_not_null(gk.nulls, i);
+    bool defer = false;
+    if (is_null) s = AGG_LOCAL_SLOTS;
+    else {
+      long long k;
+      if (gk.kind == GK_I64) k = reinterpret_cast<const long long*>(gk.data)[i];
+      else { double d = reinterpret_cast<const double*>(gk.data)[i]; if (d == 0) d = 0; k = __double_as_longlong(d); }
+      if (k == kEmptyKey) s = AGG_LOCAL_SLOTS + 1;
+      else {
+        s = slot32(mix64((uint64_t)k), AGG_LOCAL_SLOTS);
+        for (;;) {
+          long long cur = *reinterpret_cast<volatile long long*>(&lt.keys[s]);
+          if (cur == k) break;
+          if (cur == kEmptyKey) {
+            unsigned int f = atomicAdd(&s_fill, 1u);
+            if (f >= AGG_LOCAL_MAX_FILL) { atomicSub(&s_fill, 1u); defer = true; break; }
+            unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&lt.keys[s]), (unsigned long long)kEmptyKey, (unsigned long long)k);
+            if (old == (unsigned long long)kEmptyKey) break;
+            atomicSub(&s_fill, 1u);
+            if (old == (unsigned long long)k) break;
+          }
+          if (++s == AGG_LOCAL_SLOTS) s = 0;
+        }
+      }
+    }
+    if (defer) { atomicOr(&deferred[i >> 5], 1u << (i & 31)); my_deferred++; continue; }
+    agg_apply(lt, spec, cols, i, s);
+  }
+  for (int o = 16; o; o >>= 1) my_deferred += __shfl_xor_sync(0xffffffffu, my_deferred, o);
+  if ((threadIdx.x & 31) == 0 && my_deferred) atomicAdd(n_deferred, my_deferred);
+  __syncthreads();
+  // emit the partial results of this CTA
+  for (int i = threadIdx.x; i < NT; i += blockDim.x) {
+    bool occ = i < AGG_LOCAL_SLOTS ? lt.keys[i] != kEmptyKey : lt.rows[i] != 0;
+    if (!occ) continue;
+    unsigned long long o = atomicAdd(out.count, 1ull);
+    out.keys[o] = i < AGG_LOCAL_SLOTS ? lt.keys[i] : 0;
+    out.kind[o] = i < AGG_LOCAL_SLOTS ? 0 : (i == AGG_LOCAL_SLOTS ? 1 : 2);
+    out.rows[o] = lt.rows[i];
+    for (int s = 0; s < nstates; s++) out.state[s][o] = lt.state[s][i];
+  }
+}
+
+// fold partial results into the global table; same deferral protocol as k_agg_update
+__global__ void __launch_bounds__(256)
+k_agg_merge(AggPartials in, int64_t m, AggTable t, AggSpec spec, unsigned long long max_fill, unsigned long long* fill,
+            uint32_t* deferred, const uint32_t* only, unsigned long long* n_deferred) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < m; i += stride) {
+    if (only && !((only[i >> 5] >> (i & 31)) & 1u)) continue;
+    unsigned long long s;
+    if (in.kind[i] == 1) s = t.nslots;
+    else if (in.kind[i] == 2) s = t.nslots + 1;
+    else {
+      long long k = in.keys[i];
+      s = slot_of(mix64((uint64_t)k), t.nslots);
+      bool defer = false;
+      for (;;) {
+        long long cur = *reinterpret_cast<volatile long long*>(&t.keys[s]);
+        if (cur == k) break;
+        if (cur == kEmptyKey) {
+          unsigned long long f = atomicAdd(fill, 1ull);
+          if (f >= max_fill) { atomicAdd(fill, (unsigned long long)-1ll); defer = true; break; }
+          unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&t.keys[s]), (unsigned long long)kEmptyKey, (unsigned long long)k);
+          if (old == (unsigned long long)kEmptyKey) break;
+          atomicAdd(fill, (unsigned long long)-1ll);
+          if (old == (unsigned long long)k) break;
+        }
+        if (++s == t.nslots) s = 0;
+      }
+      if (defer) { atomicOr(&deferred[i >> 5], 1u << (i & 31)); atomicAdd(n_deferred, 1ull); continue; }
+    }
+    atomicAdd(&t.rows[s], in.rows[i]);
+    for (int k = 0; k < spec.n; k++) {
+      const AggFuncDev& f = spec.f[k];
+      if (f.s0 >= 0) {
+        unsigned long long v = in.state[f.s0][i];
+        switch (f.name) {
+          case TG_AGG_COUNT: atomicAdd(&t.state[f.s0][s], v); break;                                                  // countPartial merge func_count.go:481
+          case TG_AGG_SUM: case TG_AGG_AVG: atomicAdd(reinterpret_cast<double*>(&t.state[f.s0][s]), __longlong_as_double((long long)v)); break;   // func_sum.go:106, func_avg.go:444
+          case TG_AGG_MIN: atomicMin(&t.state[f.s0][s], v); break;
+          case TG_AGG_MAX: atomicMax(&t.state[f.s0][s], v); break;
+          default: break;
+        }
+      }
+      if (f.s1 >= 0) atomicAdd(&t.state[f.s1][s], in.state[f.s1][i]);
+    }
+  }
+}
+
 // re-insert every group of an old table into a bigger one (no atomics on the states: keys are unique)
 __global__ void k_agg_rehash(AggTable oldt, AggTable newt, AggSpec spec, int nstates, unsigned long long* fill) {
   unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
@@ -336,8 +470,9 @@ struct tg_agg {
   AggTable tbl{};
   unsigned long long nslots = 0;
   DevBuf scalars;              // [0] fill [1] n_deferred [2] out cursor
-  DevBuf deferred;
+  DevBuf deferred, partials_mem;
   int64_t expected_groups = 0;
+  int local_mode = -1;            // -1 undecided, 0 global atomics only, 1 CTA-local partial aggregation first
 
   // staging
   AggHostStage stage;
@@ -470,6 +605,72 @@ static int grow_table(tg_agg* a, unsigned long long want_slots) {
   return TG_OK;
 }
 
+__global__ void k_mark_range(uint32_t* bits, int64_t lo, int64_t hi) {
+  int64_t i = lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < hi; i += stride) atomicOr(&bits[i >> 5], 1u << (i & 31));
+}
+static int mark_range_deferred(tg_agg* a, int64_t lo, int64_t hi) {
+  // whole 32-bit words with memset, ragged edges with a tiny kernel
+  int64_t wlo = (lo + 31) / 32, whi = hi / 32;
+  uint32_t* bits = a->deferred.as<uint32_t>();
+  if (whi > wlo) TG_CUDA(cudaMemsetAsync(bits + wlo, 0xff, (size_t)(whi - wlo) * 4, a->stream));
+  int64_t e1 = std::min<int64_t>(hi, wlo * 32);
+  if (lo < e1) { k_mark_range<<<1, 64, 0, a->stream>>>(bits, lo, e1); a->stats.kernel_launches++; }
+  int64_t s2 = std::max<int64_t>(std::max<int64_t>(lo, e1), whi * 32);
+  if (s2 < hi) { k_mark_range<<<1, 64, 0, a->stream>>>(bits, s2, hi); a->stats.kernel_launches++; }
+  return TG_OK;
+}
+
+// rows [lo, hi): CTA-local partial aggregation, then merge of the partial results into the global table
+static int local_partial_pass(tg_agg* a, const GroupKey& gk, const DevCols& cols, int64_t lo, int64_t hi, unsigned long long* sc) {
+  int grid = agrid(a, hi - lo, 256, 4);
+  size_t cap = (size_t)grid * (AGG_LOCAL_MAX_FILL + 2);
+  size_t per = 8 /*keys*/ + 8 /*rows*/ + 8 * (size_t)a->nstates + 1 /*kind*/;
+  TG_TRY(a->partials_mem.ensure(a->device, cap * per + 256));
+  AggPartials pp{};
+  uint8_t* base = a->partials_mem.as<uint8_t>();
+  pp.keys = reinterpret_cast<long long*>(base); base += cap * 8;
+  pp.rows = reinterpret_cast<unsigned long long*>(base); base += cap * 8;
+  for (int s = 0; s < a->nstates; s++) { pp.state[s] = reinterpret_cast<unsigned long long*>(base); base += cap * 8; }
+  pp.kind = base;
+  pp.count = sc + 3;
+  TG_CUDA(cudaMemsetAsync(sc + 3, 0, 8, a->stream));
+  size_t smem = (size_t)(AGG_LOCAL_SLOTS + 2) * 8 * (2 + a->nstates);
+  TG_CUDA(cudaFuncSetAttribute(k_agg_update_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_agg_update_local<<<grid, 256, smem, a->stream>>>(gk, cols, lo, hi, a->spec, a->nstates, pp, a->deferred.as<uint32_t>(), sc + 1);
+  a->stats.kernel_launches++;
+  unsigned long long m = 0;
+  TG_CUDA(cudaMemcpyAsync(&m, sc + 3, 8, cudaMemcpyDeviceToHost, a->stream));
+  TG_CUDA(cudaStreamSynchronize(a->stream));
+  if (m == 0) return TG_OK;
+  // merge with its own grow-and-retry loop (tuples, not rows)
+  DevBuf mdef, mprev;
+  size_t dwords = (size_t)((m + 31) / 32);
+  TG_TRY(mdef.ensure(a->device, dwords * 4 + 16));
+  TG_CUDA(cudaMemsetAsync(mdef.p, 0, dwords * 4, a->stream));
+  TG_CUDA(cudaMemsetAsync(sc + 4, 0, 8, a->stream));
+  const uint32_t* only = nullptr;
+  for (int round = 0; round < 40; round++) {
+    unsigned long long max_fill = (unsigned long long)((double)a->nslots * 0.6);
+    k_agg_merge<<<agrid(a, (int64_t)m), 256, 0, a->stream>>>(pp, (int64_t)m, a->tbl, a->spec, max_fill, sc, mdef.as<uint32_t>(), only, sc + 4);
+    a->stats.kernel_launches++;
+    unsigned long long nd = 0;
+    TG_CUDA(cudaMemcpyAsync(&nd, sc + 4, 8, cudaMemcpyDeviceToHost, a->stream));
+    TG_CUDA(cudaStreamSynchronize(a->stream));
+    if (nd == 0) break;
+    unsigned long long want = std::max<unsigned long long>(a->nslots * 4, (unsigned long long)((a->nslots * 0.6 + (double)nd) * 2));
+    TG_TRY(grow_table(a, want));
+    TG_TRY(mprev.ensure(a->device, dwords * 4 + 16));
+    TG_CUDA(cudaMemcpyAsync(mprev.p, mdef.p, dwords * 4, cudaMemcpyDeviceToDevice, a->stream));
+    TG_CUDA(cudaMemsetAsync(mdef.p, 0, dwords * 4, a->stream));
+    TG_CUDA(cudaMemsetAsync(sc + 4, 0, 8, a->stream));
+    only = mprev.as<uint32_t>();
+    if (round == 39) return fail(TG_ERR_CUDA, "internal: aggregation merge failed to converge");
+  }
+  return TG_OK;
+}
+
 // aggregate n device-resident rows
 static int update_device(tg_agg* a, const DevCols& cols, int64_t n) {
   if (n == 0) return TG_OK;
@@ -496,25 +697,58 @@ static int update_device(tg_agg* a, const DevCols& cols, int64_t n) {
     TG_TRY(a->deferred.ensure(a->device, dwords * 4 + 16));
     TG_CUDA(cudaMemsetAsync(a->deferred.p, 0, dwords * 4, a->stream));
     TG_CUDA(cudaMemsetAsync(sc + 1, 0, 8, a->stream));
-    const uint32_t* only = nullptr;
-    DevBuf prev_deferred;
-    for (int round = 0; round < 40; round++) {
-      unsigned long long max_fill = (unsigned long long)((double)a->nslots * 0.6);
-      k_agg_update<<<agrid(a, n), 256, 0, a->stream>>>(gk, cols, n, a->tbl, a->spec, max_fill, sc, a->deferred.as<uint32_t>(), only, sc + 1);
-      a->stats.kernel_launches++;
-      unsigned long long nd = 0;
-      TG_CUDA(cudaMemcpyAsync(&nd, sc + 1, 8, cudaMemcpyDeviceToHost, a->stream));
-      TG_CUDA(cudaStreamSynchronize(a->stream));
-      if (nd == 0) break;
-      // grow ×4 (at least enough for every deferred row to be a new group), re-run only the deferred rows
-      unsigned long long want = std::max<unsigned long long>(a->nslots * 4, (unsigned long long)((a->nslots * 0.6 + (double)nd) * 2));
-      TG_TRY(grow_table(a, want));
-      TG_TRY(prev_deferred.ensure(a->device, dwords * 4 + 16));
-      TG_CUDA(cudaMemcpyAsync(prev_deferred.p, a->deferred.p, dwords * 4, cudaMemcpyDeviceToDevice, a->stream));
-      TG_CUDA(cudaMemsetAsync(a->deferred.p, 0, dwords * 4, a->stream));
+    bool have_deferred = false;
+    // ---- phase 1 (low cardinality): CTA-local partial aggregation, decided on a 1M-row sample when there is no hint ----
+    bool try_local = a->nstates <= AGG_LOCAL_MAX_STATES && a->local_mode != 0 &&
+                     (a->local_mode == 1 || a->expected_groups == 0 || a->expected_groups <= 4 * AGG_LOCAL_MAX_FILL);
+    if (try_local) {
+      int64_t done = 0;
+      while (done < n) {
+        int64_t hi = (a->local_mode == 1) ? n : std::min<int64_t>(n, done + (1ll << 20));
+        TG_TRY(local_partial_pass(a, gk, cols, done, hi, sc));
+        unsigned long long nd = 0;
+        TG_CUDA(cudaMemcpyAsync(&nd, sc + 1, 8, cudaMemcpyDeviceToHost, a->stream));
+        TG_CUDA(cudaStreamSynchronize(a->stream));
+        int64_t span = hi - done;
+        done = hi;
+        if (nd) have_deferred = true;
+        if (a->local_mode < 0) a->local_mode = (nd * 10 <= (unsigned long long)span) ? 1 : 0;   // < 10 % of the sample overflowed
+        if (a->local_mode == 0) break;
+      }
+      if (done < n) {   // the rest of the batch goes through the global kernel: mark it "deferred"
+        TG_TRY(mark_range_deferred(a, done, n));
+        have_deferred = true;
+      }
       TG_CUDA(cudaMemsetAsync(sc + 1, 0, 8, a->stream));
-      only = prev_deferred.as<uint32_t>();
-      if (round == 39) return fail(TG_ERR_CUDA, "internal: aggregation table failed to converge");
+    }
+    // ---- phase 2: global atomics on every row (or only the deferred ones), growing the table on demand ----
+    if (!try_local || have_deferred) {
+      DevBuf prev_deferred;
+      const uint32_t* only = nullptr;
+      if (try_local) {
+        TG_TRY(prev_deferred.ensure(a->device, dwords * 4 + 16));
+        TG_CUDA(cudaMemcpyAsync(prev_deferred.p, a->deferred.p, dwords * 4, cudaMemcpyDeviceToDevice, a->stream));
+        TG_CUDA(cudaMemsetAsync(a->deferred.p, 0, dwords * 4, a->stream));
+        only = prev_deferred.as<uint32_t>();
+      }
+      for (int round = 0; round < 40; round++) {
+        unsigned long long max_fill = (unsigned long long)((double)a->nslots * 0.6);
+        k_agg_update<<<agrid(a, n), 256, 0, a->stream>>>(gk, cols, n, a->tbl, a->spec, max_fill, sc, a->deferred.as<uint32_t>(), only, sc + 1);
+        a->stats.kernel_launches++;
+        unsigned long long nd = 0;
+        TG_CUDA(cudaMemcpyAsync(&nd, sc + 1, 8, cudaMemcpyDeviceToHost, a->stream));
+        TG_CUDA(cudaStreamSynchronize(a->stream));
+        if (nd == 0) break;
+        // grow x4 (at least enough for every deferred row to be a new group), re-run only the deferred rows
+        unsigned long long want = std::max<unsigned long long>(a->nslots * 4, (unsigned long long)((a->nslots * 0.6 + (double)nd) * 2));
+        TG_TRY(grow_table(a, want));
+        TG_TRY(prev_deferred.ensure(a->device, dwords * 4 + 16));
+        TG_CUDA(cudaMemcpyAsync(prev_deferred.p, a->deferred.p, dwords * 4, cudaMemcpyDeviceToDevice, a->stream));
+        TG_CUDA(cudaMemsetAsync(a->deferred.p, 0, dwords * 4, a->stream));
+        TG_CUDA(cudaMemsetAsync(sc + 1, 0, 8, a->stream));
+        only = prev_deferred.as<uint32_t>();
+        if (round == 39) return fail(TG_ERR_CUDA, "internal: aggregation table failed to converge");
+      }
     }
   }
   TG_CUDA(cudaEventRecord(a->ev1, a->stream));

@@ -13,39 +13,52 @@ namespace tg {
 
 struct VArg { const void* data; const uint8_t* nulls; };
 
-__device__ __forceinline__ uint8_t merged_null_byte(const VArg& a, const VArg& b, int64_t byte) {
-  uint8_t x = a.nulls ? a.nulls[byte] : 0xff;
-  uint8_t y = b.nulls ? b.nulls[byte] : 0xff;
-  return x & y;
+// Streaming layout: lane l of a warp owns rows base+l, base+32+l, ... (VEC_ITEMS per thread, all loads issued before
+// use) so every load/store instruction is one fully coalesced 256-byte request; the 32 validity bits of a warp-row are
+// one ballot, written as one aligned 32-bit word of the result bitmap.
+#define VEC_ITEMS 4
+__device__ __forceinline__ bool arg_valid(const VArg& a, int64_t i) { return !a.nulls || bit_not_null(a.nulls, i); }
+
+// write the 32 validity bits of rows [wbase, wbase+32) (wbase % 32 == 0); tail rows are masked off
+__device__ __forceinline__ void store_valid_word(uint8_t* rnulls, int64_t wbase, int64_t n, unsigned bal, int lane) {
+  if (lane == 0 && wbase < n) {
+    int64_t rem = n - wbase;
+    if (rem >= 32) *reinterpret_cast<uint32_t*>(rnulls + (wbase >> 3)) = bal;
+    else {
+      bal &= (1u << rem) - 1u;
+      for (int b = 0; b < (int)((rem + 7) / 8); b++) rnulls[(wbase >> 3) + b] = (uint8_t)(bal >> (8 * b));
+    }
+  }
 }
 
-// one thread per 8 rows so that each thread owns one byte of the result bitmap
 template <bool REAL>
 __global__ void __launch_bounds__(256)
 k_vec_compare(int op, int ua, int ub, VArg a, VArg b, long long bc_i, double bc_f, int64_t n,
               long long* __restrict__ result, uint8_t* __restrict__ rnulls) {
-  int64_t nb = (n + 7) / 8;
-  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; t < nb; t += stride) {
-    uint8_t m = merged_null_byte(a, b, t);
-    int64_t r0 = t * 8;
-    int cnt = (int)((n - r0) < 8 ? (n - r0) : 8);
-    if (cnt < 8) m &= (uint8_t)((1u << cnt) - 1);
-    rnulls[t] = m;
-    for (int j = 0; j < cnt; j++) {
-      int64_t i = r0 + j;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t tile = 32 * VEC_ITEMS;
+  for (int64_t base = warp * tile; base < n; base += nwarps * tile) {
+    unsigned long long x[VEC_ITEMS], y[VEC_ITEMS];
+    bool in[VEC_ITEMS];
+#pragma unroll
+    for (int j = 0; j < VEC_ITEMS; j++) {
+      int64_t i = base + j * 32 + lane;
+      in[j] = i < n;
+      x[j] = in[j] ? __ldcs(reinterpret_cast<const unsigned long long*>(a.data) + i) : 0ull;
+      y[j] = (in[j] && b.data) ? __ldcs(reinterpret_cast<const unsigned long long*>(b.data) + i) : 0ull;
+    }
+#pragma unroll
+    for (int j = 0; j < VEC_ITEMS; j++) {
+      int64_t i = base + j * 32 + lane;
+      bool valid = in[j] && arg_valid(a, i) && arg_valid(b, i);
       int c;
-      if (REAL) {
-        double x = reinterpret_cast<const double*>(a.data)[i];
-        double y = b.data ? reinterpret_cast<const double*>(b.data)[i] : bc_f;
-        c = cmp_real(x, y);
-      } else {
-        long long x = reinterpret_cast<const long long*>(a.data)[i];
-        long long y = b.data ? reinterpret_cast<const long long*>(b.data)[i] : bc_i;
-        c = cmp_int(x, ua != 0, y, ub != 0);
-      }
-      result[i] = apply_cmp(op, c) ? 1 : 0;
+      if (REAL) c = cmp_real(__longlong_as_double((long long)x[j]), b.data ? __longlong_as_double((long long)y[j]) : bc_f);
+      else c = cmp_int((long long)x[j], ua != 0, b.data ? (long long)y[j] : bc_i, ub != 0);
+      if (in[j]) __stcs(result + i, apply_cmp(op, c) ? 1ll : 0ll);
+      unsigned bal = __ballot_sync(0xffffffffu, valid);
+      store_valid_word(rnulls, base + j * 32, n, bal, lane);
     }
   }
 }
@@ -72,20 +85,25 @@ __device__ __forceinline__ bool minus_overflow(bool lu, bool ru, long long a, lo
 __global__ void __launch_bounds__(256)
 k_vec_arith_int(int op, int lu, int ru, VArg a, VArg b, long long bc, int64_t n, long long* __restrict__ result,
                 uint8_t* __restrict__ rnulls, int* overflow) {
-  int64_t nb = (n + 7) / 8;
-  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t tile = 32 * VEC_ITEMS;
   const long long MAXI = 0x7fffffffffffffffll, MINI = (long long)0x8000000000000000ull;
-  for (; t < nb; t += stride) {
-    uint8_t m = merged_null_byte(a, b, t);
-    int64_t r0 = t * 8;
-    int cnt = (int)((n - r0) < 8 ? (n - r0) : 8);
-    if (cnt < 8) m &= (uint8_t)((1u << cnt) - 1);
-    rnulls[t] = m;
-    for (int j = 0; j < cnt; j++) {
-      int64_t i = r0 + j;
-      long long lh = reinterpret_cast<const long long*>(a.data)[i];
-      long long rh = b.data ? reinterpret_cast<const long long*>(b.data)[i] : bc;
+  for (int64_t base = warp * tile; base < n; base += nwarps * tile) {
+    long long xs[VEC_ITEMS], ys[VEC_ITEMS];
+    bool in[VEC_ITEMS];
+#pragma unroll
+    for (int j = 0; j < VEC_ITEMS; j++) {
+      int64_t i = base + j * 32 + lane;
+      in[j] = i < n;
+      xs[j] = in[j] ? __ldcs(reinterpret_cast<const long long*>(a.data) + i) : 0ll;
+      ys[j] = in[j] ? (b.data ? __ldcs(reinterpret_cast<const long long*>(b.data) + i) : bc) : 0ll;
+    }
+#pragma unroll
+    for (int j = 0; j < VEC_ITEMS; j++) {
+      int64_t i = base + j * 32 + lane;
+      long long lh = xs[j], rh = ys[j];
       bool ovf;
       long long r;
       if (op == TG_ARITH_PLUS) {
@@ -107,9 +125,11 @@ k_vec_arith_int(int op, int lu, int ru, VArg a, VArg b, long long bc, int64_t n,
         ovf = special || (lh != 0 && tmp / lh != rh);
         r = tmp;
       }
-      bool not_null = (m >> j) & 1;
-      if (ovf) { if (not_null) atomicExch(overflow, 1); r = 0; }
-      result[i] = r;
+      bool valid = in[j] && arg_valid(a, i) && arg_valid(b, i);
+      if (ovf) { if (valid) atomicExch(overflow, 1); r = 0; }
+      if (in[j]) __stcs(result + i, r);
+      unsigned bal = __ballot_sync(0xffffffffu, valid);
+      store_valid_word(rnulls, base + j * 32, n, bal, lane);
     }
   }
 }
@@ -117,26 +137,33 @@ k_vec_arith_int(int op, int lu, int ru, VArg a, VArg b, long long bc, int64_t n,
 __global__ void __launch_bounds__(256)
 k_vec_arith_real(int op, VArg a, VArg b, double bc, int64_t n, double* __restrict__ result, uint8_t* __restrict__ rnulls,
                  int* overflow) {
-  int64_t nb = (n + 7) / 8;
-  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; t < nb; t += stride) {
-    uint8_t m = merged_null_byte(a, b, t);
-    int64_t r0 = t * 8;
-    int cnt = (int)((n - r0) < 8 ? (n - r0) : 8);
-    if (cnt < 8) m &= (uint8_t)((1u << cnt) - 1);
-    rnulls[t] = m;
-    for (int j = 0; j < cnt; j++) {
-      int64_t i = r0 + j;
-      double x = reinterpret_cast<const double*>(a.data)[i];
-      double y = b.data ? reinterpret_cast<const double*>(b.data)[i] : bc;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t tile = 32 * VEC_ITEMS;
+  for (int64_t base = warp * tile; base < n; base += nwarps * tile) {
+    double xs[VEC_ITEMS], ys[VEC_ITEMS];
+    bool in[VEC_ITEMS];
+#pragma unroll
+    for (int j = 0; j < VEC_ITEMS; j++) {
+      int64_t i = base + j * 32 + lane;
+      in[j] = i < n;
+      xs[j] = in[j] ? __ldcs(reinterpret_cast<const double*>(a.data) + i) : 0.0;
+      ys[j] = in[j] ? (b.data ? __ldcs(reinterpret_cast<const double*>(b.data) + i) : bc) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < VEC_ITEMS; j++) {
+      int64_t i = base + j * 32 + lane;
       double r;
       bool ovf;
-      if (op == TG_ARITH_PLUS) { r = x + y; ovf = !isfinite(r); }          // mathutil.IsFinite
-      else if (op == TG_ARITH_MINUS) { r = x - y; ovf = !isfinite(r); }
-      else { r = x * y; ovf = isinf(r); }                                    // math.IsInf only (:51-58)
-      if (ovf && ((m >> j) & 1)) atomicExch(overflow, 1);
-      result[i] = r;
+      if (op == TG_ARITH_PLUS) { r = xs[j] + ys[j]; ovf = !isfinite(r); }          // mathutil.IsFinite
+      else if (op == TG_ARITH_MINUS) { r = xs[j] - ys[j]; ovf = !isfinite(r); }
+      else { r = xs[j] * ys[j]; ovf = isinf(r); }                                    // math.IsInf only (:51-58)
+      bool valid = in[j] && arg_valid(a, i) && arg_valid(b, i);
+      if (ovf && valid) atomicExch(overflow, 1);
+      if (in[j]) __stcs(result + i, r);
+      unsigned bal = __ballot_sync(0xffffffffu, valid);
+      store_valid_word(rnulls, base + j * 32, n, bal, lane);
     }
   }
 }
@@ -200,18 +227,22 @@ static int run_binary(int device, int on_device, const tg_column* a, const tg_co
   ArgDev da, db;
   TG_TRY(da.load(device, on_device, a, st));
   TG_TRY(db.load(device, on_device, b, st));
-  DevBuf dres, dnul, dovf;
+  DevBuf dres, dnul;
+  static std::mutex flag_mu;
+  static int* ovf_flag[16];   // one overflow flag per device, allocated once and intentionally never freed
+  std::lock_guard<std::mutex> flag_lock(flag_mu);   // VecEval calls are serialised per process
+  int*& dovf = ovf_flag[device & 15];
   void* res_dev = result; uint8_t* nul_dev = rnulls;
   size_t nb = (size_t)((n + 7) / 8);
   if (!on_device) {
     TG_TRY(dres.ensure(device, (size_t)n * 8 + 16)); TG_TRY(dnul.ensure(device, nb + 16));
     res_dev = dres.p; nul_dev = dnul.as<uint8_t>();
   }
-  TG_TRY(dovf.ensure(device, 16));
-  TG_CUDA(cudaMemsetAsync(dovf.p, 0, 4, st));
-  if (n > 0) launch(vgrid(device, (n + 7) / 8), st, da.v, db.v, n, res_dev, nul_dev, dovf.as<int>());
+  if (!dovf) TG_CUDA(cudaMalloc(reinterpret_cast<void**>(&dovf), 16));
+  TG_CUDA(cudaMemsetAsync(dovf, 0, 4, st));
+  if (n > 0) launch(vgrid(device, (n + VEC_ITEMS - 1) / VEC_ITEMS), st, da.v, db.v, n, res_dev, nul_dev, dovf);
   int ovf = 0;
-  if (has_overflow) TG_CUDA(cudaMemcpyAsync(&ovf, dovf.p, 4, cudaMemcpyDeviceToHost, st));
+  if (has_overflow) TG_CUDA(cudaMemcpyAsync(&ovf, dovf, 4, cudaMemcpyDeviceToHost, st));
   if (!on_device && n > 0) {
     TG_CUDA(cudaMemcpyAsync(result, res_dev, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     TG_CUDA(cudaMemcpyAsync(rnulls, nul_dev, nb, cudaMemcpyDeviceToHost, st));
