@@ -37,6 +37,25 @@ void append_bits(uint8_t* dst, int64_t pos, const uint8_t* src, int64_t nbits) {
   if (((pos + nbits + 7) >> 3) > d + nbytes) dst[d + nbytes] = carry;
 }
 
+cudaStream_t service_stream(int device) {
+  static std::mutex mu;
+  static cudaStream_t streams[64];
+  std::lock_guard<std::mutex> lk(mu);
+  int d = device & 63;
+  if (!streams[d]) {
+    int prev = -1; cudaGetDevice(&prev); cudaSetDevice(device);
+    if (cudaStreamCreateWithFlags(&streams[d], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); streams[d] = nullptr; }
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;   // never give memory back to the driver between operators
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  return streams[d];
+}
+
 int device_sm_count(int device) {
   static int cache[64];
   if (device >= 0 && device < 64 && cache[device] > 0) return cache[device];
