@@ -218,14 +218,13 @@ k_agg_update_nogroup(DevCols cols, int64_t n, AggTable t, AggSpec spec) {
 // Two-phase path for low-cardinality GROUP BY (the reference's own benchmark uses NDV 1000, benchmark_test.go:224): the
 // same partial → final split as HashAggPartialWorker / HashAggFinalWorker (agg_hash_partial_worker.go:256,
 // agg_hash_final_worker.go:73), with a CTA playing the partial worker.  Each CTA aggregates its rows into a
-// shared-memory table (AGG_LOCAL_SLOTS slots + the NULL and sentinel groups); rows whose new key does not fit are
+// shared-memory table (2048-4096 slots + the NULL and sentinel groups); rows whose new key does not fit are
 // deferred to the global kernel.  At the end the CTA emits its partial results, and k_agg_merge folds them into the
 // global table (MergePartialResult semantics) with the usual grow-and-retry protocol.
 // ---------------------------------------------------------------------------------------------------------------
-#define AGG_LOCAL_SLOTS 1024
-#define AGG_LOCAL_MAX_FILL 512
+#define AGG_LOCAL_SLOTS_MAX 4096   // per-CTA table: 4096 slots with <= 1 state array, 2048 otherwise (about 96 KB, 2 CTAs per SM)
 #define AGG_LOCAL_MAX_STATES 4
-struct AggPartials {   // columnar partial results, capacity = gridDim.x * (AGG_LOCAL_MAX_FILL + 2)
+struct AggPartials {   // columnar partial results, capacity = gridDim.x * (local_slots / 2 + 2)
   long long* keys;
   unsigned char* kind;                 // 0 regular key, 1 NULL group, 2 sentinel-valued key
   unsigned long long* rows;
@@ -234,12 +233,13 @@ struct AggPartials {   // columnar partial results, capacity = gridDim.x * (AGG_
 };
 
 __global__ void __launch_bounds__(256)
-k_agg_update_local(GroupKey gk, DevCols cols, int64_t row_lo, int64_t row_hi, AggSpec spec, int nstates, AggPartials out,
-                   uint32_t* deferred, unsigned long long* n_deferred) {
+k_agg_update_local(GroupKey gk, DevCols cols, int64_t row_lo, int64_t row_hi, AggSpec spec, int nstates, int local_slots,
+                   AggPartials out, uint32_t* deferred, unsigned long long* n_deferred) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int NT = AGG_LOCAL_SLOTS + 2;
+  const int LS = local_slots, NT = local_slots + 2;
+  const unsigned int max_local_fill = (unsigned int)(local_slots / 2);
   AggTable lt;
-  lt.nslots = AGG_LOCAL_SLOTS;
+  lt.nslots = (unsigned long long)LS;
   lt.keys = reinterpret_cast<long long*>(smem_raw);
   lt.rows = reinterpret_cast<unsigned long long*>(smem_raw) + NT;
   for (int s = 0; s < nstates; s++) lt.state[s] = reinterpret_cast<unsigned long long*>(smem_raw) + (size_t)NT * (2 + s);
@@ -259,26 +259,26 @@ k_agg_update_local(GroupKey gk, DevCols cols, int64_t row_lo, int64_t row_hi, Ag
     unsigned long long s;
     bool is_null = gk.nulls && !bit_not_null(gk.nulls, i);
     bool defer = false;
-    if (is_null) s = AGG_LOCAL_SLOTS;
+    if (is_null) s = LS;
     else {
       long long k;
       if (gk.kind == GK_I64) k = reinterpret_cast<const long long*>(gk.data)[i];
       else { double d = reinterpret_cast<const double*>(gk.data)[i]; if (d == 0) d = 0; k = __double_as_longlong(d); }
-      if (k == kEmptyKey) s = AGG_LOCAL_SLOTS + 1;
+      if (k == kEmptyKey) s = LS + 1;
       else {
-        s = slot32(mix64((uint64_t)k), AGG_LOCAL_SLOTS);
+        s = slot32(mix64((uint64_t)k), (uint32_t)LS);
         for (;;) {
           long long cur = *reinterpret_cast<volatile long long*>(&lt.keys[s]);
           if (cur == k) break;
           if (cur == kEmptyKey) {
             unsigned int f = atomicAdd(&s_fill, 1u);
-            if (f >= AGG_LOCAL_MAX_FILL) { atomicSub(&s_fill, 1u); defer = true; break; }
+            if (f >= max_local_fill) { atomicSub(&s_fill, 1u); defer = true; break; }
             unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(&lt.keys[s]), (unsigned long long)kEmptyKey, (unsigned long long)k);
             if (old == (unsigned long long)kEmptyKey) break;
             atomicSub(&s_fill, 1u);
             if (old == (unsigned long long)k) break;
           }
-          if (++s == AGG_LOCAL_SLOTS) s = 0;
+          if (++s == (unsigned long long)LS) s = 0;
         }
       }
     }
@@ -290,11 +290,11 @@ k_agg_update_local(GroupKey gk, DevCols cols, int64_t row_lo, int64_t row_hi, Ag
   __syncthreads();
   // emit the partial results of this CTA
   for (int i = threadIdx.x; i < NT; i += blockDim.x) {
-    bool occ = i < AGG_LOCAL_SLOTS ? lt.keys[i] != kEmptyKey : lt.rows[i] != 0;
+    bool occ = i < LS ? lt.keys[i] != kEmptyKey : lt.rows[i] != 0;
     if (!occ) continue;
     unsigned long long o = atomicAdd(out.count, 1ull);
-    out.keys[o] = i < AGG_LOCAL_SLOTS ? lt.keys[i] : 0;
-    out.kind[o] = i < AGG_LOCAL_SLOTS ? 0 : (i == AGG_LOCAL_SLOTS ? 1 : 2);
+    out.keys[o] = i < LS ? lt.keys[i] : 0;
+    out.kind[o] = i < LS ? 0 : (i == LS ? 1 : 2);
     out.rows[o] = lt.rows[i];
     for (int s = 0; s < nstates; s++) out.state[s][o] = lt.state[s][i];
   }
@@ -633,8 +633,9 @@ static int mark_range_deferred(tg_agg* a, int64_t lo, int64_t hi) {
 
 // rows [lo, hi): CTA-local partial aggregation, then merge of the partial results into the global table
 static int local_partial_pass(tg_agg* a, const GroupKey& gk, const DevCols& cols, int64_t lo, int64_t hi, unsigned long long* sc) {
-  int grid = agrid(a, hi - lo, 256, 4);
-  size_t cap = (size_t)grid * (AGG_LOCAL_MAX_FILL + 2);
+  const int local_slots = a->nstates <= 1 ? AGG_LOCAL_SLOTS_MAX : AGG_LOCAL_SLOTS_MAX / 2;
+  int grid = agrid(a, hi - lo, 256, 2);
+  size_t cap = (size_t)grid * (local_slots / 2 + 2);
   size_t per = 8 /*keys*/ + 8 /*rows*/ + 8 * (size_t)a->nstates + 1 /*kind*/;
   TG_TRY(a->partials_mem.ensure(a->device, cap * per + 256));
   AggPartials pp{};
@@ -645,9 +646,9 @@ static int local_partial_pass(tg_agg* a, const GroupKey& gk, const DevCols& cols
   pp.kind = base;
   pp.count = sc + 3;
   TG_CUDA(cudaMemsetAsync(sc + 3, 0, 8, a->stream));
-  size_t smem = (size_t)(AGG_LOCAL_SLOTS + 2) * 8 * (2 + a->nstates);
+  size_t smem = (size_t)(local_slots + 2) * 8 * (2 + a->nstates);
   TG_CUDA(cudaFuncSetAttribute(k_agg_update_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_agg_update_local<<<grid, 256, smem, a->stream>>>(gk, cols, lo, hi, a->spec, a->nstates, pp, a->deferred.as<uint32_t>(), sc + 1);
+  k_agg_update_local<<<grid, 256, smem, a->stream>>>(gk, cols, lo, hi, a->spec, a->nstates, local_slots, pp, a->deferred.as<uint32_t>(), sc + 1);
   a->stats.kernel_launches++;
   unsigned long long m = 0;
   TG_CUDA(cudaMemcpyAsync(&m, sc + 3, 8, cudaMemcpyDeviceToHost, a->stream));
@@ -709,7 +710,7 @@ static int update_device(tg_agg* a, const DevCols& cols, int64_t n) {
     bool have_deferred = false;
     // ---- phase 1 (low cardinality): CTA-local partial aggregation, decided on a 1M-row sample when there is no hint ----
     bool try_local = a->nstates <= AGG_LOCAL_MAX_STATES && a->local_mode != 0 &&
-                     (a->local_mode == 1 || a->expected_groups == 0 || a->expected_groups <= 4 * AGG_LOCAL_MAX_FILL);
+                     (a->local_mode == 1 || a->expected_groups == 0 || a->expected_groups <= 2 * AGG_LOCAL_SLOTS_MAX);
     if (try_local) {
       int64_t done = 0;
       while (done < n) {
