@@ -633,8 +633,11 @@ static int mark_range_deferred(tg_agg* a, int64_t lo, int64_t hi) {
 
 // rows [lo, hi): CTA-local partial aggregation, then merge of the partial results into the global table
 static int local_partial_pass(tg_agg* a, const GroupKey& gk, const DevCols& cols, int64_t lo, int64_t hi, unsigned long long* sc) {
-  const int local_slots = a->nstates <= 1 ? AGG_LOCAL_SLOTS_MAX : AGG_LOCAL_SLOTS_MAX / 2;
-  int grid = agrid(a, hi - lo, 256, 2);
+  int local_slots = 1024;   // measured best on B200 (tools/bench_ops.py): bigger tables lose more to occupancy than they gain
+  if (const char* e = getenv("TG_AGG_LOCAL_SLOTS")) { int v = atoi(e); if (v == 512 || v == 1024 || v == 2048 || v == 4096) local_slots = v; }
+  size_t smem_per_cta = (size_t)(local_slots + 2) * 8 * (2 + a->nstates);
+  int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200u << 10) / smem_per_cta));
+  int grid = agrid(a, hi - lo, 256, per_sm);
   size_t cap = (size_t)grid * (local_slots / 2 + 2);
   size_t per = 8 /*keys*/ + 8 /*rows*/ + 8 * (size_t)a->nstates + 1 /*kind*/;
   TG_TRY(a->partials_mem.ensure(a->device, cap * per + 256));
@@ -722,7 +725,10 @@ static int update_device(tg_agg* a, const DevCols& cols, int64_t n) {
         int64_t span = hi - done;
         done = hi;
         if (nd) have_deferred = true;
-        if (a->local_mode < 0) a->local_mode = (nd * 10 <= (unsigned long long)span) ? 1 : 0;   // < 10 % of the sample overflowed
+        // Keep the CTA-local phase while it absorbs a useful share of the rows.  Measured (profiles/r1_agg_notes.md): shared-memory
+        // atomics (LSU) and L2 atomics are different engines; 1000 groups with half of the rows aggregated in shared memory and
+        // half deferred to the L2 path take 2.7 ms, all-L2 5.0 ms, all-shared 9 ms.
+        if (a->local_mode < 0) a->local_mode = (nd * 10 <= (unsigned long long)span * 7) ? 1 : 0;
         if (a->local_mode == 0) break;
       }
       if (done < n) {   // the rest of the batch goes through the global kernel: mark it "deferred"
