@@ -212,12 +212,20 @@ def run_gpu(args):
 
     # ---- build side (untimed): repartition by key hash when N > 1, then build the local table ---------
     xch_b = xch_p = None
+    xstream = None
+    xchunks = max(1, args.xchunks) if world > 1 else 1
     if world > 1:
         from tidb_b200.parallel import KeyExchange
+        xstream = torch.cuda.Stream(device=dev)
+        # receive capacity: expected rows + 2 % (uniform hash; a skewed key set would need a count-then-allocate round)
         with torch.cuda.stream(stream):
-            # receive capacity: expected rows + 2 % (uniform hash; a skewed key set would need a count-then-allocate round)
             xch_b = KeyExchange(rank, world, local, stream, 2, int(nb * 1.02) + 4096, args.exchange)
-            xch_p = KeyExchange(rank, world, local, stream, 2, int(npb * 1.02) + 4096, args.exchange)
+        with torch.cuda.stream(xstream):
+            # the probe side is exchanged in `xchunks` pieces through two alternating sets of receive buffers, so that the
+            # NVLink scatter of piece c+1 overlaps the probe kernel of piece c
+            xch_p = [KeyExchange(rank, world, local, xstream, 2, int(npb / xchunks * 1.03) + 8192, args.exchange) for _ in range(2 if xchunks > 1 else 1)]
+        # leave room on every SM for the scatter CTAs next to the persistent probe CTAs
+        os.environ.setdefault("TG_PROBE_CTAS_PER_SM", "2" if xchunks > 1 else "8")
 
     join = DeviceJoin(plan)
     with torch.cuda.stream(stream):
@@ -229,50 +237,61 @@ def run_gpu(args):
     bstats = join.stats()
 
     # ---- one step ------------------------------------------------------------------------------------------
+    bounds = [(npb * c // xchunks, npb * (c + 1) // xchunks) for c in range(xchunks)]
+    done_ev = [None, None]
+
+    def dview(p, n):
+        class _A:   # __cuda_array_interface__ wrapper for a library-owned device buffer (verification only, no copy)
+            pass
+        a = _A()
+        a.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (p, False), "version": 3}
+        return torch.as_tensor(a, device=dev)
+
+    def check_piece(cols, rows):
+        """size-independent properties of one probe result: equal keys, payload belongs to the key; returns checksums of
+        the probe row ids (every probe row must appear exactly once overall)"""
+        o_pk, o_pv, o_bk, o_bv = [dview(p, rows) for p in cols]
+        assert bool((o_pk == o_bk).all()), "joined rows must carry equal keys"
+        assert bool((o_bv * ODD == o_bk * 7).all()), "build payload does not belong to the matched key"   # bv = 7*id, bk = id*ODD
+        return torch.stack([o_pv.sum(), (o_pv * o_pv).sum()])
+
     def step(sync: bool):
-        if world > 1:
-            lpk, lpv = xch_p.exchange(pk, [pk, pv])
-        else:
-            lpk, lpv = pk, pv
-        rows, cols, _ = join.probe([lpk, lpv], sync=sync)
-        return rows, cols, lpk.numel()
+        """sync=True is the verifying pass: returns (rows, checksums)"""
+        if world == 1:
+            rows, cols, _ = join.probe([pk, pv], sync=sync)
+            return (rows, check_piece(cols, rows)) if sync else (None, None)
+        total, chk = 0, torch.zeros(2, dtype=torch.int64, device=dev)
+        for c, (lo, hi) in enumerate(bounds):
+            x = xch_p[c % len(xch_p)]
+            if done_ev[c % 2] is not None:
+                done_ev[c % 2].synchronize()          # my probe of the piece that used this buffer set has finished
+            with torch.cuda.stream(xstream):
+                lpk, lpv = x.exchange(pk[lo:hi], [pk[lo:hi], pv[lo:hi]])    # returns after the closing barrier: data has landed
+            with torch.cuda.stream(stream):
+                rows, cols, _ = join.probe([lpk, lpv], sync=sync)
+                if sync:
+                    total += rows
+                    chk += check_piece(cols, rows)
+                ev = torch.cuda.Event(); ev.record(stream); done_ev[c % 2] = ev
+        return (total, chk) if sync else (None, None)
 
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
             step(False)
-        # correctness of the timed configuration: bit-exact output row count and a checksum of checksums
-        rows, cols, nlocal = step(True)
+        # correctness of the timed configuration: bit-exact output row count, per-row invariants, checksum of checksums
+        rows, chk = step(True)
         total_rows = torch.tensor([rows], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(total_rows)
-        assert int(total_rows.item()) == npb * world, f"output rows {int(total_rows.item())} != {npb * world}"
-
-    # verify the join semantics on the device result with size-independent properties
-    with torch.cuda.stream(stream):
-        n_out = rows
-        def col_tensor(p):
-            class _A:   # __cuda_array_interface__ wrapper for a raw device pointer
-                pass
-            a = _A()
-            a.__cuda_array_interface__ = {"shape": (n_out,), "typestr": "<i8", "data": (p, False), "version": 3}
-            return torch.as_tensor(a, device=dev)
-        o_pk, o_pv, o_bk, o_bv = [col_tensor(p) for p in cols]
-        assert bool((o_pk == o_bk).all()), "joined rows must carry equal keys"
-        # build payload is 7 * id and key = id * ODD  ⇒  bv * ODD == bk * 7
-        assert bool((o_bv * ODD == o_bk * 7).all()), "build payload does not belong to the matched key"
-        chk = torch.stack([o_pv.sum(), (o_pv * o_pv).sum()])
-        if world > 1:
-            dist.all_reduce(chk)
         pvs = torch.stack([pv.sum(), (pv * pv).sum()])
         if world > 1:
-            dist.all_reduce(pvs)
+            dist.all_reduce(total_rows); dist.all_reduce(chk); dist.all_reduce(pvs)
+        assert int(total_rows.item()) == npb * world, f"output rows {int(total_rows.item())} != {npb * world}"
         assert torch.equal(chk, pvs), "every probe row must appear exactly once in the output (100% match, unique build keys)"
     stream.synchronize()
 
     # ---- timed region: value (device resident) ----------------------------------------------------------------
     sampler = ClockSampler(local)
     l0 = join.stats().kernel_launches
-    lx0 = xch_p.launches if xch_p else 0
+    lx0 = sum(x.launches for x in xch_p) if xch_p else 0
     barrier()
     if rank == 0:
         sampler.start()
@@ -290,7 +309,7 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
-    launches_extra = (xch_p.launches if xch_p else 0)
+    launches_extra = (sum(x.launches for x in xch_p) if xch_p else 0)
     launches = (join.stats().kernel_launches - l0) + (launches_extra - lx0)
     value = npb * world / (ms_step * 1e-3)
 
@@ -315,7 +334,7 @@ def run_gpu(args):
         if world == 1:
             e2e = run_e2e(args, lib, abi, torch, dev, local, rank, world, bk, bv, pk, pv, barrier)
         else:
-            e2e = run_e2e_multi(args, torch, dist, dev, stream, rank, world, pk, pv, xch_p, join, barrier)
+            e2e = run_e2e_multi(args, torch, dist, dev, stream, xstream, rank, world, pk, pv, xch_p, bounds, join, barrier)
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample on the box's host cores ------------------------------
     cpu = None
@@ -347,7 +366,9 @@ def run_gpu(args):
         print(json.dumps(line))
     join.close()
     if world > 1:
-        xch_b.close(); xch_p.close()
+        xch_b.close()
+        for x in xch_p:
+            x.close()
         dist.barrier()
         dist.destroy_process_group()
 
@@ -452,25 +473,33 @@ def run_e2e(args, lib, abi, torch, dev, local, rank, world, bk, bv, pk, pv, barr
             "timing": "host wall clock around the passes, device synchronised on both sides (host work is part of the path)"}
 
 
-def run_e2e_multi(args, torch, dist, dev, stream, rank, world, pk, pv, xch, join, barrier):
-    """N > 1 end to end: every rank's probe shard starts in pinned HOST memory; a step = H2D of the shard, key-hash
+def run_e2e_multi(args, torch, dist, dev, stream, xstream, rank, world, pk, pv, xch, bounds, join, barrier):
+    """N > 1 end to end: every rank's probe shard starts in pinned HOST memory; a step = per piece: H2D, key-hash
     exchange over NVLink, shard-local probe, D2H of the joined columns into pinned host memory."""
     npb = pk.numel()
     hk = torch.empty(npb, dtype=torch.int64, pin_memory=True); hk.copy_(pk)
     hv = torch.empty(npb, dtype=torch.int64, pin_memory=True); hv.copy_(pv)
-    cap = int(npb * 1.02) + 4096
+    piece = max(hi - lo for lo, hi in bounds)
+    cap = int(piece * 1.03) + 8192
     hout = [torch.empty(cap, dtype=torch.int64, pin_memory=True) for _ in range(4)]
-    dk = torch.empty_like(pk); dv = torch.empty_like(pv)
+    dk = [torch.empty(piece, dtype=torch.int64, device=dev) for _ in range(2)]
+    dv = [torch.empty(piece, dtype=torch.int64, device=dev) for _ in range(2)]
 
     def one_pass():
-        with torch.cuda.stream(stream):
-            dk.copy_(hk, non_blocking=True); dv.copy_(hv, non_blocking=True)
-            lpk, lpv = xch.exchange(dk, [dk, dv])
-            rows, cols, _ = join.probe([lpk, lpv], sync=True)
-            for i, p in enumerate(cols):
-                hout[i][:rows].copy_(xch._view(p, rows), non_blocking=True)
-        stream.synchronize()
-        return rows
+        total = 0
+        for c, (lo, hi) in enumerate(bounds):
+            x = xch[c % len(xch)]
+            n = hi - lo
+            with torch.cuda.stream(xstream):
+                dk[c % 2][:n].copy_(hk[lo:hi], non_blocking=True); dv[c % 2][:n].copy_(hv[lo:hi], non_blocking=True)
+                lpk, lpv = x.exchange(dk[c % 2][:n], [dk[c % 2][:n], dv[c % 2][:n]])
+            with torch.cuda.stream(stream):
+                rows, cols, _ = join.probe([lpk, lpv], sync=True)
+                for i, p in enumerate(cols):
+                    hout[i][:rows].copy_(x._view(p, rows), non_blocking=True)
+            stream.synchronize()
+            total += rows
+        return total
 
     steps = max(1, args.steps // 2)
     for _ in range(2):
@@ -488,7 +517,7 @@ def run_e2e_multi(args, torch, dist, dev, stream, rank, world, pk, pv, xch, join
     sec_step = float(tt.item()) / steps
     return {"value": npb * world / sec_step, "unit": "rows/s", "h2d_bytes_per_step": 16 * npb * world, "d2h_bytes_per_step": 32 * npb * world,
             "ms_per_step": sec_step * 1e3, "steps": steps,
-            "path": "per rank: pinned host shard -> H2D -> key-hash exchange over NVLink -> tg_join_probe_dev -> D2H of the 4 joined columns into pinned host memory",
+            "path": "per rank and piece: pinned host shard -> H2D -> key-hash exchange over NVLink -> tg_join_probe_dev -> D2H of the 4 joined columns into pinned host memory",
             "timing": "host wall clock, max over ranks, device synchronised on both sides"}
 
 
@@ -504,6 +533,7 @@ def main():
     ap.add_argument("--ref-sample-rows", type=int, default=8_000_000)
     ap.add_argument("--e2e-chunk-rows", type=int, default=4 << 20)
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--xchunks", type=int, default=4, help="N>1: pieces the probe side is exchanged in (overlap with the probe kernel)")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--ncu-traffic-bytes", type=float, default=None, help="dram bytes per launch from the committed ncu capture")

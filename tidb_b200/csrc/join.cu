@@ -676,27 +676,6 @@ static int launch_probe_tma(tg_join* j, const int64_t* pkey, int64_t ntiles, con
 }
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-// L2 partition pass with the TMA-fed scatter: full 2048-row tiles by k_partition_scatter_tma, tail by k_partition_scatter
-template <int NC>
-static int launch_scatter_tma(tg_join* j, int64_t n, PartDst& d, unsigned long long* cursors) {
-  int64_t ntiles = n / PT_TILE;
-  if (ntiles > 0) {
-    size_t smem = (size_t)2 * NC * PT_TILE * 8 + 2 * PT_TILE * 8 + 2 * 8 + 16;
-    TG_CUDA(cudaFuncSetAttribute(k_partition_scatter_tma<true, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = (int)std::min<int64_t>(ntiles, (int64_t)j->nsm * 2);
-    k_partition_scatter_tma<true, NC><<<grid, PT_BLOCK, smem, j->stream>>>(ntiles, d, cursors);
-    j->stats.kernel_launches++;
-  }
-  int64_t done = ntiles * PT_TILE;
-  if (done < n) {
-    PartDst tail = d;
-    for (int c = 0; c < NC; c++) tail.src[c] = reinterpret_cast<const unsigned long long*>(d.src[c]) + done;
-    k_partition_scatter<true><<<1, PT_BLOCK, 0, j->stream>>>(reinterpret_cast<const long long*>(tail.src[0]), nullptr, n - done, tail, cursors);
-    j->stats.kernel_launches++;
-  }
-  return TG_OK;
-}
-
 // probe `n` device-resident rows; results are appended to rb (rb.rows advanced)
 static int probe_device(tg_join* j, const DevCols& pview, int64_t n, ResultBatch& rb, bool sync_count) {
   const Side& p = j->probe;
@@ -737,31 +716,16 @@ static int probe_device(tg_join* j, const DevCols& pview, int64_t n, ResultBatch
             long long* offs = reinterpret_cast<long long*>(cursors + TG_MAX_PARTS);
             TG_CUDA(cudaMemsetAsync(counts, 0, (size_t)TG_MAX_PARTS * 8 * 3 + 8, j->stream));
             const long long* k64 = reinterpret_cast<const long long*>(pkey);
-            if (tune.tma && aligned16(k64)) k_partition_count4<true><<<grid_for(j, (n + 7) / 8, 256, 8), 256, 0, j->stream>>>(k64, n, (uint32_t)P, counts);
-            else k_partition_count<true><<<grid_for(j, n, 256, 8), 256, 0, j->stream>>>(k64, nullptr, n, (uint32_t)P, counts);
+            TG_TRY(launch_partition_count<true>(j->device, j->stream, k64, nullptr, n, (uint32_t)P, counts, &j->stats.kernel_launches));
             k_partition_offsets<<<1, 32, 0, j->stream>>>(counts, (uint32_t)P, offs, cursors);
+            j->stats.kernel_launches++;
             PartDst d{};
             d.nparts = P; d.ncols = nc;
             d.src[0] = pkey;
             for (int c = 0; c < fo.n_pcols; c++) d.src[1 + c] = fo.psrc[c];
             for (int c = 0; c < nc; c++) for (int q = 0; q < P; q++) d.dst[q][c] = j->part_cols[c]->p;
             d.dst_base = offs;
-            bool src_aligned = true;
-            for (int c = 0; c < nc; c++) src_aligned = src_aligned && aligned16(d.src[c]);
-            if (tune.tma && src_aligned) {
-              switch (nc) {
-                case 1: TG_TRY(launch_scatter_tma<1>(j, n, d, cursors)); break;
-                case 2: TG_TRY(launch_scatter_tma<2>(j, n, d, cursors)); break;
-                case 3: TG_TRY(launch_scatter_tma<3>(j, n, d, cursors)); break;
-                default: TG_TRY(launch_scatter_tma<4>(j, n, d, cursors)); break;
-              }
-              j->stats.kernel_launches += 2;
-            } else {
-              int64_t tiles = (n + PT_TILE - 1) / PT_TILE;
-              int pg = (int)std::min<int64_t>(tiles, (int64_t)j->nsm * 4);
-              k_partition_scatter<true><<<pg, PT_BLOCK, 0, j->stream>>>(k64, nullptr, n, d, cursors);
-              j->stats.kernel_launches += 3;
-            }
+            TG_TRY(launch_partition_scatter<true>(j->device, j->stream, k64, nullptr, n, d, cursors, &j->stats.kernel_launches));
             pkey = j->part_cols[0]->as<int64_t>();
             for (int c = 0; c < fo.n_pcols; c++) fo.psrc[c] = j->part_cols[1 + c]->as<unsigned long long>();
           }

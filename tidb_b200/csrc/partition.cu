@@ -38,9 +38,8 @@ int tg_partition_count(int device, const int64_t* key_dev, int64_t rows, int32_t
   if (!g.ok) return fail(TG_ERR_CUDA, "cudaSetDevice failed (no usable CUDA device)");
   cudaStream_t st = (cudaStream_t)stream;
   TG_CUDA(cudaMemsetAsync(part_counts_dev, 0, (size_t)nparts * 8, st));
-  if (rows > 0)
-    k_partition_count<false><<<pgrid(device, rows, 256, 8), 256, 0, st>>>(reinterpret_cast<const long long*>(key_dev), nullptr, rows, (uint32_t)nparts,
-                                                                   reinterpret_cast<unsigned long long*>(part_counts_dev));
+  TG_TRY(launch_partition_count<false>(device, st, reinterpret_cast<const long long*>(key_dev), nullptr, rows, (uint32_t)nparts,
+                                       reinterpret_cast<unsigned long long*>(part_counts_dev), nullptr));
   TG_CUDA(cudaGetLastError());
   return TG_OK;
 }
@@ -58,13 +57,13 @@ int tg_partition_by_key(int device, const int64_t* key_dev, const uint8_t* key_n
   unsigned long long* cursors = counts + TG_MAX_PARTS;
   TG_CUDA(cudaMemsetAsync(counts, 0, (size_t)TG_MAX_PARTS * 16, st));
   const long long* key = reinterpret_cast<const long long*>(key_dev);
-  if (rows > 0) k_partition_count<false><<<pgrid(device, rows, 256, 8), 256, 0, st>>>(key, key_nulls_dev, rows, (uint32_t)nparts, counts);
+  TG_TRY(launch_partition_count<false>(device, st, key, key_nulls_dev, rows, (uint32_t)nparts, counts, nullptr));
   k_partition_offsets<<<1, 32, 0, st>>>(counts, (uint32_t)nparts, reinterpret_cast<long long*>(part_offsets_dev), cursors);
   PartDst d{};
   d.nparts = nparts; d.ncols = ncols;
   for (int c = 0; c < ncols; c++) { d.src[c] = src_cols_dev[c]; for (int p = 0; p < nparts; p++) d.dst[p][c] = dst_cols_dev[c]; }
   d.dst_base = reinterpret_cast<const long long*>(part_offsets_dev);
-  if (rows > 0) k_partition_scatter<false><<<pgrid(device, rows, PT_TILE, 4), PT_BLOCK, 0, st>>>(key, key_nulls_dev, rows, d, cursors);
+  TG_TRY(launch_partition_scatter<false>(device, st, key, key_nulls_dev, rows, d, cursors, nullptr));
   TG_CUDA(cudaGetLastError());
   TG_CUDA(cudaStreamSynchronize(st));   // scratch is freed on return
   return TG_OK;
@@ -86,8 +85,7 @@ int tg_partition_exchange(int device, const int64_t* key_dev, int64_t rows, int3
   d.nparts = nparts; d.ncols = ncols;
   for (int c = 0; c < ncols; c++) { d.src[c] = src_cols_dev[c]; for (int p = 0; p < nparts; p++) d.dst[p][c] = recv_cols_peer[p * ncols + c]; }
   d.dst_base = reinterpret_cast<const long long*>(recv_base_dev);
-  if (rows > 0)
-    k_partition_scatter<false><<<pgrid(device, rows, PT_TILE, 4), PT_BLOCK, 0, st>>>(reinterpret_cast<const long long*>(key_dev), nullptr, rows, d, cursors);
+  TG_TRY(launch_partition_scatter<false>(device, st, reinterpret_cast<const long long*>(key_dev), nullptr, rows, d, cursors, nullptr));
   TG_CUDA(cudaGetLastError());
   TG_CUDA(cudaStreamSynchronize(st));
   return TG_OK;

@@ -4,6 +4,7 @@
 #pragma once
 #include "common.cuh"
 #include "tma.cuh"
+#include <algorithm>
 
 namespace tg {
 
@@ -280,6 +281,72 @@ k_partition_count4(const long long* __restrict__ key, int64_t n, uint32_t nparts
   }
   __syncthreads();
   if (threadIdx.x < nparts && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], s_cnt[threadIdx.x]);
+}
+
+
+// ---- host launchers shared by partition.cu (across GPUs, low hash bits) and join.cu (L2 partitions, top bits) ----------
+inline bool ptr_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <bool HIGH>
+inline int launch_partition_count(int device, cudaStream_t st, const long long* key, const uint8_t* nulls, int64_t n, uint32_t nparts,
+                                  unsigned long long* counts, int64_t* launches) {
+  if (n <= 0) return TG_OK;
+  int nsm = device_sm_count(device);
+  if (!nulls && ptr_aligned16(key)) {
+    int64_t need = ((n + 7) / 8 + 255) / 256;
+    int grid = (int)std::min<int64_t>(std::max<int64_t>(need, 1), (int64_t)nsm * 8);
+    k_partition_count4<HIGH><<<grid, 256, 0, st>>>(key, n, nparts, counts);
+  } else {
+    int64_t need = (n + 255) / 256;
+    int grid = (int)std::min<int64_t>(std::max<int64_t>(need, 1), (int64_t)nsm * 8);
+    k_partition_count<HIGH><<<grid, 256, 0, st>>>(key, nulls, n, nparts, counts);
+  }
+  if (launches) (*launches)++;
+  return TG_OK;
+}
+
+template <bool HIGH, int NC>
+inline int launch_scatter_nc(int device, cudaStream_t st, int64_t n, PartDst& d, unsigned long long* cursors, int64_t* launches) {
+  int nsm = device_sm_count(device);
+  int64_t ntiles = n / PT_TILE;
+  if (ntiles > 0) {
+    size_t smem = (size_t)2 * NC * PT_TILE * 8 + 2 * PT_TILE * 8 + 2 * 8 + 16;
+    TG_CUDA(cudaFuncSetAttribute(k_partition_scatter_tma<HIGH, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = (int)std::min<int64_t>(ntiles, (int64_t)nsm * 2);
+    k_partition_scatter_tma<HIGH, NC><<<grid, PT_BLOCK, smem, st>>>(ntiles, d, cursors);
+    if (launches) (*launches)++;
+  }
+  int64_t done = ntiles * PT_TILE;
+  if (done < n) {
+    PartDst tail = d;
+    for (int c = 0; c < NC; c++) tail.src[c] = reinterpret_cast<const unsigned long long*>(d.src[c]) + done;
+    k_partition_scatter<HIGH><<<1, PT_BLOCK, 0, st>>>(reinterpret_cast<const long long*>(tail.src[0]), nullptr, n - done, tail, cursors);
+    if (launches) (*launches)++;
+  }
+  return TG_OK;
+}
+
+// d.src[0] must be the key column; falls back to the LSU kernel for NULL-able keys, unaligned sources or > 4 columns
+template <bool HIGH>
+inline int launch_partition_scatter(int device, cudaStream_t st, const long long* key, const uint8_t* nulls, int64_t n, PartDst& d,
+                                    unsigned long long* cursors, int64_t* launches) {
+  if (n <= 0) return TG_OK;
+  bool tma_ok = !nulls && d.ncols <= 4 && d.src[0] == (const void*)key;
+  for (int c = 0; c < d.ncols && tma_ok; c++) tma_ok = ptr_aligned16(d.src[c]);
+  if (tma_ok) {
+    switch (d.ncols) {
+      case 1: return launch_scatter_nc<HIGH, 1>(device, st, n, d, cursors, launches);
+      case 2: return launch_scatter_nc<HIGH, 2>(device, st, n, d, cursors, launches);
+      case 3: return launch_scatter_nc<HIGH, 3>(device, st, n, d, cursors, launches);
+      default: return launch_scatter_nc<HIGH, 4>(device, st, n, d, cursors, launches);
+    }
+  }
+  int nsm = device_sm_count(device);
+  int64_t tiles = (n + PT_TILE - 1) / PT_TILE;
+  int grid = (int)std::min<int64_t>(tiles, (int64_t)nsm * 4);
+  k_partition_scatter<HIGH><<<grid, PT_BLOCK, 0, st>>>(key, nulls, n, d, cursors);
+  if (launches) (*launches)++;
+  return TG_OK;
 }
 
 }  // namespace tg
