@@ -533,7 +533,7 @@ def main():
     ap.add_argument("--ref-sample-rows", type=int, default=8_000_000)
     ap.add_argument("--e2e-chunk-rows", type=int, default=4 << 20)
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
-    ap.add_argument("--xchunks", type=int, default=4, help="N>1: pieces the probe side is exchanged in (overlap with the probe kernel)")
+    ap.add_argument("--xchunks", type=int, default=1, help="N>1: pieces the probe side is exchanged in (overlap with the probe kernel)")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--ncu-traffic-bytes", type=float, default=None, help="dram bytes per launch from the committed ncu capture")
