@@ -225,7 +225,8 @@ def run_gpu(args):
             # NVLink scatter of piece c+1 overlaps the probe kernel of piece c
             xch_p = [KeyExchange(rank, world, local, xstream, 2, int(npb / xchunks * 1.03) + 8192, args.exchange) for _ in range(2 if xchunks > 1 else 1)]
         # leave room on every SM for the scatter CTAs next to the persistent probe CTAs
-        os.environ.setdefault("TG_PROBE_CTAS_PER_SM", "2" if xchunks > 1 else "8")
+        if xchunks > 1:
+            os.environ.setdefault("TG_PROBE_CTAS_PER_SM", "2")
 
     join = DeviceJoin(plan)
     with torch.cuda.stream(stream):

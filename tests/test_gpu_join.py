@@ -207,12 +207,14 @@ def test_partial_match_and_stats():
     assert np.array_equal(columns_sorted(ocols), columns_sorted([(g, np.zeros(len(g), dtype=bool)) for g in got]))
 
 
-@pytest.mark.parametrize("env", [dict(TG_PROBE_TMA="1", TG_PROBE_PARTITION="1"), dict(TG_PROBE_TMA="0", TG_PROBE_PARTITION="1"),
-                                 dict(TG_PROBE_TMA="1", TG_PROBE_PARTITION="0"), dict(TG_PROBE_VARIANT="0")])
+@pytest.mark.parametrize("env", [dict(TG_PROBE_PARTITION="1", TG_PROBE_PARTS="5"), dict(TG_PROBE_PARTITION="1", TG_PROBE_PARTS="16"),
+                                 dict(TG_PROBE_PARTITION="1", TG_PROBE_PARTS="7", TG_PROBE_SEG_VEC="0"),
+                                 dict(TG_PROBE_PARTITION="2", TG_PROBE_PARTS="5", TG_PROBE_TMA="1"), dict(TG_PROBE_PARTITION="2", TG_PROBE_PARTS="3", TG_SCATTER_BULK="0"),
+                                 dict(TG_PROBE_TMA="1", TG_PROBE_PARTITION="0"), dict(TG_PROBE_PARTITION="0"), dict(TG_PROBE_VARIANT="0")])
 def test_fused_probe_variants_forced(env, monkeypatch):
     # every launch variant of the fused fast path (TMA-fed ring, L2 partition pass, warp kernel, CTA-tile kernel) must
     # give the same multiset; odd sizes exercise the tail tiles; PART_MIN_MB=0 forces the partition pass on a small table
-    for k, v in dict(env, TG_PROBE_PART_MIN_MB="0").items():
+    for k, v in dict(env, TG_PROBE_PART_MIN_MB="0", TG_PROBE_PART_MIN_ROWS="0").items():
         monkeypatch.setenv(k, v)
     rng = np.random.default_rng(17)
     nb, npr = 300_001, 2_500_003
@@ -234,6 +236,30 @@ def test_fused_probe_variants_forced(env, monkeypatch):
     assert np.array_equal(got[0], pk[got[1]]) and np.array_equal(got[2], got[0])     # keys travel with their row
     exp_pay = (order[pos] * 3)[got[1]]
     assert np.array_equal(got[3], exp_pay)                                           # and with the right build payload
+
+
+def test_partitioned_probe_overflow_falls_back(monkeypatch):
+    # count-free L2 partitioning gives every segment a fixed capacity; a skewed probe side (70 % of the rows carry ONE key)
+    # overflows its segment, the partitioned probe launch exits on the device-side flag and the gated direct launch
+    # produces the result instead — same multiset either way
+    for k, v in dict(TG_PROBE_PARTITION="1", TG_PROBE_PARTS="8", TG_PROBE_PART_MIN_MB="0", TG_PROBE_PART_MIN_ROWS="0").items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(23)
+    nb, npr = 200_000, 2_000_000
+    bk = rng.permutation(nb).astype(np.int64) * 2654435761 + 11
+    build = Chunk([Column(bk), Column(np.arange(nb, dtype=np.int64) + 5)])
+    pk = bk[rng.integers(0, nb, npr)]
+    pk[rng.random(npr) < 0.7] = bk[12345]
+    probe = Chunk([Column(pk), Column(np.arange(npr, dtype=np.int64))])
+    plan = JoinPlan(abi.JOIN_INNER, [INT_NN, INT_NN], [INT_NN, INT_NN], [0], [0])
+    e = HashJoinExec(plan, MockDataSource(plan.left_types, [probe]), MockDataSource(plan.right_types, [build]))
+    chunks = drain(e, 1 << 22)
+    got = [np.concatenate([c.columns[i].data for c in chunks]) for i in range(4)]
+    assert len(got[0]) == npr
+    assert np.array_equal(np.sort(got[1]), np.arange(npr))
+    assert np.array_equal(got[0], pk[got[1]]) and np.array_equal(got[2], got[0])
+    order = np.argsort(bk)
+    assert np.array_equal(got[3], order[np.searchsorted(bk[order], got[0])] + 5)
 
 
 def test_concurrent_push_and_next_wait_and_rewind():

@@ -582,17 +582,18 @@ static bool fast_path_ok(const tg_join* j, const DevCols& pview) {
 }
 
 // ---- fast-path launch tuning (env overrides are for A/B sweeps on the GPU box; defaults are the measured best) ----
-struct ProbeTuning { int variant; int R; int evict_last; int ctas_per_sm; int partition; int parts; int part_min_mb; int tma; int stages; int tma_ctas; int cta_agg; };
+struct ProbeTuning { int variant; int R; int evict_last; int ctas_per_sm; int partition; int parts; int part_min_mb; int part_min_rows; int seg_vec; int tma; int stages; int tma_ctas; int cta_agg; };
 static ProbeTuning probe_tuning() {
   ProbeTuning t;
   t.variant = env_int("TG_PROBE_VARIANT", 1);      // 0: CTA-tile kernel (shared-memory offsets), 1: warp-autonomous kernel
   t.R = env_int("TG_PROBE_R", 4);
   t.evict_last = env_int("TG_PROBE_EVICT_LAST", 0);
-  t.ctas_per_sm = env_int("TG_PROBE_CTAS_PER_SM", 8);
-  if (t.ctas_per_sm < 1) t.ctas_per_sm = 1;
-  t.partition = env_int("TG_PROBE_PARTITION", 0);   // split big probes into L2-sized partitions first
+  t.ctas_per_sm = env_int("TG_PROBE_CTAS_PER_SM", 0);   // 0 = exactly the resident CTA count (occupancy query)
+  t.partition = env_int("TG_PROBE_PARTITION", 1);   // regroup big probes into L2-sized partitions first (0 = never, 2 = counted/dense variant)
   t.parts = env_int("TG_PROBE_PARTS", 0);           // 0 = auto: table slices of <= 32 MB
   t.part_min_mb = env_int("TG_PROBE_PART_MIN_MB", 64);
+  t.part_min_rows = env_int("TG_PROBE_PART_MIN_ROWS", 1 << 22);
+  t.seg_vec = env_int("TG_PROBE_SEG_VEC", 1);            // 128-bit loads/stores in the segment probe
   t.tma = env_int("TG_PROBE_TMA", 0);               // TMA-fed kernels (cp.async.bulk ring) for the streamed inputs
   t.stages = env_int("TG_PROBE_STAGES", 4);
   t.tma_ctas = env_int("TG_PROBE_TMA_CTAS", 3);
@@ -639,12 +640,36 @@ static int dispatch_shape(const FastOut& fo, A&&... a) {
 
 template <int NPC, int NKD, int NMD>
 struct LaunchWarp {
-  static int run(tg_join* j, const int64_t* pkey, int64_t n, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t) {
+  static int run(tg_join* j, const int64_t* pkey, int64_t n, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t, const SegSpec& seg) {
     constexpr int R = 4;
+    static int resident = 0;   // CTAs of this instantiation one SM holds (register-bound, 3 on sm_100a)
+    if (!resident) {
+      int nb = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_probe_inner_u1_w<R, NPC, NKD, NMD>, 256, 0) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 3; }
+      resident = nb;
+      if (getenv("TG_DEBUG")) fprintf(stderr, "[tidbgpu] k_probe_inner_u1_w<%d,%d,%d>: %d resident CTAs per SM\n", NPC, NKD, NMD, nb);
+    }
     int64_t tiles = (n + 32 * R - 1) / (32 * R);
     int64_t ctas = (tiles + 7) / 8;
-    int grid = (int)std::min<int64_t>(ctas, (int64_t)j->nsm * t.ctas_per_sm);
-    k_probe_inner_u1_w<R, NPC, NKD, NMD><<<grid, 256, 0, j->stream>>>(pkey, n, j->tv, fo, cur);
+    int per_sm = t.ctas_per_sm > 0 ? t.ctas_per_sm : resident;
+    int grid = (int)std::min<int64_t>(ctas, (int64_t)j->nsm * per_sm);
+    k_probe_inner_u1_w<R, NPC, NKD, NMD><<<grid, 256, 0, j->stream>>>(pkey, n, j->tv, fo, cur, seg);
+    return TG_OK;
+  }
+};
+template <int NPC, int NKD, int NMD>
+struct LaunchSeg {
+  static int run(tg_join* j, const int64_t* pkey, int64_t n, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t, const SegSpec& seg) {
+    static int resident = 0;
+    if (!resident) {
+      int nb = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_probe_inner_u1_seg<NPC, NKD, NMD>, 256, 0) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 3; }
+      resident = nb;
+    }
+    int64_t ctas = (n / 128 + 7) / 8;
+    int per_sm = t.ctas_per_sm > 0 ? t.ctas_per_sm : resident;
+    int grid = (int)std::min<int64_t>(ctas, (int64_t)j->nsm * per_sm);
+    k_probe_inner_u1_seg<NPC, NKD, NMD><<<grid, 256, 0, j->stream>>>(pkey, n, j->tv, fo, cur, seg);
     return TG_OK;
   }
 };
@@ -668,8 +693,12 @@ struct LaunchTma {
     return TG_OK;
   }
 };
-static int launch_probe_warp(tg_join* j, const int64_t* pkey, int64_t n, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t) {
-  return dispatch_shape<LaunchWarp>(fo, j, pkey, n, fo, cur, t);
+static int launch_probe_warp(tg_join* j, const int64_t* pkey, int64_t n, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t,
+                             const SegSpec& seg = SegSpec{nullptr, 0, 0, 0, nullptr}) {
+  return dispatch_shape<LaunchWarp>(fo, j, pkey, n, fo, cur, t, seg);
+}
+static int launch_probe_seg(tg_join* j, const int64_t* pkey, int64_t n, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t, const SegSpec& seg) {
+  return dispatch_shape<LaunchSeg>(fo, j, pkey, n, fo, cur, t, seg);
 }
 static int launch_probe_tma(tg_join* j, const int64_t* pkey, int64_t ntiles, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t) {
   return dispatch_shape<LaunchTma>(fo, j, pkey, ntiles, fo, cur, t);
@@ -697,11 +726,56 @@ static int probe_device(tg_join* j, const DevCols& pview, int64_t n, ResultBatch
       if (warp_ok) {
         const int64_t* pkey = reinterpret_cast<const int64_t*>(ks.data);
         size_t table_bytes = (size_t)j->tv.nslots * sizeof(Slot);
-        if (tune.partition && n >= (1ll << 20) && table_bytes > ((size_t)tune.part_min_mb << 20)) {
-          // L2 partition pass: regroup the probe rows by the TOP hash bits.  slot = mulhi(hash, nslots) is monotone
-          // in the hash, so partition p only touches the contiguous table slice [p/P, (p+1)/P) — 20-32 MB that stay
-          // L2 resident while the fused probe kernel sweeps the partition.  Trades 32 B/row of extra streaming
-          // traffic for ~100 B/row of random HBM traffic (ncu: profiles/r1_probe_first.md).
+        bool src16 = aligned16(pkey);
+        for (int c = 0; c < fo.n_pcols; c++) src16 = src16 && aligned16(fo.psrc[c]);
+        const int64_t PTILE = 1024;   // rows per scatter tile (k_partition_scatter_bulk<.., 4>)
+        if (tune.partition == 1 && src16 && scatter_bulk_enabled() && n >= (int64_t)tune.part_min_rows && table_bytes > ((size_t)tune.part_min_mb << 20)) {
+          // L2 partition pass, count-free: regroup the probe rows by the TOP hash bits into P fixed-capacity segments.
+          // slot = mulhi(hash, nslots) is monotone in the hash, so segment p only touches the contiguous table slice
+          // [p/P, (p+1)/P) — ~32 MB that stay L2 resident while the probe kernel sweeps the segment.  Trades 32 B/row of
+          // extra streaming traffic (0.57 ms per 100 M rows) for ~100 B/row of random HBM traffic (probe 2.5 → 1.45 ms);
+          // profiles/r1_probe_lab.md.  A skewed probe side that overflows a segment raises `flag`; the partitioned probe
+          // launch then exits at once and the gated direct launch behind it does the work — no host round trip.
+          int P = tune.parts > 0 ? tune.parts : (int)((table_bytes + (32u << 20) - 1) / (32u << 20));
+          if (P > TG_MAX_PARTS) P = TG_MAX_PARTS;
+          const int64_t n_main = n / PTILE * PTILE;
+          const int64_t C = ((int64_t)((double)n_main / P * 1.05) + 16384 + 127) / 128 * 128;
+          if (P >= 2 && (int64_t)P * C / 128 < (1ll << 31)) {
+            const int nc = 1 + fo.n_pcols;
+            for (int c = 0; c < nc; c++) {
+              if (!j->part_cols[c]) j->part_cols[c].reset(new DevBuf());
+              TG_TRY(j->part_cols[c]->ensure(j->device, (size_t)P * C * 8 + 64));
+            }
+            TG_TRY(j->part_scratch.ensure(j->device, (size_t)TG_MAX_PARTS * 8 * 2 + 64));
+            unsigned long long* cursors = j->part_scratch.as<unsigned long long>();     // fill count per segment
+            long long* bases = reinterpret_cast<long long*>(cursors + TG_MAX_PARTS);     // first row of each segment
+            unsigned long long* flag = cursors + 2 * TG_MAX_PARTS;                       // overflow
+            k_segment_bases<<<1, 32, 0, j->stream>>>(cursors, bases, flag, P, C);
+            PartDst d{};
+            d.nparts = P; d.ncols = nc;
+            d.src[0] = pkey;
+            for (int c = 0; c < fo.n_pcols; c++) d.src[1 + c] = fo.psrc[c];
+            for (int c = 0; c < nc; c++) for (int q = 0; q < P; q++) d.dst[q][c] = j->part_cols[c]->p;
+            d.dst_base = bases; d.capacity = C; d.overflow = flag;
+            TG_TRY(launch_partition_scatter<true>(j->device, j->stream, reinterpret_cast<const long long*>(pkey), nullptr, n_main, d, cursors,
+                                                  &j->stats.kernel_launches));
+            FastOut pf = fo;
+            for (int c = 0; c < fo.n_pcols; c++) pf.psrc[c] = j->part_cols[1 + c]->as<unsigned long long>();
+            if (tune.seg_vec) TG_TRY(launch_probe_seg(j, j->part_cols[0]->as<int64_t>(), (int64_t)P * C, pf, cur, tune, SegSpec{cursors, (uint32_t)(C / 128), 0, C, flag}));
+            else TG_TRY(launch_probe_warp(j, j->part_cols[0]->as<int64_t>(), (int64_t)P * C, pf, cur, tune, SegSpec{cursors, (uint32_t)(C / 128), 0, C, flag}));
+            TG_TRY(launch_probe_warp(j, pkey, n_main, fo, cur, tune, SegSpec{nullptr, 0, 1, 0, flag}));   // runs only after an overflow
+            j->stats.kernel_launches += 3;
+            if (n_main < n) {
+              FastOut tail = fo;
+              for (int c = 0; c < fo.n_pcols; c++) tail.psrc[c] = fo.psrc[c] + n_main;
+              TG_TRY(launch_probe_warp(j, pkey + n_main, n - n_main, tail, cur, tune));
+              j->stats.kernel_launches++;
+            }
+            goto fast_done;
+          }
+        }
+        if (tune.partition == 2 && n >= (1ll << 20) && table_bytes > ((size_t)tune.part_min_mb << 20)) {
+          // counted variant (kept for A/B runs): histogram pass → exact offsets → dense partitions
           int P = tune.parts > 0 ? tune.parts : (int)((table_bytes + (32u << 20) - 1) / (32u << 20));
           if (P > TG_MAX_PARTS) P = TG_MAX_PARTS;
           if (P >= 2) {
@@ -744,11 +818,12 @@ static int probe_device(tg_join* j, const DevCols& pview, int64_t n, ResultBatch
       } else {
         constexpr int R = 4;
         int64_t tiles = (n + 256 * R - 1) / (256 * R);
-        int grid = (int)std::min<int64_t>(tiles, (int64_t)j->nsm * tune.ctas_per_sm);
+        int grid = (int)std::min<int64_t>(tiles, (int64_t)j->nsm * (tune.ctas_per_sm > 0 ? tune.ctas_per_sm : 8));
         k_probe_inner_u1<R><<<grid, 256, 0, j->stream>>>(reinterpret_cast<const int64_t*>(ks.data), pview, n, j->tv, oc, cur);
       }
       j->stats.kernel_launches++;
     }
+  fast_done:
     if (sync_count) {
       unsigned long long got = 0;
       TG_CUDA(cudaMemcpyAsync(&got, cur, 8, cudaMemcpyDeviceToHost, j->stream));

@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "tma.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace tg {
 
@@ -20,6 +21,10 @@ struct PartDst {
   void* dst[TG_MAX_PARTS][TG_PART_MAX_COLS];   // column base per destination
   // row offset inside the destination buffers where this launch starts writing, per destination
   const long long* dst_base;                   // device array [nparts]
+  // capacity > 0: destination p may hold at most `capacity` rows (count-free partitioning into fixed-size segments);
+  // rows beyond it are dropped and *overflow is set — the caller then falls back to an unpartitioned pass.
+  long long capacity;
+  unsigned long long* overflow;
 };
 
 // HIGH = false: destination GPU, low 32 hash bits (disjoint from the slot bits).
@@ -67,6 +72,13 @@ static __global__ void k_partition_offsets(const unsigned long long* counts, uin
     for (uint32_t p = 0; p < nparts; p++) { part_offsets[p] = run; cursors[p] = 0; run += (long long)counts[p]; }
     part_offsets[nparts] = run;
   }
+}
+
+// count-free partitioning: zero the fill counters and the overflow flag, lay the segments out back to back
+static __global__ void k_segment_bases(unsigned long long* cursors, long long* bases, unsigned long long* flag, int nparts, long long cap) {
+  if (threadIdx.x < TG_MAX_PARTS) { cursors[threadIdx.x] = 0; bases[threadIdx.x] = (long long)threadIdx.x * cap; }
+  if (threadIdx.x == 0) *flag = 0;
+  (void)nparts;
 }
 
 template <bool HIGH>
@@ -184,12 +196,9 @@ k_partition_scatter_tma(int64_t ntiles, PartDst d, unsigned long long* __restric
       key[j] = in[j * PT_BLOCK + tid];
       uint64_t h = hash64(key[j]);
       uint32_t p = HIGH ? mulhi32((uint32_t)(h >> 32), P) : part_of(h, P);
-      unsigned peers = __match_any_sync(0xffffffffu, p);
-      int leader = __ffs(peers) - 1;
-      uint32_t wbase = 0;
-      if (lane == leader) wbase = atomicAdd(&s_cnt[p], (uint32_t)__popc(peers));
-      wbase = __shfl_sync(peers, wbase, leader);
-      pr[j] = (p << 16) | (wbase + __popc(peers & ((1u << lane) - 1)));
+      // rank inside (tile, destination): one shared-memory atomic per row.  Warp-aggregating it (match_any + leader
+      // election) was measured 1.6x SLOWER end to end (tools/scratch/probe_lab.cu: 0.92 vs 0.58 ms per 100 M rows).
+      pr[j] = (p << 16) | atomicAdd(&s_cnt[p], 1u);
     }
     __syncthreads();
     if (tid < 32) {   // exclusive scan of the P counts by one warp + one global reservation per destination
@@ -227,6 +236,109 @@ k_partition_scatter_tma(int64_t ntiles, PartDst d, unsigned long long* __restric
       __syncthreads();
     }
   }
+}
+
+// shared → global bulk store (cp.async.bulk, bulk_group completion) and its fences
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Scatter with the copy engine on BOTH sides (8-byte columns, no NULL keys): source tiles arrive through a 2-stage
+// cp.async.bulk ring; each tile is regrouped by destination inside a shared-memory staging buffer and every
+// (destination, column) run leaves as ONE bulk store (SASS UBLKCP ... to global; local HBM or a peer over NVLink).
+// The run of destination p is parked at a staging offset whose parity equals the parity of its global row, so the
+// 16-byte aligned middle of the run is a legal bulk copy; an odd head / tail element goes out as a scalar store.
+// Threads only touch shared memory: per row one LDS + one atomic (rank) and, per column, one LDS + one STS.
+// Count-free mode (d.capacity > 0): destinations are fixed-size segments and the global cursor atomics are the only
+// bookkeeping — no histogram pass over the keys.  Full TILE-row tiles only; the caller handles the tail.
+template <bool HIGH, int NC, int ITEMS>
+__global__ void __launch_bounds__(PT_BLOCK)
+k_partition_scatter_bulk(int64_t ntiles, PartDst d, unsigned long long* __restrict__ cursors) {
+  constexpr int STAGES = 2, TILE = PT_BLOCK * ITEMS, SROWS = TILE + 2 * TG_MAX_PARTS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned long long* ring = reinterpret_cast<unsigned long long*>(smem_raw);      // [STAGES][NC][TILE]
+  unsigned long long* stage = ring + (size_t)STAGES * NC * TILE;                   // [NC][SROWS]
+  uint64_t* full = reinterpret_cast<uint64_t*>(stage + (size_t)NC * SROWS);
+  __shared__ uint32_t s_cnt[TG_MAX_PARTS], s_off[TG_MAX_PARTS], s_len[TG_MAX_PARTS];
+  __shared__ unsigned long long s_gbase[TG_MAX_PARTS];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t P = (uint32_t)d.nparts;
+  const unsigned long long pol = l2_policy_evict_first();
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](int64_t it) {
+    int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
+    if (tile >= ntiles) return;
+    int s = (int)(it % STAGES);
+    mbar_arrive_expect_tx(&full[s], (uint32_t)(NC * TILE * 8));
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+      bulk_g2s(ring + ((size_t)s * NC + c) * TILE, reinterpret_cast<const unsigned long long*>(d.src[c]) + tile * TILE, TILE * 8, &full[s], pol);
+  };
+  if (tid == 0) for (int it = 0; it < STAGES; it++) issue(it);
+  for (int64_t it = 0;; it++) {
+    const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
+    if (tile >= ntiles) break;
+    const int s = (int)(it % STAGES);
+    if (tid < TG_MAX_PARTS) s_cnt[tid] = 0;
+    mbar_wait(&full[s], (uint32_t)((it / STAGES) & 1));
+    __syncthreads();
+    const unsigned long long* in = ring + (size_t)s * NC * TILE;
+    uint32_t pr[ITEMS];   // destination << 16 | rank inside (tile, destination)
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+      uint64_t h = hash64(in[j * PT_BLOCK + tid]);
+      uint32_t p = HIGH ? mulhi32((uint32_t)(h >> 32), P) : part_of(h, P);
+      pr[j] = (p << 16) | atomicAdd(&s_cnt[p], 1u);
+    }
+    __syncthreads();
+    if (tid < 32) {
+      uint32_t c = tid < (int)P ? s_cnt[tid] : 0, len = c;
+      unsigned long long g = 0;
+      if (tid < (int)P) {
+        unsigned long long old = c ? atomicAdd(&cursors[tid], (unsigned long long)c) : 0ull;
+        if (d.capacity > 0) {
+          unsigned long long avail = old < (unsigned long long)d.capacity ? (unsigned long long)d.capacity - old : 0ull;
+          if ((unsigned long long)c > avail) { len = (uint32_t)avail; *d.overflow = 1ull; }
+        }
+        g = old + (unsigned long long)d.dst_base[tid];
+      }
+      uint32_t w = tid < (int)P ? (((uint32_t)(g & 1) + c + 1) & ~1u) : 0, incl = w;
+      for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+      if (tid < (int)P) { s_off[tid] = incl - w + (uint32_t)(g & 1); s_gbase[tid] = g; s_len[tid] = len; }
+    }
+    if (tid < (int)P * NC) bulk_wait_read_all();   // the previous tile's bulk stores have read the staging buffer
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+#pragma unroll
+      for (int j = 0; j < ITEMS; j++)
+        stage[(size_t)c * SROWS + s_off[pr[j] >> 16] + (pr[j] & 0xffffu)] = in[(size_t)c * TILE + j * PT_BLOCK + tid];
+    }
+    fence_async_smem();              // generic-proxy STS → visible to the async proxy that executes the bulk stores
+    __syncthreads();                 // staging complete, ring stage s fully consumed (LDS results fed the STS above)
+    if (tid == 0) issue(it + STAGES);
+    if (tid < (int)P * NC) {
+      const uint32_t p = tid / NC, c = tid % NC;
+      const unsigned long long g = s_gbase[p];
+      const uint32_t len = s_len[p], so = s_off[p];
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(d.dst[p][c]);
+      const unsigned long long* src = stage + (size_t)c * SROWS;
+      const uint32_t head = (uint32_t)(g & 1) & (len > 0 ? 1u : 0u);
+      const uint32_t mid = (len - head) & ~1u;
+      if (mid) bulk_s2g(dst + g + head, src + so + head, mid * 8);
+      bulk_commit();
+      if (head) dst[g] = src[so];
+      if ((len - head) & 1u) dst[g + len - 1] = src[so + len - 1];
+    }
+  }
+  if (tid < (int)P * NC) bulk_wait_read_all();
 }
 
 // histogram of destinations: 128-bit loads, 4 in flight per thread, counts packed 8 x 8 bit in two 64-bit registers
@@ -305,9 +417,37 @@ inline int launch_partition_count(int device, cudaStream_t st, const long long* 
   return TG_OK;
 }
 
+inline int scatter_bulk_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TG_SCATTER_BULK"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
 template <bool HIGH, int NC>
 inline int launch_scatter_nc(int device, cudaStream_t st, int64_t n, PartDst& d, unsigned long long* cursors, int64_t* launches) {
   int nsm = device_sm_count(device);
+  if (scatter_bulk_enabled()) {
+    // 1024-row tiles: 4 CTAs per SM for NC <= 2 (profiles/r1_scatter_bulk.md)
+    constexpr int ITEMS = 4, TILE = PT_BLOCK * ITEMS;
+    int64_t ntiles = n / TILE;
+    if (ntiles > 0) {
+      size_t smem = (size_t)2 * NC * TILE * 8 + (size_t)NC * (TILE + 2 * TG_MAX_PARTS) * 8 + 2 * 8 + 16;
+      TG_CUDA(cudaFuncSetAttribute(k_partition_scatter_bulk<HIGH, NC, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(220 * 1024) / (smem + 1024)));
+      int grid = (int)std::min<int64_t>(ntiles, (int64_t)nsm * per_sm);
+      k_partition_scatter_bulk<HIGH, NC, ITEMS><<<grid, PT_BLOCK, smem, st>>>(ntiles, d, cursors);
+      if (launches) (*launches)++;
+    }
+    int64_t done = ntiles * TILE;
+    if (done < n) {
+      if (d.capacity > 0) return fail(TG_ERR_CUDA, "internal: capacity-bounded scatter needs a whole number of tiles");
+      PartDst tail = d;
+      for (int c = 0; c < NC; c++) tail.src[c] = reinterpret_cast<const unsigned long long*>(d.src[c]) + done;
+      k_partition_scatter<HIGH><<<1, PT_BLOCK, 0, st>>>(reinterpret_cast<const long long*>(tail.src[0]), nullptr, n - done, tail, cursors);
+      if (launches) (*launches)++;
+    }
+    return TG_OK;
+  }
   int64_t ntiles = n / PT_TILE;
   if (ntiles > 0) {
     size_t smem = (size_t)2 * NC * PT_TILE * 8 + 2 * PT_TILE * 8 + 2 * 8 + 16;

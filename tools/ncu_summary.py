@@ -23,6 +23,7 @@ for v, h in sorted(st, reverse=True)[:8]:
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 if rows:
+    if rows[0] and rows[0][0] == 'Kernel Name': rows = rows[1:]
     h = rows[0]
     try:
         ci = h.index("Source"); si = [i for i, x in enumerate(h) if x.startswith("Warp Stall Sampling (All")][0]
