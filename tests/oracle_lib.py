@@ -199,7 +199,7 @@ def vec_compare_int(op, a: Column, b: Optional[Column], b_const=0, a_unsigned=Fa
     res = np.zeros(n, dtype=np.int64); nulls = np.zeros((n + 7) // 8, dtype=np.uint8)
     pa, ka = _colptr(a); pb, kb = _colptr(b)
     rc = lib().orc_vec_compare_int(op, int(a_unsigned), int(b_unsigned), pa, pb, C.c_int64(b_const),
-                                   res.ctypes.data, nulls.ctypes.data)
+                                   C.c_void_p(res.ctypes.data), C.c_void_p(nulls.ctypes.data))
     assert rc == 0, _err()
     return res, np.unpackbits(nulls, bitorder="little")[:n] == 0
 
@@ -208,7 +208,7 @@ def vec_compare_real(op, a: Column, b: Optional[Column], b_const=0.0):
     n = a.length
     res = np.zeros(n, dtype=np.int64); nulls = np.zeros((n + 7) // 8, dtype=np.uint8)
     pa, ka = _colptr(a); pb, kb = _colptr(b)
-    rc = lib().orc_vec_compare_real(op, pa, pb, C.c_double(b_const), res.ctypes.data, nulls.ctypes.data)
+    rc = lib().orc_vec_compare_real(op, pa, pb, C.c_double(b_const), C.c_void_p(res.ctypes.data), C.c_void_p(nulls.ctypes.data))
     assert rc == 0, _err()
     return res, np.unpackbits(nulls, bitorder="little")[:n] == 0
 
@@ -218,7 +218,7 @@ def vec_arith_int(op, a: Column, b: Optional[Column], b_const=0, a_unsigned=Fals
     res = np.zeros(n, dtype=np.int64); nulls = np.zeros((n + 7) // 8, dtype=np.uint8)
     pa, ka = _colptr(a); pb, kb = _colptr(b)
     rc = lib().orc_vec_arith_int(op, int(a_unsigned), int(b_unsigned), pa, pb, C.c_int64(b_const),
-                                 res.ctypes.data, nulls.ctypes.data)
+                                 C.c_void_p(res.ctypes.data), C.c_void_p(nulls.ctypes.data))
     return rc, res, np.unpackbits(nulls, bitorder="little")[:n] == 0
 
 
@@ -226,7 +226,7 @@ def vec_arith_real(op, a: Column, b: Optional[Column], b_const=0.0):
     n = a.length
     res = np.zeros(n, dtype=np.float64); nulls = np.zeros((n + 7) // 8, dtype=np.uint8)
     pa, ka = _colptr(a); pb, kb = _colptr(b)
-    rc = lib().orc_vec_arith_real(op, pa, pb, C.c_double(b_const), res.ctypes.data, nulls.ctypes.data)
+    rc = lib().orc_vec_arith_real(op, pa, pb, C.c_double(b_const), C.c_void_p(res.ctypes.data), C.c_void_p(nulls.ctypes.data))
     return rc, res, np.unpackbits(nulls, bitorder="little")[:n] == 0
 
 
@@ -236,6 +236,6 @@ def vec_filter(chk: Chunk, items: Sequence[FilterItem]):
     cnt = C.c_int64(0)
     cs = chk.to_struct()
     fa = filter_array(items)
-    rc = lib().orc_vec_filter(C.byref(cs), fa, C.c_int32(len(items)), sel.ctypes.data, C.byref(cnt))
+    rc = lib().orc_vec_filter(C.byref(cs), fa, C.c_int32(len(items)), C.c_void_p(sel.ctypes.data), C.byref(cnt))
     assert rc == 0, _err()
     return sel.astype(bool), cnt.value
