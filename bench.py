@@ -211,7 +211,7 @@ def run_gpu(args):
         torch.cuda.synchronize(dev)
 
     # ---- build side (untimed): repartition by key hash when N > 1, then build the local table ---------
-    xch_b = xch_p = None
+    xch_b = xch_p = xseg = None
     xstream = None
     xchunks = max(1, args.xchunks) if world > 1 else 1
     if world > 1:
@@ -219,11 +219,16 @@ def run_gpu(args):
         xstream = torch.cuda.Stream(device=dev)
         # receive capacity: expected rows + 2 % (uniform hash; a skewed key set would need a count-then-allocate round)
         with torch.cuda.stream(stream):
-            xch_b = KeyExchange(rank, world, local, stream, 2, int(nb * 1.02) + 4096, args.exchange)
+            xch_b = KeyExchange(rank, world, local, stream, 2, int(nb * 1.02) + 4096, "p2p" if args.exchange == "cf" else args.exchange)
         with torch.cuda.stream(xstream):
             # the probe side is exchanged in `xchunks` pieces through two alternating sets of receive buffers, so that the
             # NVLink scatter of piece c+1 overlaps the probe kernel of piece c
-            xch_p = [KeyExchange(rank, world, local, xstream, 2, int(npb / xchunks * 1.03) + 8192, args.exchange) for _ in range(2 if xchunks > 1 else 1)]
+            xch_p = [KeyExchange(rank, world, local, xstream, 2, int(npb / xchunks * 1.03) + 8192, "p2p" if args.exchange == "cf" else args.exchange)
+                     for _ in range(2 if xchunks > 1 else 1)]
+        if args.exchange == "cf":
+            from tidb_b200.parallel import SegmentExchange
+            with torch.cuda.stream(stream):
+                xseg = SegmentExchange(rank, world, local, stream, 2, npb)
         # leave room on every SM for the scatter CTAs next to the persistent probe CTAs
         if xchunks > 1:
             os.environ.setdefault("TG_PROBE_CTAS_PER_SM", "2")
@@ -261,6 +266,13 @@ def run_gpu(args):
         if world == 1:
             rows, cols, _ = join.probe([pk, pv], sync=sync)
             return (rows, check_piece(cols, rows)) if sync else (None, None)
+        if xseg is not None:
+            # count-free exchange: scatter into the peers' regions -> all-gather of the counts (the barrier) -> segmented
+            # probe; everything is enqueued on `stream`, the host never waits inside a step
+            with torch.cuda.stream(stream):
+                cols_in, seg_cnt, cap = xseg.exchange(pk, [pk, pv])
+                rows, cols, _ = join.probe_segments(cols_in, seg_cnt, cap, sync=sync)
+            return (rows, check_piece(cols, rows)) if sync else (None, None)
         total, chk = 0, torch.zeros(2, dtype=torch.int64, device=dev)
         for c, (lo, hi) in enumerate(bounds):
             x = xch_p[c % len(xch_p)]
@@ -292,7 +304,7 @@ def run_gpu(args):
     # ---- timed region: value (device resident) ----------------------------------------------------------------
     sampler = ClockSampler(local)
     l0 = join.stats().kernel_launches
-    lx0 = sum(x.launches for x in xch_p) if xch_p else 0
+    lx0 = (sum(x.launches for x in xch_p) if xch_p else 0) + (xseg.launches if xseg else 0)
     barrier()
     if rank == 0:
         sampler.start()
@@ -310,7 +322,9 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
-    launches_extra = (sum(x.launches for x in xch_p) if xch_p else 0)
+    launches_extra = (sum(x.launches for x in xch_p) if xch_p else 0) + (xseg.launches if xseg else 0)
+    if xseg is not None:
+        xseg.check_overflow()
     launches = (join.stats().kernel_launches - l0) + (launches_extra - lx0)
     value = npb * world / (ms_step * 1e-3)
 
@@ -357,7 +371,9 @@ def run_gpu(args):
             "config": {"workload": f"hash join {npb}x{nb} int64 keys per GPU, 8-byte payload, 100% match, output 4 columns (BASELINE configs[1])",
                        "l2": "inputs larger than L2 (1.6 GB probe columns + 3.2 GB output + %.0f MB table per step vs 126 MB L2)" % (bstats.table_slots * 16 / 1e6),
                        "table": {"slots": bstats.table_slots, "mode": bstats.table_mode, "distinct_keys": bstats.distinct_keys, "build_ms": bstats.build_ms},
-                       "exchange": "none" if world == 1 else ("k_partition_scatter storing into peer receive buffers over NVLink (tg_partition_exchange), counts all-gathered" if args.exchange == "p2p" else "tg_partition_by_key + NCCL all_to_all_single per column")},
+                       "exchange": "none" if world == 1 else {"cf": "count-free: k_partition_scatter_bulk appends to this rank's fixed-capacity region on every peer over NVLink (tg_partition_exchange_cf), one all-gather of the counts per step, segmented probe (tg_join_probe_dev_seg)",
+                                                                    "p2p": "k_partition_scatter storing into peer receive buffers over NVLink (tg_partition_exchange), counts all-gathered through the host",
+                                                                    "nccl": "tg_partition_by_key + NCCL all_to_all_single per column"}[args.exchange]},
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
         }
         if roof:
@@ -533,7 +549,7 @@ def main():
     ap.add_argument("--cpu-sample-rows", type=int, default=8_000_000)
     ap.add_argument("--ref-sample-rows", type=int, default=8_000_000)
     ap.add_argument("--e2e-chunk-rows", type=int, default=4 << 20)
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--exchange", default="cf", choices=["cf", "p2p", "nccl"], help="N>1 probe-side exchange: cf = count-free peer stores + segmented probe (no host round trip), p2p = counted peer stores, nccl = local scatter + all_to_all")
     ap.add_argument("--xchunks", type=int, default=1, help="N>1: pieces the probe side is exchanged in (overlap with the probe kernel)")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")

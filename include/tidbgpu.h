@@ -228,6 +228,14 @@ int tg_join_close(tg_join* j);
  * on this handle or close.  This is the kernel-only path bench.py times as `value`.           */
 int tg_join_probe_dev(tg_join* j, const tg_chunk* dev_chk, int64_t* out_rows,
                       void** out_cols, void** out_nulls);
+/* Same, for a device chunk that is SEGMENTED: `nseg` segments of `seg_cap` rows each (seg_cap a multiple of
+ * 1024), segment s holding seg_cnt_dev[s] valid rows at its start; dev_chk->cols[*].length = nseg*seg_cap.  This is
+ * the shape a count-free exchange delivers (tg_partition_exchange_cf: one fixed-capacity region per sending GPU,
+ * fill counts known only on the device), so the receiver probes without compacting and without a host round trip.
+ * Only for plans the fused fast path covers (tg_join_get_stats().table_mode == 1); others: TG_ERR_UNSUPPORTED.  */
+int tg_join_probe_dev_seg(tg_join* j, const tg_chunk* dev_chk, const int64_t* seg_cnt_dev, int32_t nseg,
+                          int64_t seg_cap, int64_t* out_rows, void** out_cols, void** out_nulls);
+
 
 /* hashJoinRuntimeStatsV2 (pkg/executor/join/hash_join_stats.go:142)                          */
 typedef struct tg_join_stats {
@@ -352,6 +360,17 @@ int tg_partition_exchange(int device, const int64_t* key_dev, int64_t rows, int3
                           int32_t ncols, const void* const* src_cols_dev,
                           void* const* recv_cols_peer, const int64_t* part_counts_dev,
                           const int64_t* recv_base_dev, void* stream);
+/* Count-free variant (no histogram pass, no host round trip): every destination p owns, inside each receiver's
+ * buffers, the fixed-capacity region [region_base, region_base + region_cap) reserved for THIS sender; rows are
+ * appended there in arrival order and sent_rows_dev[p] (device, zeroed by the call) ends up holding how many rows went
+ * to p.  A destination that would overflow raises *overflow_dev (device u64, zeroed by the call) and drops the excess —
+ * the caller re-runs that step through tg_partition_count + tg_partition_exchange.  Returns after ENQUEUEING on `stream`.
+ * The MPP analogue is still ExchangeSender/HashPartition (physical_exchange_sender.go:115); the reference sizes
+ * its per-partition chunks dynamically on the host (shuffle.go:450), which a single GPU kernel cannot.            */
+int tg_partition_exchange_cf(int device, const int64_t* key_dev, int64_t rows, int32_t nparts, int32_t ncols,
+                             const void* const* src_cols_dev, void* const* recv_cols_peer, int64_t region_base,
+                             int64_t region_cap, int64_t* sent_rows_dev, uint64_t* overflow_dev, void* stream);
+
 /* count rows per destination (first half of the exchange: counts are all-gathered by the host) */
 int tg_partition_count(int device, const int64_t* key_dev, int64_t rows, int32_t nparts,
                        int64_t* part_counts_dev, void* stream);

@@ -309,3 +309,49 @@ def test_concurrent_push_and_next_wait_and_rewind():
         assert np.array_equal(np.sort(got[1]), np.arange(3_000_000)) and np.array_equal(got[3], got[0] * 7)
         abi.check(lib.tg_join_probe_rewind(h))
     lib.tg_join_close(h)
+
+
+def test_probe_device_segments_matches_dense_probe(monkeypatch):
+    # the shape a count-free exchange delivers: `nseg` fixed-capacity regions, each valid for its first seg_cnt[s] rows.
+    # The segmented device probe must return exactly what the dense device probe returns for the concatenated valid rows,
+    # with and without the L2 partition pass.
+    import torch
+    from tidb_b200.device import DeviceJoin
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(5)
+    nb, cap, nseg = 120_000, 300 * 1024, 5
+    fill = [cap, 0, 123_457, cap - 1, 77]
+    bk = rng.permutation(nb).astype(np.int64) * 2654435761 + 3
+    pk_all, pv_all = [], []
+    kcol = np.full(nseg * cap, -7, dtype=np.int64); vcol = np.full(nseg * cap, -9, dtype=np.int64)    # padding never matches
+    for s_, f in enumerate(fill):
+        k = np.where(rng.random(f) < 0.9, bk[rng.integers(0, nb, f)], rng.integers(1 << 50, 1 << 51, f))
+        v = np.arange(f, dtype=np.int64) + s_ * 10_000_000
+        kcol[s_ * cap:s_ * cap + f] = k; vcol[s_ * cap:s_ * cap + f] = v
+        pk_all.append(k); pv_all.append(v)
+    pk, pv = np.concatenate(pk_all), np.concatenate(pv_all)
+    t = lambda a: torch.from_numpy(a).to(dev)
+    for env in (dict(TG_PROBE_PARTITION="0"), dict(TG_PROBE_PARTITION="1", TG_PROBE_PARTS="6", TG_PROBE_PART_MIN_MB="0", TG_PROBE_PART_MIN_ROWS="0")):
+        for k_, v_ in env.items():
+            monkeypatch.setenv(k_, v_)
+        plan = JoinPlan(abi.JOIN_INNER, [INT_NN, INT_NN], [INT_NN, INT_NN], [0], [0], device=0)
+        j = DeviceJoin(plan)
+        j.build([t(bk), t(np.arange(nb, dtype=np.int64) * 5)])
+        rows_d, cols_d, _ = j.probe([t(pk), t(pv)])
+        dense = [_dev_to_np(p, rows_d) for p in cols_d]
+        rows_s, cols_s, _ = j.probe_segments([t(kcol), t(vcol)], t(np.array(fill, dtype=np.int64)), cap)
+        seg = [_dev_to_np(p, rows_s) for p in cols_s]
+        j.close()
+        assert rows_s == rows_d == int(np.isin(pk, bk).sum())
+        od, os_ = np.argsort(dense[1]), np.argsort(seg[1])
+        for a, b in zip(dense, seg):
+            assert np.array_equal(a[od], b[os_])
+
+
+def _dev_to_np(ptr, n):
+    import torch
+    class _A:
+        pass
+    a = _A()
+    a.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+    return torch.as_tensor(a, device=torch.device("cuda", 0)).cpu().numpy()

@@ -106,12 +106,12 @@ EXPORTED_SYMBOLS = [
     "tg_device_synchronize",
     "tg_join_supported", "tg_join_open", "tg_join_build_push", "tg_join_build_push_dev",
     "tg_join_build_finish", "tg_join_probe_push", "tg_join_probe_finish", "tg_join_next", "tg_join_next_wait", "tg_join_probe_rewind",
-    "tg_join_close", "tg_join_probe_dev", "tg_join_get_stats",
+    "tg_join_close", "tg_join_probe_dev", "tg_join_probe_dev_seg", "tg_join_get_stats",
     "tg_agg_supported", "tg_agg_open", "tg_agg_push", "tg_agg_push_dev", "tg_agg_finish",
     "tg_agg_next", "tg_agg_close", "tg_agg_result_dev", "tg_agg_get_stats",
     "tg_vec_compare_int", "tg_vec_compare_real", "tg_vec_arith_int", "tg_vec_arith_real",
     "tg_vec_filter",
-    "tg_partition_by_key", "tg_partition_of_key", "tg_partition_exchange", "tg_partition_count",
+    "tg_partition_by_key", "tg_partition_of_key", "tg_partition_exchange", "tg_partition_exchange_cf", "tg_partition_count",
     "tg_ipc_export", "tg_ipc_open", "tg_ipc_close",
 ]
 

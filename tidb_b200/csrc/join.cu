@@ -706,12 +706,13 @@ static int launch_probe_tma(tg_join* j, const int64_t* pkey, int64_t ntiles, con
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // probe `n` device-resident rows; results are appended to rb (rb.rows advanced)
-static int probe_device(tg_join* j, const DevCols& pview, int64_t n, ResultBatch& rb, bool sync_count) {
+static int probe_device(tg_join* j, const DevCols& pview, int64_t n, ResultBatch& rb, bool sync_count, const SegSpec* in_seg = nullptr) {
   const Side& p = j->probe;
   j->stats.probe_rows += n;
   KeySpec ks = j->probe_key;
   ks.data = pview.data[p.key_col]; ks.nulls = pview.nulls[p.key_col];
   TG_TRY(j->out_cursor.ensure(j->device, 64));
+  if (in_seg && !fast_path_ok(j, pview)) return fail(TG_ERR_UNSUPPORTED, "segmented device chunks are only accepted by the fused fast path (unique build keys, <= 1 payload, no filters)");
   if (fast_path_ok(j, pview)) {
     TG_TRY(ensure_result(j, rb, rb.rows + n, rb.rows > 0, rb.rows));
     OutCols oc{};
@@ -722,7 +723,8 @@ static int probe_device(tg_join* j, const DevCols& pview, int64_t n, ResultBatch
     if (n > 0) {
       const ProbeTuning& tune = probe_tuning();
       FastOut fo{};
-      bool warp_ok = tune.variant != 0 && build_fast_out(j, oc, pview, fo);
+      bool warp_ok = (tune.variant != 0 || in_seg) && build_fast_out(j, oc, pview, fo);
+      if (in_seg && !warp_ok) return fail(TG_ERR_UNSUPPORTED, "segmented device chunks: output shape not covered by the warp kernels");
       if (warp_ok) {
         const int64_t* pkey = reinterpret_cast<const int64_t*>(ks.data);
         size_t table_bytes = (size_t)j->tv.nslots * sizeof(Slot);
@@ -757,13 +759,15 @@ static int probe_device(tg_join* j, const DevCols& pview, int64_t n, ResultBatch
             for (int c = 0; c < fo.n_pcols; c++) d.src[1 + c] = fo.psrc[c];
             for (int c = 0; c < nc; c++) for (int q = 0; q < P; q++) d.dst[q][c] = j->part_cols[c]->p;
             d.dst_base = bases; d.capacity = C; d.overflow = flag;
+            if (in_seg) { d.in_cnt = in_seg->cnt; d.in_cap = in_seg->cap; d.in_tiles_per_seg = (uint32_t)(in_seg->cap / PTILE); }
             TG_TRY(launch_partition_scatter<true>(j->device, j->stream, reinterpret_cast<const long long*>(pkey), nullptr, n_main, d, cursors,
                                                   &j->stats.kernel_launches));
             FastOut pf = fo;
             for (int c = 0; c < fo.n_pcols; c++) pf.psrc[c] = j->part_cols[1 + c]->as<unsigned long long>();
             if (tune.seg_vec) TG_TRY(launch_probe_seg(j, j->part_cols[0]->as<int64_t>(), (int64_t)P * C, pf, cur, tune, SegSpec{cursors, (uint32_t)(C / 128), 0, C, flag}));
             else TG_TRY(launch_probe_warp(j, j->part_cols[0]->as<int64_t>(), (int64_t)P * C, pf, cur, tune, SegSpec{cursors, (uint32_t)(C / 128), 0, C, flag}));
-            TG_TRY(launch_probe_warp(j, pkey, n_main, fo, cur, tune, SegSpec{nullptr, 0, 1, 0, flag}));   // runs only after an overflow
+            TG_TRY(launch_probe_warp(j, pkey, n_main, fo, cur, tune,
+                                     in_seg ? SegSpec{in_seg->cnt, in_seg->tiles_per_seg, 1, in_seg->cap, flag} : SegSpec{nullptr, 0, 1, 0, flag}));   // runs only after an overflow
             j->stats.kernel_launches += 3;
             if (n_main < n) {
               FastOut tail = fo;
@@ -804,7 +808,7 @@ static int probe_device(tg_join* j, const DevCols& pview, int64_t n, ResultBatch
             for (int c = 0; c < fo.n_pcols; c++) fo.psrc[c] = j->part_cols[1 + c]->as<unsigned long long>();
           }
         }
-        bool tma_ok = tune.tma && aligned16(pkey);
+        bool tma_ok = tune.tma && !in_seg && aligned16(pkey);
         for (int c = 0; c < fo.n_pcols; c++) tma_ok = tma_ok && aligned16(fo.psrc[c]);
         int64_t full_tiles = tma_ok ? n / TG_PROBE_TILE : 0;
         if (full_tiles > 0) TG_TRY(launch_probe_tma(j, pkey, full_tiles, fo, cur, tune));
@@ -812,7 +816,8 @@ static int probe_device(tg_join* j, const DevCols& pview, int64_t n, ResultBatch
         if (done < n) {
           FastOut tail = fo;
           for (int c = 0; c < fo.n_pcols; c++) tail.psrc[c] = fo.psrc[c] + done;
-          TG_TRY(launch_probe_warp(j, pkey + done, n - done, tail, cur, tune));
+          if (in_seg) TG_TRY(launch_probe_warp(j, pkey, n, fo, cur, tune, SegSpec{in_seg->cnt, in_seg->tiles_per_seg, 0, in_seg->cap, nullptr}));
+          else TG_TRY(launch_probe_warp(j, pkey + done, n - done, tail, cur, tune));
           if (full_tiles > 0) j->stats.kernel_launches++;
         }
       } else {
@@ -1184,6 +1189,34 @@ int tg_join_probe_dev(tg_join* j, const tg_chunk* dev_chk, int64_t* out_rows, vo
   rb.rows = 0; rb.consumed = 0;
   TG_CUDA(cudaEventRecord(j->ev0, j->stream));
   TG_TRY(probe_device(j, pview, n, rb, out_rows != nullptr));
+  TG_CUDA(cudaEventRecord(j->ev1, j->stream));
+  if (out_rows) {
+    TG_CUDA(cudaStreamSynchronize(j->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, j->ev0, j->ev1); j->stats.probe_ms += ms;
+    *out_rows = rb.rows;
+  }
+  for (int c = 0; c < j->n_out; c++) {
+    if (out_cols) out_cols[c] = rb.cols[c]->p;
+    if (out_nulls) out_nulls[c] = rb.bitmaps[c]->p;
+  }
+  return TG_OK;
+}
+
+int tg_join_probe_dev_seg(tg_join* j, const tg_chunk* dev_chk, const int64_t* seg_cnt_dev, int32_t nseg, int64_t seg_cap,
+                          int64_t* out_rows, void** out_cols, void** out_nulls) {
+  TG_LOCK(j);
+  if (!j->built) return fail(TG_ERR_STATE, "probe before build_finish");
+  if (!seg_cnt_dev || nseg < 1 || seg_cap < 1024 || seg_cap % 1024) return fail(TG_ERR_INVALID, "seg_cnt_dev required; seg_cap must be a positive multiple of 1024");
+  DevCols pview; int64_t n = 0;
+  TG_TRY(devchunk_view(dev_chk, j->probe, pview, &n));
+  if (n != (int64_t)nseg * seg_cap) return fail(TG_ERR_INVALID, "column length must be nseg * seg_cap");
+  if (n / 128 >= (1ll << 31)) return fail(TG_ERR_UNSUPPORTED, "segmented chunk too large");
+  if (!j->dev_result) j->dev_result.reset(new ResultBatch());
+  ResultBatch& rb = *j->dev_result;
+  rb.rows = 0; rb.consumed = 0;
+  SegSpec seg{reinterpret_cast<const unsigned long long*>(seg_cnt_dev), (uint32_t)(seg_cap / 128), 0, seg_cap, nullptr};
+  TG_CUDA(cudaEventRecord(j->ev0, j->stream));
+  TG_TRY(probe_device(j, pview, n, rb, out_rows != nullptr, &seg));
   TG_CUDA(cudaEventRecord(j->ev1, j->stream));
   if (out_rows) {
     TG_CUDA(cudaStreamSynchronize(j->stream));

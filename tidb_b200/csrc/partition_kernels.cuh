@@ -25,6 +25,11 @@ struct PartDst {
   // rows beyond it are dropped and *overflow is set — the caller then falls back to an unpartitioned pass.
   long long capacity;
   unsigned long long* overflow;
+  // segmented INPUT (k_partition_scatter_bulk only): segment s = rows [s*in_cap, s*in_cap + min(in_cnt[s], in_cap)),
+  // in_cap a multiple of the scatter tile; nullptr = dense input
+  const unsigned long long* in_cnt;
+  long long in_cap;
+  uint32_t in_tiles_per_seg, pad;
 };
 
 // HIGH = false: destination GPU, low 32 hash bits (disjoint from the slot bits).
@@ -86,7 +91,7 @@ __global__ void __launch_bounds__(PT_BLOCK)
 k_partition_scatter(const long long* __restrict__ key, const uint8_t* __restrict__ nulls, int64_t n, PartDst d,
                     unsigned long long* __restrict__ cursors) {
   __shared__ unsigned long long s_val[PT_TILE];
-  __shared__ uint32_t s_cnt[TG_MAX_PARTS], s_off[TG_MAX_PARTS + 1];
+  __shared__ uint32_t s_cnt[TG_MAX_PARTS], s_off[TG_MAX_PARTS + 1], s_room[TG_MAX_PARTS];
   __shared__ unsigned long long s_gbase[TG_MAX_PARTS];
   const int lane = threadIdx.x & 31;
   const uint32_t P = (uint32_t)d.nparts;
@@ -122,7 +127,12 @@ k_partition_scatter(const long long* __restrict__ key, const uint8_t* __restrict
     }
     if (threadIdx.x < P) {
       uint32_t c = s_cnt[threadIdx.x];
-      s_gbase[threadIdx.x] = (c ? atomicAdd(&cursors[threadIdx.x], (unsigned long long)c) : 0ull) + (unsigned long long)d.dst_base[threadIdx.x];
+      unsigned long long old = c ? atomicAdd(&cursors[threadIdx.x], (unsigned long long)c) : 0ull;
+      s_gbase[threadIdx.x] = old + (unsigned long long)d.dst_base[threadIdx.x];
+      // rows of this tile that still fit the destination's capacity (0 = unbounded)
+      unsigned long long room = d.capacity > 0 ? (old < (unsigned long long)d.capacity ? (unsigned long long)d.capacity - old : 0ull) : ~0ull;
+      s_room[threadIdx.x] = room > c ? c : (uint32_t)room;
+      if (d.capacity > 0 && room < c) *d.overflow = 1ull;
     }
     __syncthreads();
     const uint32_t tile_rows = s_off[P];
@@ -139,7 +149,7 @@ k_partition_scatter(const long long* __restrict__ key, const uint8_t* __restrict
         uint32_t p = 0;
         while (sidx >= s_off[p + 1]) p++;   // ≤ nparts steps
         unsigned long long* dst = reinterpret_cast<unsigned long long*>(d.dst[p][c]);
-        dst[s_gbase[p] + (sidx - s_off[p])] = s_val[sidx];
+        if (sidx - s_off[p] < s_room[p]) dst[s_gbase[p] + (sidx - s_off[p])] = s_val[sidx];
       }
       __syncthreads();
     }
@@ -290,12 +300,21 @@ k_partition_scatter_bulk(int64_t ntiles, PartDst d, unsigned long long* __restri
     mbar_wait(&full[s], (uint32_t)((it / STAGES) & 1));
     __syncthreads();
     const unsigned long long* in = ring + (size_t)s * NC * TILE;
-    uint32_t pr[ITEMS];   // destination << 16 | rank inside (tile, destination)
+    int valid = TILE;     // rows of this tile that exist (segmented input: the tail of a segment is padding)
+    if (d.in_cnt) {
+      const uint32_t sg = (uint32_t)tile / d.in_tiles_per_seg;
+      const unsigned long long c = d.in_cnt[sg];
+      const long long left = (long long)sg * d.in_cap + (long long)(c < (unsigned long long)d.in_cap ? c : (unsigned long long)d.in_cap) - tile * TILE;
+      valid = left <= 0 ? 0 : (left < TILE ? (int)left : TILE);
+    }
+    uint32_t pr[ITEMS];   // destination << 16 | rank inside (tile, destination); 0xffff.... = padding row
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
-      uint64_t h = hash64(in[j * PT_BLOCK + tid]);
-      uint32_t p = HIGH ? mulhi32((uint32_t)(h >> 32), P) : part_of(h, P);
-      pr[j] = (p << 16) | atomicAdd(&s_cnt[p], 1u);
+      if (j * PT_BLOCK + tid < valid) {
+        uint64_t h = hash64(in[j * PT_BLOCK + tid]);
+        uint32_t p = HIGH ? mulhi32((uint32_t)(h >> 32), P) : part_of(h, P);
+        pr[j] = (p << 16) | atomicAdd(&s_cnt[p], 1u);
+      } else pr[j] = 0xffffffffu;
     }
     __syncthreads();
     if (tid < 32) {
@@ -319,7 +338,7 @@ k_partition_scatter_bulk(int64_t ntiles, PartDst d, unsigned long long* __restri
     for (int c = 0; c < NC; c++) {
 #pragma unroll
       for (int j = 0; j < ITEMS; j++)
-        stage[(size_t)c * SROWS + s_off[pr[j] >> 16] + (pr[j] & 0xffffu)] = in[(size_t)c * TILE + j * PT_BLOCK + tid];
+        if (pr[j] != 0xffffffffu) stage[(size_t)c * SROWS + s_off[pr[j] >> 16] + (pr[j] & 0xffffu)] = in[(size_t)c * TILE + j * PT_BLOCK + tid];
     }
     fence_async_smem();              // generic-proxy STS → visible to the async proxy that executes the bulk stores
     __syncthreads();                 // staging complete, ring stage s fully consumed (LDS results fed the STS above)

@@ -59,6 +59,17 @@ class DeviceJoin:
         abi.check(self.lib.tg_join_probe_dev(self.h, C.byref(ck), C.byref(rows) if sync else None, out_cols, out_nulls))
         return (rows.value if sync else None), [p or 0 for p in out_cols], [p or 0 for p in out_nulls]
 
+    def probe_segments(self, cols: Sequence[torch.Tensor], seg_cnt: torch.Tensor, seg_cap: int, sync: bool = True):
+        """cols hold len(seg_cnt) segments of seg_cap rows each, segment s valid for its first seg_cnt[s] rows (the shape a
+        count-free exchange delivers, parallel.py:SegmentExchange).  Same return value as probe()."""
+        ck = dev_chunk(cols, None)
+        out_cols = (C.c_void_p * self.n_out)()
+        out_nulls = (C.c_void_p * self.n_out)()
+        rows = C.c_int64(0)
+        abi.check(self.lib.tg_join_probe_dev_seg(self.h, C.byref(ck), C.c_void_p(seg_cnt.data_ptr()), C.c_int32(seg_cnt.numel()), C.c_int64(seg_cap),
+                                                 C.byref(rows) if sync else None, out_cols, out_nulls))
+        return (rows.value if sync else None), [p or 0 for p in out_cols], [p or 0 for p in out_nulls]
+
     def stats(self) -> abi.TgJoinStats:
         s = abi.TgJoinStats()
         abi.check(self.lib.tg_join_get_stats(self.h, C.byref(s)))

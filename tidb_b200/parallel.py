@@ -180,3 +180,108 @@ class KeyExchange:
             for ptr in self.recv_ptrs:
                 self.lib.tg_dev_free(self.device, C.c_void_p(ptr))
             self.recv_ptrs = []
+
+
+class SegmentExchange:
+    """Count-free key-hash exchange (tg_partition_exchange_cf): no histogram pass and NO host round trip per step.
+
+    Every rank owns, inside each peer's receive buffers, one fixed-capacity region (region s of rank d's buffer belongs to
+    sender s).  One kernel regroups 1024-row tiles by destination in shared memory and appends each destination's run to
+    this rank's region on that peer with bulk stores over NVLink; the per-destination row counts stay on the device and
+    are exchanged with ONE all-gather, which is also the barrier that makes the peer stores visible.  The receiver probes
+    the `world` regions as segments (DeviceJoin.probe_segments), so nothing is compacted or counted on the host.
+    Two alternating sets of receive buffers: a rank may start sending step k+1 while a peer still probes step k.
+    The reference's analogue is the MPP HashPartition exchange (physical_exchange_sender.go:115)."""
+
+    def __init__(self, rank: int, world: int, device: int, stream, ncols: int, rows_per_step: int, slack: float = 1.06):
+        import torch
+        import torch.distributed as dist
+        from . import abi
+        self.torch, self.dist, self.abi = torch, dist, abi
+        self.lib = abi.load_lib()
+        self.rank, self.world, self.device, self.stream, self.ncols = rank, world, device, stream, ncols
+        self.dev = torch.device("cuda", device)
+        self.cap = ((int(rows_per_step / world * slack) + 8192 + 1023) // 1024) * 1024   # rows per (sender, receiver) region
+        self.sets = 2
+        self.step = 0
+        self.launches = 0
+        self.sent = [torch.zeros(16, dtype=torch.int64, device=self.dev) for _ in range(self.sets)]
+        self.overflow = [torch.zeros(1, dtype=torch.int64, device=self.dev) for _ in range(self.sets)]
+        self.count_mat = [torch.zeros(world * world, dtype=torch.int64, device=self.dev) for _ in range(self.sets)]
+        self.seg_cnt = [torch.zeros(world, dtype=torch.int64, device=self.dev) for _ in range(self.sets)]
+        lib = self.lib
+        self.recv_ptrs = []      # [set][col]
+        handles = []
+        for _ in range(self.sets):
+            row = []
+            for _c in range(ncols):
+                p = C.c_void_p()
+                abi.check(lib.tg_dev_alloc(device, C.c_size_t(world * self.cap * 8 + 64), C.byref(p)))
+                row.append(p.value)
+                h = (C.c_uint8 * 64)()
+                abi.check(lib.tg_ipc_export(device, p, h))
+                handles.append(bytes(h))
+            self.recv_ptrs.append(row)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, handles)
+        self.peer_ptrs = []      # [set][peer][col]
+        self.peer_arr = []
+        for s in range(self.sets):
+            per_set = []
+            for p in range(world):
+                row = []
+                for c in range(ncols):
+                    if p == rank:
+                        row.append(self.recv_ptrs[s][c])
+                    else:
+                        mp = C.c_void_p()
+                        hb = (C.c_uint8 * 64).from_buffer_copy(gathered[p][s * ncols + c])
+                        abi.check(lib.tg_ipc_open(device, hb, C.byref(mp)))
+                        row.append(mp.value)
+                per_set.append(row)
+            self.peer_ptrs.append(per_set)
+            flat = [per_set[p][c] for p in range(world) for c in range(ncols)]
+            self.peer_arr.append((C.c_void_p * len(flat))(*flat))
+
+    def _view(self, ptr: int, n: int):
+        class _A:
+            pass
+        a = _A()
+        a.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+        return self.torch.as_tensor(a, device=self.dev)
+
+    def exchange(self, key, cols):
+        """cols[0] must be `key`.  Everything is enqueued on self.stream (the caller's current stream must be self.stream).
+        -> (received columns: world*cap rows each, seg_cnt tensor [world], cap)"""
+        torch, dist, lib, abi = self.torch, self.dist, self.lib, self.abi
+        s = self.step % self.sets
+        self.step += 1
+        st = C.c_void_p(self.stream.cuda_stream)
+        src_p = (C.c_void_p * len(cols))(*[c.data_ptr() for c in cols])
+        abi.check(lib.tg_partition_exchange_cf(self.device, C.c_void_p(key.data_ptr()), C.c_int64(key.numel()), self.world, len(cols), src_p,
+                                               self.peer_arr[s], C.c_int64(self.rank * self.cap), C.c_int64(self.cap),
+                                               C.c_void_p(self.sent[s].data_ptr()), C.c_void_p(self.overflow[s].data_ptr()), st))
+        self.launches += 2
+        # counts[src, dst] on every rank; completes only after every peer's scatter kernel (stream order) — the barrier
+        dist.all_gather_into_tensor(self.count_mat[s], self.sent[s][:self.world])
+        self.seg_cnt[s].copy_(self.count_mat[s].view(self.world, self.world)[:, self.rank])
+        return [self._view(self.recv_ptrs[s][c], self.world * self.cap) for c in range(len(cols))], self.seg_cnt[s], self.cap
+
+    def check_overflow(self):
+        """host check (synchronises): raises when some step dropped rows because a region was too small"""
+        bad = sum(int(o.item()) for o in self.overflow)
+        flag = self.torch.tensor([bad], device=self.dev)
+        self.dist.all_reduce(flag)
+        if int(flag.item()):
+            raise RuntimeError("count-free exchange overflowed a receive region: raise `slack` or use KeyExchange (counted)")
+
+    def close(self):
+        for s in range(self.sets):
+            for p in range(self.world):
+                if p == self.rank:
+                    continue
+                for c in range(self.ncols):
+                    self.lib.tg_ipc_close(self.device, C.c_void_p(self.peer_ptrs[s][p][c]))
+            for ptr in self.recv_ptrs[s]:
+                self.lib.tg_dev_free(self.device, C.c_void_p(ptr))
+        self.recv_ptrs = []
