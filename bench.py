@@ -227,8 +227,9 @@ def run_gpu(args):
                      for _ in range(2 if xchunks > 1 else 1)]
         if args.exchange == "cf":
             from tidb_b200.parallel import SegmentExchange
-            with torch.cuda.stream(stream):
-                xseg = SegmentExchange(rank, world, local, stream, 2, npb)
+            xs = xstream if args.overlap else stream
+            with torch.cuda.stream(xs):
+                xseg = SegmentExchange(rank, world, local, xs, 2, npb, dma=bool(args.dma))
         # leave room on every SM for the scatter CTAs next to the persistent probe CTAs
         if xchunks > 1:
             os.environ.setdefault("TG_PROBE_CTAS_PER_SM", "2")
@@ -261,6 +262,8 @@ def run_gpu(args):
         assert bool((o_bv * ODD == o_bk * 7).all()), "build payload does not belong to the matched key"   # bv = 7*id, bk = id*ODD
         return torch.stack([o_pv.sum(), (o_pv * o_pv).sum()])
 
+    TRACE = [] if os.environ.get("BENCH_TRACE") else None
+
     def step(sync: bool):
         """sync=True is the verifying pass: returns (rows, checksums)"""
         if world == 1:
@@ -269,10 +272,25 @@ def run_gpu(args):
         if xseg is not None:
             # count-free exchange: scatter into the peers' regions -> all-gather of the counts (the barrier) -> segmented
             # probe; everything is enqueued on `stream`, the host never waits inside a step
+            # Two streams when --overlap: the NVLink-bound scatter of this step runs under the probe of the previous step;
+            # only the all-gather (which releases the peers into the step that reuses the buffer set still being probed)
+            # waits for that probe.  Without --overlap both streams are the same one and the waits are no-ops.
+            xs = xseg.stream
+            prev = done_ev[0]
+            with torch.cuda.stream(xs):
+                if prev is not None and (sync or not args.overlap):
+                    xs.wait_event(prev)
+                cols_in, seg_cnt, cap = xseg.exchange(pk, [pk, pv], before_gather=(lambda: xs.wait_event(prev)) if prev is not None else None, trace=TRACE)
+                got = torch.cuda.Event(); got.record(xs)
             with torch.cuda.stream(stream):
-                cols_in, seg_cnt, cap = xseg.exchange(pk, [pk, pv])
+                stream.wait_event(got)
+                if TRACE is not None:
+                    e = torch.cuda.Event(enable_timing=True); e.record(stream); TRACE.append(("probe start", e))
                 rows, cols, _ = join.probe_segments(cols_in, seg_cnt, cap, sync=sync)
-            return (rows, check_piece(cols, rows)) if sync else (None, None)
+                ev = torch.cuda.Event(enable_timing=TRACE is not None); ev.record(stream); done_ev[0] = ev
+                if TRACE is not None:
+                    TRACE.append(("probe end", ev))
+                return (rows, check_piece(cols, rows)) if sync else (None, None)
         total, chk = 0, torch.zeros(2, dtype=torch.int64, device=dev)
         for c, (lo, hi) in enumerate(bounds):
             x = xch_p[c % len(xch_p)]
@@ -311,11 +329,17 @@ def run_gpu(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         ev0.record(stream)
+        if xstream is not None:
+            xstream.wait_event(ev0)
         for _ in range(args.steps):
             step(False)
         ev1.record(stream)
     stream.synchronize()
     barrier()
+    if TRACE and rank == 0:
+        t0 = ev0
+        for name, e in TRACE[-7 * min(args.steps, 4):]:
+            print(f"[trace] {t0.elapsed_time(e):9.3f} ms  {name}", file=sys.stderr)
     clocks = sampler.stop() if rank == 0 else None
     ms_total = ev0.elapsed_time(ev1)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -550,6 +574,8 @@ def main():
     ap.add_argument("--ref-sample-rows", type=int, default=8_000_000)
     ap.add_argument("--e2e-chunk-rows", type=int, default=4 << 20)
     ap.add_argument("--exchange", default="cf", choices=["cf", "p2p", "nccl"], help="N>1 probe-side exchange: cf = count-free peer stores + segmented probe (no host round trip), p2p = counted peer stores, nccl = local scatter + all_to_all")
+    ap.add_argument("--overlap", type=int, default=1, help="N>1, --exchange cf: run the exchange of step k+1 on a second stream under the probe of step k")
+    ap.add_argument("--dma", type=int, default=1, help="N>1, --exchange cf: regroup locally, let copy engines move the regions over NVLink")
     ap.add_argument("--xchunks", type=int, default=1, help="N>1: pieces the probe side is exchanged in (overlap with the probe kernel)")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")

@@ -138,6 +138,9 @@ int tg_dev_alloc(int device, size_t bytes, void** out);
 int tg_dev_free(int device, void* p);
 int tg_memcpy_h2d(int device, void* dst_dev, const void* src_host, size_t bytes);
 int tg_memcpy_d2h(int device, void* dst_host, const void* src_dev, size_t bytes);
+/* Asynchronous device-to-device copy on `stream` (cudaMemcpyAsync, copy engine): `dst` may be memory of a peer GPU mapped
+ * with tg_ipc_open — the DMA then crosses NVLink without occupying SMs (SegmentExchange's transfer step).          */
+int tg_memcpy_d2d_async(int device, void* dst_dev, const void* src_dev, size_t bytes, void* stream);
 int tg_device_synchronize(int device);
 
 /* ---------------------------------------------------------------------------------------------

@@ -102,7 +102,7 @@ class TgAggStats(C.Structure):
 # every symbol include/tidbgpu.h declares; tests/test_abi_exports.py checks the .so exports them all
 EXPORTED_SYMBOLS = [
     "tg_last_error", "tg_abi_version", "tg_device_count", "tg_device_info", "tg_fixed_len",
-    "tg_host_alloc", "tg_host_free", "tg_dev_alloc", "tg_dev_free", "tg_memcpy_h2d", "tg_memcpy_d2h",
+    "tg_host_alloc", "tg_host_free", "tg_dev_alloc", "tg_dev_free", "tg_memcpy_h2d", "tg_memcpy_d2h", "tg_memcpy_d2d_async",
     "tg_device_synchronize",
     "tg_join_supported", "tg_join_open", "tg_join_build_push", "tg_join_build_push_dev",
     "tg_join_build_finish", "tg_join_probe_push", "tg_join_probe_finish", "tg_join_next", "tg_join_next_wait", "tg_join_probe_rewind",

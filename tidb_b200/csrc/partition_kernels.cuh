@@ -453,6 +453,11 @@ inline int launch_scatter_nc(int device, cudaStream_t st, int64_t n, PartDst& d,
       size_t smem = (size_t)2 * NC * TILE * 8 + (size_t)NC * (TILE + 2 * TG_MAX_PARTS) * 8 + 2 * 8 + 16;
       TG_CUDA(cudaFuncSetAttribute(k_partition_scatter_bulk<HIGH, NC, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(220 * 1024) / (smem + 1024)));
+      // a scatter that runs NEXT TO a probe kernel (exchange of step k+1 under the probe of step k) should leave the SMs'
+      // L1 to the probe: TG_SCATTER_CTAS_PER_SM caps the CTAs (and with them the shared-memory carve-out) per SM
+      static int cap_env = -1;
+      if (cap_env < 0) { const char* e = getenv("TG_SCATTER_CTAS_PER_SM"); cap_env = e ? atoi(e) : 0; }
+      if (!HIGH && cap_env > 0 && per_sm > cap_env) per_sm = cap_env;
       int grid = (int)std::min<int64_t>(ntiles, (int64_t)nsm * per_sm);
       k_partition_scatter_bulk<HIGH, NC, ITEMS><<<grid, PT_BLOCK, smem, st>>>(ntiles, d, cursors);
       if (launches) (*launches)++;

@@ -130,6 +130,12 @@ int tg_memcpy_d2h(int device, void* dst, const void* src, size_t bytes) {
   TG_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
   return TG_OK;
 }
+int tg_memcpy_d2d_async(int device, void* dst, const void* src, size_t bytes, void* stream) {
+  DeviceGuard g(device);
+  if (!g.ok) return fail(TG_ERR_CUDA, "cudaSetDevice failed (no usable CUDA device)");
+  TG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+  return TG_OK;
+}
 int tg_device_synchronize(int device) {
   DeviceGuard g(device);
   if (!g.ok) return fail(TG_ERR_CUDA, "cudaSetDevice failed (no usable CUDA device)");

@@ -193,7 +193,7 @@ class SegmentExchange:
     Two alternating sets of receive buffers: a rank may start sending step k+1 while a peer still probes step k.
     The reference's analogue is the MPP HashPartition exchange (physical_exchange_sender.go:115)."""
 
-    def __init__(self, rank: int, world: int, device: int, stream, ncols: int, rows_per_step: int, slack: float = 1.06):
+    def __init__(self, rank: int, world: int, device: int, stream, ncols: int, rows_per_step: int, slack: float = 1.06, dma: bool = False):
         import torch
         import torch.distributed as dist
         from . import abi
@@ -201,6 +201,7 @@ class SegmentExchange:
         self.lib = abi.load_lib()
         self.rank, self.world, self.device, self.stream, self.ncols = rank, world, device, stream, ncols
         self.dev = torch.device("cuda", device)
+        self.dma = bool(dma) and world > 1
         self.cap = ((int(rows_per_step / world * slack) + 8192 + 1023) // 1024) * 1024   # rows per (sender, receiver) region
         self.sets = 2
         self.step = 0
@@ -242,6 +243,26 @@ class SegmentExchange:
             self.peer_ptrs.append(per_set)
             flat = [per_set[p][c] for p in range(world) for c in range(ncols)]
             self.peer_arr.append((C.c_void_p * len(flat))(*flat))
+        # dma=True: the kernel regroups into a LOCAL staging copy of the region layout (own rows go straight into the own
+        # receive buffer) and copy engines push region p to peer p (tg_memcpy_d2d_async) — the NVLink transfer then needs
+        # no SM and runs under the probe kernel of the previous step
+        self.staging = []
+        self.stage_arr = []
+        self.copy_streams = []
+        if self.dma:
+            # one stream's copies run back to back on one copy engine (~500 GB/s measured at 8 GPUs); a few streams keep
+            # several engines and NVLink paths busy
+            self.copy_streams = [torch.cuda.Stream(device=self.dev) for _ in range(min(4, world - 1))]
+            for c in range(ncols):
+                p = C.c_void_p()
+                abi.check(lib.tg_dev_alloc(device, C.c_size_t(world * self.cap * 8 + 64), C.byref(p)))
+                self.staging.append(p.value)
+            for s in range(self.sets):
+                # the kernel writes destination p at rows [rank*cap, ...) of the pointer it is given: bias the staging
+                # pointer so that this lands in staging region p
+                flat = [self.recv_ptrs[s][c] if p == rank else self.staging[c] + (p - rank) * self.cap * 8
+                        for p in range(world) for c in range(ncols)]
+                self.stage_arr.append((C.c_void_p * len(flat))(*flat))
 
     def _view(self, ptr: int, n: int):
         class _A:
@@ -250,21 +271,50 @@ class SegmentExchange:
         a.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
         return self.torch.as_tensor(a, device=self.dev)
 
-    def exchange(self, key, cols):
+    def exchange(self, key, cols, before_gather=None, trace=None):
         """cols[0] must be `key`.  Everything is enqueued on self.stream (the caller's current stream must be self.stream).
+        `before_gather` (optional callable) runs between the scatter and the all-gather: a caller that probes on another
+        stream makes self.stream wait there for its probe of the PREVIOUS step — the all-gather is what lets the peers
+        move on to the step that overwrites the buffer set that probe is still reading, the scatter is not.
         -> (received columns: world*cap rows each, seg_cnt tensor [world], cap)"""
         torch, dist, lib, abi = self.torch, self.dist, self.lib, self.abi
         s = self.step % self.sets
         self.step += 1
         st = C.c_void_p(self.stream.cuda_stream)
         src_p = (C.c_void_p * len(cols))(*[c.data_ptr() for c in cols])
+
+        def mark(name):
+            if trace is not None:
+                e = torch.cuda.Event(enable_timing=True); e.record(self.stream); trace.append((name, e))
+        mark("x0")
         abi.check(lib.tg_partition_exchange_cf(self.device, C.c_void_p(key.data_ptr()), C.c_int64(key.numel()), self.world, len(cols), src_p,
-                                               self.peer_arr[s], C.c_int64(self.rank * self.cap), C.c_int64(self.cap),
+                                               self.stage_arr[s] if self.dma else self.peer_arr[s], C.c_int64(self.rank * self.cap), C.c_int64(self.cap),
                                                C.c_void_p(self.sent[s].data_ptr()), C.c_void_p(self.overflow[s].data_ptr()), st))
         self.launches += 2
+        if self.dma:
+            # whole regions (capacity, not fill: the fill counts never reach the host), ring order so that the peers'
+            # NVLink ingress is spread evenly
+            regrouped = torch.cuda.Event(); regrouped.record(self.stream)
+            for cs in self.copy_streams:
+                cs.wait_event(regrouped)
+            for k in range(1, self.world):
+                p = (self.rank + k) % self.world
+                cs = self.copy_streams[(k - 1) % len(self.copy_streams)]
+                for c in range(len(cols)):
+                    abi.check(lib.tg_memcpy_d2d_async(self.device, C.c_void_p(self.peer_ptrs[s][p][c] + self.rank * self.cap * 8),
+                                                      C.c_void_p(self.staging[c] + p * self.cap * 8), C.c_size_t(self.cap * 8),
+                                                      C.c_void_p(cs.cuda_stream)))
+            for cs in self.copy_streams:
+                sent = torch.cuda.Event(); sent.record(cs)
+                self.stream.wait_event(sent)
+        mark("scatter+dma enqueued-end")
+        if before_gather is not None:
+            before_gather()
+        mark("after wait")
         # counts[src, dst] on every rank; completes only after every peer's scatter kernel (stream order) — the barrier
         dist.all_gather_into_tensor(self.count_mat[s], self.sent[s][:self.world])
         self.seg_cnt[s].copy_(self.count_mat[s].view(self.world, self.world)[:, self.rank])
+        mark("gathered")
         return [self._view(self.recv_ptrs[s][c], self.world * self.cap) for c in range(len(cols))], self.seg_cnt[s], self.cap
 
     def check_overflow(self):
@@ -284,4 +334,7 @@ class SegmentExchange:
                     self.lib.tg_ipc_close(self.device, C.c_void_p(self.peer_ptrs[s][p][c]))
             for ptr in self.recv_ptrs[s]:
                 self.lib.tg_dev_free(self.device, C.c_void_p(ptr))
+        for ptr in self.staging:
+            self.lib.tg_dev_free(self.device, C.c_void_p(ptr))
         self.recv_ptrs = []
+        self.staging = []
