@@ -277,6 +277,14 @@ def run_gpu(args):
             # waits for that probe.  Without --overlap both streams are the same one and the waits are no-ops.
             xs = xseg.stream
             prev = done_ev[0]
+            if args.overlap >= 2 and xseg.dma:
+                # three-deep: regroup step k+1 | copy engines move step k (NVLink) | probe step k-1
+                cols_in, seg_cnt, cap, got = xseg.exchange_async(pk, [pk, pv], prev_probe_done=prev, prev2_probe_done=done_ev[1])
+                with torch.cuda.stream(stream):
+                    stream.wait_event(got)
+                    rows, cols, _ = join.probe_segments(cols_in, seg_cnt, cap, sync=sync)
+                    ev = torch.cuda.Event(); ev.record(stream); done_ev[1] = done_ev[0]; done_ev[0] = ev
+                    return (rows, check_piece(cols, rows)) if sync else (None, None)
             with torch.cuda.stream(xs):
                 if prev is not None and (sync or not args.overlap):
                     xs.wait_event(prev)
@@ -357,14 +365,16 @@ def run_gpu(args):
     traffic = args.ncu_traffic_bytes
     if traffic is None:
         try:   # per-launch DRAM bytes of the committed ncu --set full capture of this kernel
-            traffic = float(json.load(open(os.path.join(ROOT, "profiles", "r1_probe_final_traffic.json")))["dram_bytes_per_launch"])
+            traffic = float(json.load(open(os.path.join(ROOT, "profiles", "r1_pipeline_traffic.json" if os.environ.get("TG_PROBE_PARTITION", "1") == "1" else "r1_probe_final_traffic.json")))["dram_bytes_per_launch"])
         except Exception:
             traffic = None
     if world == 1:
         achieved = BYTES_PER_PROBE_ROW * npb / (ms_step * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "kernel": "k_probe_inner_u1_w<4,1,2,1>", "algorithmic_bytes_per_launch": BYTES_PER_PROBE_ROW * npb,
+                "kernel": ("k_partition_scatter_bulk<1,2,4> + k_probe_inner_u1_seg<1,2,1> (L2 partition pass + segment probe: one step; frac is over the WHOLE step)"
+                           if os.environ.get("TG_PROBE_PARTITION", "1") == "1" else "k_probe_inner_u1_w<4,1,2,1>"),
+                "algorithmic_bytes_per_launch": BYTES_PER_PROBE_ROW * npb,
                 "read_only_frac": 32 * npb / (ms_step * 1e-3) / 1e9 / hbm_peak}
 
     # ---- e2e: host buffers through tg_join_probe_push / tg_join_next (N = 1 path; per rank at N > 1) ---------
@@ -574,7 +584,7 @@ def main():
     ap.add_argument("--ref-sample-rows", type=int, default=8_000_000)
     ap.add_argument("--e2e-chunk-rows", type=int, default=4 << 20)
     ap.add_argument("--exchange", default="cf", choices=["cf", "p2p", "nccl"], help="N>1 probe-side exchange: cf = count-free peer stores + segmented probe (no host round trip), p2p = counted peer stores, nccl = local scatter + all_to_all")
-    ap.add_argument("--overlap", type=int, default=1, help="N>1, --exchange cf: run the exchange of step k+1 on a second stream under the probe of step k")
+    ap.add_argument("--overlap", type=int, default=2, help="N>1, --exchange cf: 1: run the exchange of step k+1 on a second stream under the probe of step k; 2: additionally a transfer stream, so regroup / NVLink copy / probe work on three consecutive steps")
     ap.add_argument("--dma", type=int, default=1, help="N>1, --exchange cf: regroup locally, let copy engines move the regions over NVLink")
     ap.add_argument("--xchunks", type=int, default=1, help="N>1: pieces the probe side is exchanged in (overlap with the probe kernel)")
     ap.add_argument("--skip-e2e", action="store_true")

@@ -366,7 +366,7 @@ int tg_partition_exchange(int device, const int64_t* key_dev, int64_t rows, int3
 /* Count-free variant (no histogram pass, no host round trip): every destination p owns, inside each receiver's
  * buffers, the fixed-capacity region [region_base, region_base + region_cap) reserved for THIS sender; rows are
  * appended there in arrival order and sent_rows_dev[p] (device, zeroed by the call) ends up holding how many rows went
- * to p.  A destination that would overflow raises *overflow_dev (device u64, zeroed by the call) and drops the excess —
+ * to p.  A destination that would overflow raises *overflow_dev (device u64, sticky: the caller zeroes it once) and drops the excess —
  * the caller re-runs that step through tg_partition_count + tg_partition_exchange.  Returns after ENQUEUEING on `stream`.
  * The MPP analogue is still ExchangeSender/HashPartition (physical_exchange_sender.go:115); the reference sizes
  * its per-partition chunks dynamically on the host (shuffle.go:450), which a single GPU kernel cannot.            */

@@ -542,12 +542,25 @@ k_probe_inner_u1_seg(const int64_t* __restrict__ pkey, int64_t n, TableView t, F
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t ntiles = n / 128;
-  for (int64_t tile = warp_id; tile < ntiles; tile += warps_total) {
+  const int64_t nseg = ntiles / seg.tiles_per_seg;
+  // Pass 1 sweeps the FULL tiles, pass 2 the (at most one per segment) partial tile at the end of each segment: a partial
+  // tile adds an odd row count to the output cursor about half the time, and from then on every 128-row reservation
+  // would start at an odd row — misaligned for the 128-bit stores of the all-matched path.
+  for (int64_t it = warp_id; it < ntiles + nseg; it += warps_total) {
+    int64_t tile = it;
+    if (it >= ntiles) {
+      const int64_t sp = it - ntiles;
+      const unsigned long long cc = seg.cnt[sp];
+      const int64_t fill = (int64_t)(cc < (unsigned long long)seg.cap ? cc : (unsigned long long)seg.cap);
+      if ((fill & 127) == 0) continue;
+      tile = sp * seg.tiles_per_seg + fill / 128;
+    }
     const int64_t base = tile * 128;
     const uint32_t p = (uint32_t)tile / seg.tiles_per_seg;
     const unsigned long long c = seg.cnt[p];
     const int64_t limit = (int64_t)p * seg.cap + (int64_t)(c < (unsigned long long)seg.cap ? c : (unsigned long long)seg.cap);
     if (base >= limit) continue;
+    if (it < ntiles && limit - base < 128) continue;   // partial tile: pass 2
     int64_t k[R];
     unsigned long long pv[R][NPC > 0 ? NPC : 1];
     unsigned long long sl[R];

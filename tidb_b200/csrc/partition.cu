@@ -94,7 +94,7 @@ int tg_partition_exchange(int device, const int64_t* key_dev, int64_t rows, int3
 
 static __global__ void k_zero_cf(unsigned long long* sent, unsigned long long* overflow, long long* bases, long long base) {
   if (threadIdx.x < TG_MAX_PARTS) { sent[threadIdx.x] = 0; bases[threadIdx.x] = base; }
-  if (threadIdx.x == 0) *overflow = 0;
+  (void)overflow;   // sticky: zeroed once by the owner, so an overflow of ANY step is still visible when the host looks
 }
 
 int tg_partition_exchange_cf(int device, const int64_t* key_dev, int64_t rows, int32_t nparts, int32_t ncols,

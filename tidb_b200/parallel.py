@@ -257,6 +257,23 @@ class SegmentExchange:
                 p = C.c_void_p()
                 abi.check(lib.tg_dev_alloc(device, C.c_size_t(world * self.cap * 8 + 64), C.byref(p)))
                 self.staging.append(p.value)
+            # exchange_async(): a second staging set and a dedicated transfer stream, so that the regrouping kernel of
+            # step k+2 runs while the copy engines still move step k+1
+            self.staging2 = []
+            for s2 in range(self.sets):
+                row = []
+                for c in range(ncols):
+                    p = C.c_void_p()
+                    abi.check(lib.tg_dev_alloc(device, C.c_size_t(world * self.cap * 8 + 64), C.byref(p)))
+                    row.append(p.value)
+                self.staging2.append(row)
+            self.stage2_arr = []
+            for s2 in range(self.sets):
+                flat = [self.recv_ptrs[s2][c] if p == rank else self.staging2[s2][c] + (p - rank) * self.cap * 8
+                        for p in range(world) for c in range(ncols)]
+                self.stage2_arr.append((C.c_void_p * len(flat))(*flat))
+            self.dstream = torch.cuda.Stream(device=self.dev)
+            self.got = [None] * self.sets
             for s in range(self.sets):
                 # the kernel writes destination p at rows [rank*cap, ...) of the pointer it is given: bias the staging
                 # pointer so that this lands in staging region p
@@ -317,6 +334,49 @@ class SegmentExchange:
         mark("gathered")
         return [self._view(self.recv_ptrs[s][c], self.world * self.cap) for c in range(len(cols))], self.seg_cnt[s], self.cap
 
+    def exchange_async(self, key, cols, prev_probe_done=None, prev2_probe_done=None):
+        """Pipelined form of exchange() (dma=True): three engines work on three different steps at once —
+            self.stream : regroup step k into staging set k%2                         (SMs, HBM-bound)
+            self.dstream: copy the regions of step k to the peers, then all-gather    (copy engines, NVLink-bound)
+            caller      : probe step k-1                                              (SMs)
+        `prev_probe_done`: event recorded after the caller's probe of the PREVIOUS step; the all-gather of this step waits
+        for it (it releases the peers into the step that overwrites the receive set that probe reads).
+        `prev2_probe_done`: event after the probe of the step BEFORE that one — it read the receive set this step's
+        regrouping kernel writes its own rows into, so the kernel waits for it.
+        -> (received columns, seg_cnt, cap, event to wait for before probing)"""
+        assert self.dma, "exchange_async needs dma=True"
+        torch, dist, lib, abi = self.torch, self.dist, self.lib, self.abi
+        s = self.step % self.sets
+        self.step += 1
+        X, D = self.stream, self.dstream
+        src_p = (C.c_void_p * len(cols))(*[c.data_ptr() for c in cols])
+        with torch.cuda.stream(X):
+            if self.got[s] is not None:
+                X.wait_event(self.got[s])     # step k-2: its copies have left staging set s, its all-gather has read sent[s]
+            if prev2_probe_done is not None:
+                X.wait_event(prev2_probe_done)
+            abi.check(lib.tg_partition_exchange_cf(self.device, C.c_void_p(key.data_ptr()), C.c_int64(key.numel()), self.world, len(cols), src_p,
+                                                   self.stage2_arr[s], C.c_int64(self.rank * self.cap), C.c_int64(self.cap),
+                                                   C.c_void_p(self.sent[s].data_ptr()), C.c_void_p(self.overflow[s].data_ptr()),
+                                                   C.c_void_p(X.cuda_stream)))
+            self.launches += 2
+            regrouped = torch.cuda.Event(); regrouped.record(X)
+        with torch.cuda.stream(D):
+            D.wait_event(regrouped)
+            for k in range(1, self.world):
+                p = (self.rank + k) % self.world
+                for c in range(len(cols)):
+                    abi.check(lib.tg_memcpy_d2d_async(self.device, C.c_void_p(self.peer_ptrs[s][p][c] + self.rank * self.cap * 8),
+                                                      C.c_void_p(self.staging2[s][c] + p * self.cap * 8), C.c_size_t(self.cap * 8),
+                                                      C.c_void_p(D.cuda_stream)))
+            if prev_probe_done is not None:
+                D.wait_event(prev_probe_done)
+            dist.all_gather_into_tensor(self.count_mat[s], self.sent[s][:self.world])
+            self.seg_cnt[s].copy_(self.count_mat[s].view(self.world, self.world)[:, self.rank])
+            got = torch.cuda.Event(); got.record(D)
+            self.got[s] = got
+        return [self._view(self.recv_ptrs[s][c], self.world * self.cap) for c in range(len(cols))], self.seg_cnt[s], self.cap, got
+
     def check_overflow(self):
         """host check (synchronises): raises when some step dropped rows because a region was too small"""
         bad = sum(int(o.item()) for o in self.overflow)
@@ -334,7 +394,7 @@ class SegmentExchange:
                     self.lib.tg_ipc_close(self.device, C.c_void_p(self.peer_ptrs[s][p][c]))
             for ptr in self.recv_ptrs[s]:
                 self.lib.tg_dev_free(self.device, C.c_void_p(ptr))
-        for ptr in self.staging:
+        for ptr in self.staging + [q for row in getattr(self, "staging2", []) for q in row]:
             self.lib.tg_dev_free(self.device, C.c_void_p(ptr))
         self.recv_ptrs = []
         self.staging = []
