@@ -20,7 +20,8 @@ def _worker(rank, world, port, q):
     from nested_loop import columns_sorted
     from tidb_b200 import abi
     from tidb_b200.chunk import Chunk, Column
-    from tidb_b200.parallel import exchange_by_key_host, partition_of_keys_np, recv_bases
+    from tidb_b200.parallel import (exchange_by_key_host, exchange_segments_host, partition_of_keys_np, recv_bases, region_capacity,
+                                    segments_to_dense)
     from tidb_b200.plan import FieldType, JoinPlan
     lib = abi.load_lib()
     INT = FieldType(abi.TYPE_LONGLONG, abi.FLAG_NOT_NULL)
@@ -48,8 +49,20 @@ def _worker(rank, world, port, q):
     mat = np.stack(mats)
     base, nrecv = recv_bases(mat, rank)
     assert nrecv == len(lpk) and np.array_equal(base, mat[:rank].sum(axis=0))
+    # count-free (segment) exchange, the layout SegmentExchange / tg_partition_exchange_cf use on the device: one fixed-capacity
+    # region per sender, fill counts travel separately, nothing is compacted; the valid rows are the same multiset
+    cap = region_capacity(npr, world)
+    assert cap % 1024 == 0 and cap >= npr / world
+    seg_cols, seg_cnt, ovf = exchange_segments_host(pk, [pk, pv], world, rank, cap, all_to_all)
+    assert not ovf and int(seg_cnt.sum()) == nrecv and np.array_equal(seg_cnt, mat[:, rank])
+    assert all(len(c) == world * cap for c in seg_cols)
+    dk, dv = segments_to_dense(seg_cols, seg_cnt, cap)
+    assert np.array_equal(np.sort(dv), np.sort(lpv)) and np.array_equal(dk[np.argsort(dv)], lpk[np.argsort(lpv)])
+    # a region that is too small drops rows and says so (the device path raises its sticky flag the same way)
+    _, small_cnt, small_ovf = exchange_segments_host(pk, [pk, pv], world, rank, 1024, all_to_all)
+    assert small_ovf and int(small_cnt.max()) == 1024
     plan = JoinPlan(abi.JOIN_INNER, [INT, INT], [INT, INT], [0], [0])
-    n, cols = O.OracleJoin(plan, 2).run([Chunk([Column(lbk), Column(lbv)])], Chunk([Column(lpk), Column(lpv)]).split(1024))
+    n, cols = O.OracleJoin(plan, 2).run([Chunk([Column(lbk), Column(lbv)])], Chunk([Column(dk), Column(dv)]).split(1024))
     shard = [c[0] for c in cols]
     allparts = [None] * world
     dist.all_gather_object(allparts, (shard, (bk, bv, pk, pv)))

@@ -67,6 +67,42 @@ def exchange_by_key_host(keys: np.ndarray, cols: Sequence[np.ndarray], world: in
     return out
 
 
+def region_capacity(rows_per_step: int, world: int, slack: float = 1.06) -> int:
+    """rows of one (sender, receiver) region of the count-free exchange: expected share + slack, a multiple of the
+    1024-row scatter tile (tg_join_probe_dev_seg requires it)"""
+    return ((int(rows_per_step / world * slack) + 8192 + 1023) // 1024) * 1024
+
+
+def exchange_segments_host(keys: np.ndarray, cols: Sequence[np.ndarray], world: int, rank: int, cap: int,
+                           all_to_all: Callable[[List], List]):
+    """CPU rendering of SegmentExchange (gloo tests): same region layout, same bookkeeping, same overflow rule.
+    Every sender appends the rows of destination d to ITS region of d's receive buffer (at most `cap` rows, the excess is
+    dropped and flagged); the receiver sees `world` segments of `cap` rows, segment s valid for seg_cnt[s] rows.
+    -> (received columns of world*cap rows each, seg_cnt[world], overflow flag)"""
+    dest = partition_of_keys_np(keys, world)
+    pieces, sent, overflow = [], np.zeros(world, dtype=np.int64), False
+    for d in range(world):
+        idx = np.nonzero(dest == d)[0]
+        if len(idx) > cap:
+            overflow = True
+            idx = idx[:cap]
+        sent[d] = len(idx)
+        pieces.append([np.ascontiguousarray(c[idx]) for c in cols])
+    got = all_to_all(pieces)                      # got[s] = the columns sender s appended to my region s
+    out = [np.zeros(world * cap, dtype=c.dtype) for c in cols]
+    seg_cnt = np.zeros(world, dtype=np.int64)
+    for s_, piece in enumerate(got):
+        seg_cnt[s_] = len(piece[0])
+        for c in range(len(cols)):
+            out[c][s_ * cap:s_ * cap + len(piece[c])] = piece[c]
+    return out, seg_cnt, overflow
+
+
+def segments_to_dense(cols: Sequence[np.ndarray], seg_cnt: np.ndarray, cap: int) -> List[np.ndarray]:
+    """the valid rows of a segmented column set, in segment order (what tg_join_probe_dev_seg probes)"""
+    return [np.concatenate([c[s_ * cap:s_ * cap + int(n)] for s_, n in enumerate(seg_cnt)]) for c in cols]
+
+
 class KeyExchange:
     """Device-side exchange for `ncols` 8-byte columns (key first) on one rank."""
 
@@ -202,7 +238,7 @@ class SegmentExchange:
         self.rank, self.world, self.device, self.stream, self.ncols = rank, world, device, stream, ncols
         self.dev = torch.device("cuda", device)
         self.dma = bool(dma) and world > 1
-        self.cap = ((int(rows_per_step / world * slack) + 8192 + 1023) // 1024) * 1024   # rows per (sender, receiver) region
+        self.cap = region_capacity(rows_per_step, world, slack)   # rows per (sender, receiver) region
         self.sets = 2
         self.step = 0
         self.launches = 0
