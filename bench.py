@@ -121,6 +121,30 @@ def gen_local(torch, dev, rank, world, n_build, n_probe):
 # ---------------------------------------------------------------------------------------------------------
 # CPU legs (oracle): the only place bench.py touches oracle/
 # ---------------------------------------------------------------------------------------------------------
+def host_threads():
+    """threads the CPU baseline may really use: CPUs in the affinity mask, capped by a cgroup CPU quota when one is set
+    (os.cpu_count() reports the machine, not the container)"""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.999)))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, (q + per - 1) // per))
+            break
+        except Exception:
+            continue
+    return max(1, n)
+
+
 def cpu_probe_rate(bk, bv, pk, pv, sample_rows, threads, steps, warmup):
     """Probe rows/s of the reference algorithm's restatement (oracle/join.cpp) on `threads` host threads:
     full build, probe of the first `sample_rows` probe rows fed as 1024-row chunks."""
@@ -157,7 +181,7 @@ def run_reference(args):
     rng = np.random.default_rng(43)
     pk = rng.integers(0, nb, sample).astype(np.int64) * np.int64(ODD)
     pv = np.arange(sample, dtype=np.int64)
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     rate, ms, rows, bsec = cpu_probe_rate(bk, bv, pk, pv, sample, threads, args.steps, args.warmup)
     assert rows == sample
     line = {
@@ -389,7 +413,7 @@ def run_gpu(args):
     cpu = None
     if world == 1 and not args.skip_cpu:
         sample = min(npb, args.cpu_sample_rows)
-        threads = os.cpu_count() or 1
+        threads = host_threads()
         rate, ms, rows_c, bsec = cpu_probe_rate(bk.cpu().numpy(), bv.cpu().numpy(), pk[:sample].cpu().numpy(), pv[:sample].cpu().numpy(),
                                                 sample, threads, 2, 1)
         assert rows_c == sample

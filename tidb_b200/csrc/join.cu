@@ -728,6 +728,7 @@ static int probe_device(tg_join* j, const DevCols& pview, int64_t n, ResultBatch
       if (warp_ok) {
         const int64_t* pkey = reinterpret_cast<const int64_t*>(ks.data);
         size_t table_bytes = (size_t)j->tv.nslots * sizeof(Slot);
+        bool partitioned = false;   // the L2 partition pass + segment probe took the whole call
         bool src16 = aligned16(pkey);
         for (int c = 0; c < fo.n_pcols; c++) src16 = src16 && aligned16(fo.psrc[c]);
         const int64_t PTILE = 1024;   // rows per scatter tile (k_partition_scatter_bulk<.., 4>)
@@ -775,10 +776,10 @@ static int probe_device(tg_join* j, const DevCols& pview, int64_t n, ResultBatch
               TG_TRY(launch_probe_warp(j, pkey + n_main, n - n_main, tail, cur, tune));
               j->stats.kernel_launches++;
             }
-            goto fast_done;
+            partitioned = true;
           }
         }
-        if (tune.partition == 2 && n >= (1ll << 20) && table_bytes > ((size_t)tune.part_min_mb << 20)) {
+        if (!partitioned && !in_seg && tune.partition == 2 && n >= (1ll << 20) && table_bytes > ((size_t)tune.part_min_mb << 20)) {
           // counted variant (kept for A/B runs): histogram pass → exact offsets → dense partitions
           int P = tune.parts > 0 ? tune.parts : (int)((table_bytes + (32u << 20) - 1) / (32u << 20));
           if (P > TG_MAX_PARTS) P = TG_MAX_PARTS;
@@ -808,27 +809,27 @@ static int probe_device(tg_join* j, const DevCols& pview, int64_t n, ResultBatch
             for (int c = 0; c < fo.n_pcols; c++) fo.psrc[c] = j->part_cols[1 + c]->as<unsigned long long>();
           }
         }
-        bool tma_ok = tune.tma && !in_seg && aligned16(pkey);
+        bool tma_ok = !partitioned && tune.tma && !in_seg && aligned16(pkey);
         for (int c = 0; c < fo.n_pcols; c++) tma_ok = tma_ok && aligned16(fo.psrc[c]);
         int64_t full_tiles = tma_ok ? n / TG_PROBE_TILE : 0;
         if (full_tiles > 0) TG_TRY(launch_probe_tma(j, pkey, full_tiles, fo, cur, tune));
-        int64_t done = full_tiles * TG_PROBE_TILE;
+        int64_t done = partitioned ? n : full_tiles * TG_PROBE_TILE;
         if (done < n) {
           FastOut tail = fo;
           for (int c = 0; c < fo.n_pcols; c++) tail.psrc[c] = fo.psrc[c] + done;
           if (in_seg) TG_TRY(launch_probe_warp(j, pkey, n, fo, cur, tune, SegSpec{in_seg->cnt, in_seg->tiles_per_seg, 0, in_seg->cap, nullptr}));
           else TG_TRY(launch_probe_warp(j, pkey + done, n - done, tail, cur, tune));
-          if (full_tiles > 0) j->stats.kernel_launches++;
+          j->stats.kernel_launches++;
         }
+        if (full_tiles > 0) j->stats.kernel_launches++;
       } else {
         constexpr int R = 4;
         int64_t tiles = (n + 256 * R - 1) / (256 * R);
         int grid = (int)std::min<int64_t>(tiles, (int64_t)j->nsm * (tune.ctas_per_sm > 0 ? tune.ctas_per_sm : 8));
         k_probe_inner_u1<R><<<grid, 256, 0, j->stream>>>(reinterpret_cast<const int64_t*>(ks.data), pview, n, j->tv, oc, cur);
+        j->stats.kernel_launches++;
       }
-      j->stats.kernel_launches++;
     }
-  fast_done:
     if (sync_count) {
       unsigned long long got = 0;
       TG_CUDA(cudaMemcpyAsync(&got, cur, 8, cudaMemcpyDeviceToHost, j->stream));
