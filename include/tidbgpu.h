@@ -126,6 +126,23 @@ typedef struct tg_mut_chunk {
 } tg_mut_chunk;
 
 /* ---------------------------------------------------------------------------------------------
+ * Chunk wire format (host code): chunk.Codec, pkg/util/chunk/codec.go — Encode :41, DecodeToChunk :93,
+ * decodeColumn :101, setAllNotNull :145.  Per column: u32 length | u32 nullCount | [bitmap if nullCount > 0] |
+ * [offsets (length+1) x i64 if var-len] | data.  Coprocessor / TiFlash responses use it, so a cgo shim can hand the
+ * response buffer over as is.
+ * ------------------------------------------------------------------------------------------- */
+int tg_chunk_wire_size(const tg_chunk* chk, size_t* bytes);
+int tg_chunk_encode(const tg_chunk* chk, uint8_t* buf, size_t cap, size_t* written);
+/* zero copy: cols_out[i] alias buf, like the Go decoder's Columns alias the gRPC message; null_bitmap == NULL where the
+ * wire carried no NULLs.  `consumed` = bytes of buf that belonged to these ncols columns.                          */
+int tg_chunk_decode(const uint8_t* buf, size_t len, int32_t ncols, const int32_t* mysql_types, tg_column* cols_out,
+                    size_t* consumed);
+/* decode the fixed-width columns straight into caller-owned (e.g. tg_host_alloc'ed, pinned) buffers; columns whose
+ * out->cols[i].data is NULL are skipped                                                                           */
+int tg_chunk_decode_into(const uint8_t* buf, size_t len, int32_t ncols, const int32_t* mysql_types, tg_mut_chunk* out,
+                         int64_t* rows, size_t* consumed);
+
+/* ---------------------------------------------------------------------------------------------
  * pinned host memory for a chunk.ColumnAllocator (pkg/util/chunk/column.go:85) backed by
  * cudaHostAlloc, precedent: pkg/lightning/manual/manual.go (C.calloc behind Go slices).
  * Buffers from here make H2D/D2H copies true DMA; any other host pointer is accepted too.

@@ -104,6 +104,7 @@ EXPORTED_SYMBOLS = [
     "tg_last_error", "tg_abi_version", "tg_device_count", "tg_device_info", "tg_fixed_len",
     "tg_host_alloc", "tg_host_free", "tg_dev_alloc", "tg_dev_free", "tg_memcpy_h2d", "tg_memcpy_d2h", "tg_memcpy_d2d_async",
     "tg_device_synchronize",
+    "tg_chunk_wire_size", "tg_chunk_encode", "tg_chunk_decode", "tg_chunk_decode_into",
     "tg_join_supported", "tg_join_open", "tg_join_build_push", "tg_join_build_push_dev",
     "tg_join_build_finish", "tg_join_probe_push", "tg_join_probe_finish", "tg_join_next", "tg_join_next_wait", "tg_join_probe_rewind",
     "tg_join_close", "tg_join_probe_dev", "tg_join_probe_dev_seg", "tg_join_get_stats",
