@@ -13,8 +13,12 @@ probe side against the already built table:
           buffers, host→device and device→host copies inside the timed region
 N > 1 (weak scaling, per-GPU work fixed): every rank owns 10M build + 100M probe rows whose keys are uniform
 over the GLOBAL key set, so a key-hash repartition is mandatory: build side repartitioned once (untimed,
-like the build itself), every timed step = partition kernel + exchange of the probe columns over NVLink +
-shard-local probe.
+like the build itself), every timed step = regroup the probe columns by destination GPU + move them over
+NVLink + shard-local probe (L2 partition pass + segment probe).  Default (--exchange cf --dma 1 --overlap 2):
+the count-free exchange of tidb_b200/parallel.py:SegmentExchange; the three stages of consecutive steps overlap
+(regroup k+1 | copy engines k | probe k-1), the way a stream of probe batches is processed.  The timed region
+holds exactly K regroups, K transfers and K probes (the pipeline is empty at both events: barrier +
+synchronize before, the last probe's completion after), so short runs pay the fill/drain once.
 
 Prints ONE JSON line (rank 0).
 """
