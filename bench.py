@@ -424,6 +424,12 @@ def run_gpu(args):
         cpu = {"value": rate, "unit": "rows/s", "cores": threads, "kind": "port",
                "sample": f"full {nb}-row build ({bsec:.2f}s, untimed) + probe of the first {sample} probe rows as 1024-row chunks, mean of 2 after 1 warm-up; "
                          "oracle/join.cpp restates TiDB's HashJoinV2 (not the Go binary)"}
+        if threads > 5:
+            # the reference's own default: tidb_executor_concurrency = 5 (SURVEY §8d asks for both figures)
+            s5 = min(sample, 2_000_000)
+            r5, _, rows5, _ = cpu_probe_rate(bk.cpu().numpy(), bv.cpu().numpy(), pk[:s5].cpu().numpy(), pv[:s5].cpu().numpy(), s5, 5, 2, 1)
+            assert rows5 == s5
+            cpu["value_at_reference_default_concurrency_5"] = r5
 
     if rank == 0:
         line = {
