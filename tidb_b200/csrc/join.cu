@@ -582,7 +582,7 @@ static bool fast_path_ok(const tg_join* j, const DevCols& pview) {
 }
 
 // ---- fast-path launch tuning (env overrides are for A/B sweeps on the GPU box; defaults are the measured best) ----
-struct ProbeTuning { int variant; int R; int evict_last; int ctas_per_sm; int partition; int parts; int part_min_mb; int part_min_rows; int seg_vec; int tma; int stages; int tma_ctas; int cta_agg; };
+struct ProbeTuning { int variant; int R; int evict_last; int ctas_per_sm; int partition; int parts; int part_min_mb; int part_min_rows; int seg_vec; int seg_lean; int carveout; int tma; int stages; int tma_ctas; int cta_agg; };
 static ProbeTuning probe_tuning() {
   ProbeTuning t;
   t.variant = env_int("TG_PROBE_VARIANT", 1);      // 0: CTA-tile kernel (shared-memory offsets), 1: warp-autonomous kernel
@@ -594,6 +594,8 @@ static ProbeTuning probe_tuning() {
   t.part_min_mb = env_int("TG_PROBE_PART_MIN_MB", 64);
   t.part_min_rows = env_int("TG_PROBE_PART_MIN_ROWS", 1 << 22);
   t.seg_vec = env_int("TG_PROBE_SEG_VEC", 1);            // 128-bit loads/stores in the segment probe
+  t.seg_lean = env_int("TG_PROBE_SEG_LEAN", 0);          // EXPERIMENTAL: 1 = lean full-tile path, 2 = + register prefetch (round-2 A/B)
+  t.carveout = env_int("TG_PROBE_CARVEOUT", -1);         // EXPERIMENTAL: preferred shared-memory carve-out (%) of the segment probe kernels, -1 = driver default
   t.tma = env_int("TG_PROBE_TMA", 0);               // TMA-fed kernels (cp.async.bulk ring) for the streamed inputs
   t.stages = env_int("TG_PROBE_STAGES", 4);
   t.tma_ctas = env_int("TG_PROBE_TMA_CTAS", 3);
@@ -669,6 +671,16 @@ struct LaunchSeg {
     int64_t ctas = (n / 128 + 7) / 8;
     int per_sm = t.ctas_per_sm > 0 ? t.ctas_per_sm : resident;
     int grid = (int)std::min<int64_t>(ctas, (int64_t)j->nsm * per_sm);
+    if (t.seg_lean && j->tv.pair_home) {   // experimental lean variants (see join_kernels.cuh); 3 CTAs per SM as well
+      if (t.carveout >= 0) {
+        cudaFuncSetAttribute(k_probe_inner_u1_seg_lean<NPC, NKD, NMD, false>, cudaFuncAttributePreferredSharedMemoryCarveout, t.carveout);
+        cudaFuncSetAttribute(k_probe_inner_u1_seg_lean<NPC, NKD, NMD, true>, cudaFuncAttributePreferredSharedMemoryCarveout, t.carveout);
+      }
+      if (t.seg_lean >= 2) k_probe_inner_u1_seg_lean<NPC, NKD, NMD, true><<<grid, 256, 0, j->stream>>>(pkey, n, j->tv, fo, cur, seg);
+      else k_probe_inner_u1_seg_lean<NPC, NKD, NMD, false><<<grid, 256, 0, j->stream>>>(pkey, n, j->tv, fo, cur, seg);
+      return TG_OK;
+    }
+    if (t.carveout >= 0) cudaFuncSetAttribute(k_probe_inner_u1_seg<NPC, NKD, NMD>, cudaFuncAttributePreferredSharedMemoryCarveout, t.carveout);
     k_probe_inner_u1_seg<NPC, NKD, NMD><<<grid, 256, 0, j->stream>>>(pkey, n, j->tv, fo, cur, seg);
     return TG_OK;
   }

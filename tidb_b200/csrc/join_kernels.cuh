@@ -588,6 +588,151 @@ k_probe_inner_u1_seg(const int64_t* __restrict__ pkey, int64_t n, TableView t, F
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// EXPERIMENTAL (TG_PROBE_SEG_LEAN=1|2, off by default; measured in tools/scratch/probe_lab.cu as P2b / P6, not yet on the
+// library's data): the same segment probe with a lean full-tile path — no per-row `in` flags, no slot array, sentinel-valued
+// keys detected once per tile (then the tile takes the generic path) — and, with PREFETCH, the next tile's keys/payloads
+// requested before the current tile's gathers are issued.  ncu: the production kernel executes 551 M warp instructions per
+// 100 M rows, the lab kernel 351 M.
+// ---------------------------------------------------------------------------------------------
+template <int NPC, int NKD, int NMD>
+__device__ __forceinline__ void probe_tile_generic(const int64_t* __restrict__ pkey, int64_t base, int64_t limit, const TableView& t,
+                                                   const FastOut& out, unsigned long long* __restrict__ out_cursor, int lane) {
+  constexpr int R = 4;
+  int64_t k[R];
+  unsigned long long pv[R][NPC > 0 ? NPC : 1];
+  unsigned long long sl[R];
+  bool in[R];
+#pragma unroll
+  for (int g = 0; g < R / 2; g++) {
+    const int64_t i = base + g * 64 + 2 * lane;
+    const ulonglong2 kk = __ldcs(reinterpret_cast<const ulonglong2*>(pkey + i));
+    in[2 * g] = i < limit; in[2 * g + 1] = i + 1 < limit;
+    k[2 * g] = in[2 * g] ? (int64_t)kk.x : kEmptyKey;
+    k[2 * g + 1] = in[2 * g + 1] ? (int64_t)kk.y : kEmptyKey;
+  }
+#pragma unroll
+  for (int g = 0; g < R / 2; g++) {
+    const int64_t i = base + g * 64 + 2 * lane;
+    sl[2 * g] = (k[2 * g] == kEmptyKey) ? t.nslots : home_slot(hash64((uint64_t)k[2 * g]), t.nslots, t.pair_home);
+    sl[2 * g + 1] = (k[2 * g + 1] == kEmptyKey) ? t.nslots : home_slot(hash64((uint64_t)k[2 * g + 1]), t.nslots, t.pair_home);
+#pragma unroll
+    for (int cc = 0; cc < NPC; cc++) {
+      const ulonglong2 pp = __ldcs(reinterpret_cast<const ulonglong2*>(out.psrc[cc] + i));
+      pv[2 * g][cc] = pp.x; pv[2 * g + 1][cc] = pp.y;
+    }
+  }
+  probe_rows_u1<R, NPC, NKD, NMD, false, true>(k, pv, sl, in, t, out, out_cursor, lane);
+}
+
+template <int NPC, int NKD, int NMD, bool PREFETCH>
+__global__ void __launch_bounds__(256, 3)
+k_probe_inner_u1_seg_lean(const int64_t* __restrict__ pkey, int64_t n, TableView t, FastOut out,
+                          unsigned long long* __restrict__ out_cursor, SegSpec seg) {
+  constexpr int R = 4, G = 2, NP = NPC > 0 ? NPC : 1;
+  if (seg.gate && ((*seg.gate != 0ull) != (seg.gate_want != 0))) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t ntiles = n / 128;
+  const int64_t nseg = ntiles / seg.tiles_per_seg;
+  ulonglong2 kn[G], pn[G][NP];
+  auto fetch = [&](int64_t tile) {
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      const int64_t i = tile * 128 + g * 64 + 2 * lane;
+      kn[g] = __ldcs(reinterpret_cast<const ulonglong2*>(pkey + i));
+#pragma unroll
+      for (int c = 0; c < NPC; c++) pn[g][c] = __ldcs(reinterpret_cast<const ulonglong2*>(out.psrc[c] + i));
+    }
+  };
+  // pass 1: full tiles (tile == it); the capacity of every segment is allocated in full, so a tile can always be loaded
+  if (PREFETCH && warp_id < ntiles) fetch(warp_id);
+  for (int64_t tile = warp_id; tile < ntiles; tile += warps_total) {
+    if (!PREFETCH) fetch(tile);
+    int64_t k[R];
+    unsigned long long pv[R][NP];
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      k[2 * g] = (int64_t)kn[g].x; k[2 * g + 1] = (int64_t)kn[g].y;
+#pragma unroll
+      for (int c = 0; c < NPC; c++) { pv[2 * g][c] = pn[g][c].x; pv[2 * g + 1][c] = pn[g][c].y; }
+    }
+    if (PREFETCH && tile + warps_total < ntiles) fetch(tile + warps_total);
+    const int64_t base = tile * 128;
+    const uint32_t p = (uint32_t)tile / seg.tiles_per_seg;
+    const unsigned long long c = seg.cnt[p];
+    const int64_t limit = (int64_t)p * seg.cap + (int64_t)(c < (unsigned long long)seg.cap ? c : (unsigned long long)seg.cap);
+    if (limit - base < 128) continue;                       // empty or partial tile: pass 2
+    const bool sentinel = (k[0] == kEmptyKey) | (k[1] == kEmptyKey) | (k[2] == kEmptyKey) | (k[3] == kEmptyKey);
+    if (__any_sync(0xffffffffu, sentinel)) {                // the key value used as the empty marker: generic path for this tile
+      probe_tile_generic<NPC, NKD, NMD>(pkey, base, limit, t, out, out_cursor, lane);
+      continue;
+    }
+    Slot v[R], w[R];
+#pragma unroll
+    for (int j = 0; j < R; j++) load_pair(t.slots + home_slot(hash64((uint64_t)k[j]), t.nslots, 1), v[j], w[j]);
+    unsigned long long meta[R];
+    unsigned bal[R];
+    uint32_t total = 0;
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+      bool m;
+      if (v[j].key == k[j]) { m = true; meta[j] = v[j].meta; }
+      else if (w[j].key == k[j]) { m = true; meta[j] = w[j].meta; }
+      else if (v[j].key == kEmptyKey || w[j].key == kEmptyKey) { m = false; meta[j] = 0; }
+      else {
+        // both home slots hold other keys: continue the linear probe behind the pair (rare at the configured load factor)
+        unsigned long long sl = home_slot(hash64((uint64_t)k[j]), t.nslots, 1) + 2;
+        if (sl >= t.nslots) sl = 0;
+        Slot x = load_slot(t.slots + sl);
+        while (x.key != k[j] && x.key != kEmptyKey) { if (++sl == t.nslots) sl = 0; x = load_slot(t.slots + sl); }
+        m = x.key == k[j]; meta[j] = x.meta;
+      }
+      bal[j] = __ballot_sync(0xffffffffu, m);
+      total += __popc(bal[j]);
+    }
+    unsigned long long wbase = 0;
+    if (lane == 0 && total) wbase = atomicAdd(out_cursor, (unsigned long long)total);
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (total == 128u && (wbase & 1ull) == 0) {
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        const unsigned long long o = wbase + (unsigned long long)(g * 64 + 2 * lane);
+        const ulonglong2 kk = make_ulonglong2((unsigned long long)k[2 * g], (unsigned long long)k[2 * g + 1]);
+#pragma unroll
+        for (int d = 0; d < NKD; d++) __stcs(reinterpret_cast<ulonglong2*>(out.key_dst[d] + o), kk);
+#pragma unroll
+        for (int d = 0; d < NMD; d++) __stcs(reinterpret_cast<ulonglong2*>(out.meta_dst[d] + o), make_ulonglong2(meta[2 * g], meta[2 * g + 1]));
+#pragma unroll
+        for (int cc = 0; cc < NPC; cc++) __stcs(reinterpret_cast<ulonglong2*>(out.pdst[cc] + o), make_ulonglong2(pv[2 * g][cc], pv[2 * g + 1][cc]));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < R; j++) {
+        if ((bal[j] >> lane) & 1u) {
+          const unsigned long long o = wbase + __popc(bal[j] & ((1u << lane) - 1));
+#pragma unroll
+          for (int d = 0; d < NKD; d++) __stcs(out.key_dst[d] + o, (unsigned long long)k[j]);
+#pragma unroll
+          for (int d = 0; d < NMD; d++) __stcs(out.meta_dst[d] + o, meta[j]);
+#pragma unroll
+          for (int cc = 0; cc < NPC; cc++) __stcs(out.pdst[cc] + o, pv[j][cc]);
+        }
+        wbase += __popc(bal[j]);
+      }
+    }
+  }
+  // pass 2: the partial tile of each segment (see k_probe_inner_u1_seg)
+  for (int64_t sp = warp_id; sp < nseg; sp += warps_total) {
+    const unsigned long long cc = seg.cnt[sp];
+    const int64_t fill = (int64_t)(cc < (unsigned long long)seg.cap ? cc : (unsigned long long)seg.cap);
+    if ((fill & 127) == 0) continue;
+    const int64_t base = (sp * seg.tiles_per_seg + fill / 128) * 128;
+    probe_tile_generic<NPC, NKD, NMD>(pkey, base, sp * seg.cap + fill, t, out, out_cursor, lane);
+  }
+}
+
 // TMA-fed: the streamed inputs (probe key + payload columns) arrive in shared memory through a STAGES-deep ring of
 // 1024-row tiles filled by cp.async.bulk (one elected thread, mbarrier completion).  Full tiles only; the tail
 // (< 1024 rows) is finished by k_probe_inner_u1_w on the same output cursor.
