@@ -777,7 +777,9 @@ static int probe_device(tg_join* j, const DevCols& pview, int64_t n, ResultBatch
                                                   &j->stats.kernel_launches));
             FastOut pf = fo;
             for (int c = 0; c < fo.n_pcols; c++) pf.psrc[c] = j->part_cols[1 + c]->as<unsigned long long>();
-            if (tune.seg_vec) TG_TRY(launch_probe_seg(j, j->part_cols[0]->as<int64_t>(), (int64_t)P * C, pf, cur, tune, SegSpec{cursors, (uint32_t)(C / 128), 0, C, flag}));
+            // the 128-bit stores of the segment kernel need 16-byte aligned output columns: results appended behind an odd
+            // number of rows fall back to the 8-byte kernel
+            if (tune.seg_vec && (rb.rows & 1) == 0) TG_TRY(launch_probe_seg(j, j->part_cols[0]->as<int64_t>(), (int64_t)P * C, pf, cur, tune, SegSpec{cursors, (uint32_t)(C / 128), 0, C, flag}));
             else TG_TRY(launch_probe_warp(j, j->part_cols[0]->as<int64_t>(), (int64_t)P * C, pf, cur, tune, SegSpec{cursors, (uint32_t)(C / 128), 0, C, flag}));
             TG_TRY(launch_probe_warp(j, pkey, n_main, fo, cur, tune,
                                      in_seg ? SegSpec{in_seg->cnt, in_seg->tiles_per_seg, 1, in_seg->cap, flag} : SegSpec{nullptr, 0, 1, 0, flag}));   // runs only after an overflow
