@@ -11,14 +11,17 @@ probe side against the already built table:
   value : columns resident in HBM, kernel-only (tg_join_probe_dev), CUDA events on the launch stream
   e2e   : the same probe through the host-facing C-ABI (tg_join_probe_push / tg_join_next) with pinned HOST
           buffers, host→device and device→host copies inside the timed region
-N > 1 (weak scaling, per-GPU work fixed): every rank owns 10M build + 100M probe rows whose keys are uniform
-over the GLOBAL key set, so a key-hash repartition is mandatory: build side repartitioned once (untimed,
-like the build itself), every timed step = regroup the probe columns by destination GPU + move them over
-NVLink + shard-local probe (L2 partition pass + segment probe).  Default (--exchange cf --dma 1 --overlap 2):
-the count-free exchange of tidb_b200/parallel.py:SegmentExchange; the three stages of consecutive steps overlap
-(regroup k+1 | copy engines k | probe k-1), the way a stream of probe batches is processed.  The timed region
-holds exactly K regroups, K transfers and K probes (the pipeline is empty at both events: barrier +
-synchronize before, the last probe's completion after), so short runs pay the fill/drain once.
+N > 1 (weak scaling, per-GPU work fixed) = BASELINE.json configs[4] divided by 8: every rank owns 12.5M build +
+125M probe rows (N = 8: the 1B x 100M join) whose keys are uniform over the GLOBAL key set, so a key-hash
+repartition is mandatory: build side repartitioned once (untimed, like the build itself), every timed step =
+regroup the probe columns by destination GPU + move them over NVLink + shard-local probe (L2 partition pass +
+segment probe).  Default (--exchange mail): tidb_b200/parallel.py:MailboxExchange — ONE kernel regroups 1024-row
+tiles and appends them to this rank's region on every peer with bulk stores over NVLink; the only synchronisation
+is device-side mailboxes (peer stores + spinning loads): no NCCL collective, no copy-engine call and no host wait
+inside a step.  The exchange stream runs one step ahead of the probe stream (two receive sets), the way a stream
+of probe batches is processed.  The timed region holds exactly K exchanges and K probes (the pipeline is empty at
+both events: barrier + synchronize before, the last probe's completion after).  --exchange auto times the
+candidate transports for a few untimed steps and keeps the fastest (reported in config).
 
 Prints ONE JSON line (rank 0).
 """
@@ -178,6 +181,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.build_rows is None:
+        args.build_rows = 10_000_000
+    if args.probe_rows is None:
+        args.probe_rows = 100_000_000
     nb, sample = args.build_rows, min(args.probe_rows, args.ref_sample_rows)
     rng = np.random.default_rng(42)
     ids = rng.permutation(nb).astype(np.int64)
@@ -224,6 +231,10 @@ def run_gpu(args):
     lib = abi.load_lib()
     assert lib.tg_device_count() > 0
     stream = torch.cuda.Stream(device=dev)
+    if args.build_rows is None:
+        args.build_rows = 10_000_000 if world == 1 else 12_500_000
+    if args.probe_rows is None:
+        args.probe_rows = 100_000_000 if world == 1 else 125_000_000
     nb, npb = args.build_rows, args.probe_rows
     hbm_peak, peak_src = peaks()
 
@@ -247,13 +258,15 @@ def run_gpu(args):
         xstream = torch.cuda.Stream(device=dev)
         # receive capacity: expected rows + 2 % (uniform hash; a skewed key set would need a count-then-allocate round)
         with torch.cuda.stream(stream):
-            xch_b = KeyExchange(rank, world, local, stream, 2, int(nb * 1.02) + 4096, "p2p" if args.exchange == "cf" else args.exchange)
+            xch_b = KeyExchange(rank, world, local, stream, 2, int(nb * 1.02) + 4096, "nccl" if args.exchange == "nccl" else "p2p")
         with torch.cuda.stream(xstream):
             # the probe side is exchanged in `xchunks` pieces through two alternating sets of receive buffers, so that the
             # NVLink scatter of piece c+1 overlaps the probe kernel of piece c
-            xch_p = [KeyExchange(rank, world, local, xstream, 2, int(npb / xchunks * 1.03) + 8192, "p2p" if args.exchange == "cf" else args.exchange)
-                     for _ in range(2 if xchunks > 1 else 1)]
-        if args.exchange == "cf":
+            xch_p = ([KeyExchange(rank, world, local, xstream, 2, int(npb / xchunks * 1.03) + 8192, args.exchange) for _ in range(2 if xchunks > 1 else 1)]
+                     if args.exchange in ("p2p", "nccl") else [])
+        if args.exchange in ("mail", "mail-dma", "auto"):
+            pass   # created below (after the build side's exchange), possibly several candidates
+        elif args.exchange == "cf":
             from tidb_b200.parallel import SegmentExchange
             xs = xstream if args.overlap else stream
             with torch.cuda.stream(xs):
@@ -292,11 +305,57 @@ def run_gpu(args):
 
     TRACE = [] if os.environ.get("BENCH_TRACE") else None
 
+    # ---- N > 1, mailbox exchange: candidates and (for --exchange auto) an untimed calibration -----------------------
+    xmail = None
+    mail_choice = None
+    mail_timings = {}
+    MAIL_CANDIDATES = {"mail": dict(dma=False, ctas_per_sm=args.scatter_ctas), "mail-c2": dict(dma=False, ctas_per_sm=2), "mail-dma": dict(dma=True, ctas_per_sm=0)}
+
+    def mail_step(xm, sync: bool):
+        with torch.cuda.stream(xstream):
+            xm.send(pk, [pk, pv])
+        with torch.cuda.stream(stream):
+            cols_in, seg_cnt, cap, s_, ep = xm.recv(stream)
+            rows, cols, _ = join.probe_segments(cols_in, seg_cnt, cap, sync=sync)
+            out = (rows, check_piece(cols, rows)) if sync else (None, None)
+            xm.release(stream, s_, ep)     # the probe has consumed receive set s_: the senders may overwrite it
+        return out
+
+    if world > 1 and args.exchange in ("mail", "mail-dma", "auto"):
+        from tidb_b200.parallel import MailboxExchange
+        names = ["mail", "mail-c2", "mail-dma"] if args.exchange == "auto" else [args.exchange]
+        timings = {}
+        for nm in names:
+            xm = MailboxExchange(rank, world, local, xstream, 2, npb, **MAIL_CANDIDATES[nm])
+            if len(names) > 1:
+                for _ in range(2):
+                    mail_step(xm, False)
+                barrier()
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                with torch.cuda.stream(stream):
+                    c0.record(stream); xstream.wait_event(c0)
+                    for _ in range(4):
+                        mail_step(xm, False)
+                    c1.record(stream)
+                stream.synchronize(); xm.check()
+                tt = torch.tensor([c0.elapsed_time(c1) / 4], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)      # every rank sees the same numbers -> the same choice
+                timings[nm] = float(tt.item())
+                xm.close()
+        if len(names) > 1:
+            mail_choice = min(timings, key=timings.get)
+            xmail = MailboxExchange(rank, world, local, xstream, 2, npb, **MAIL_CANDIDATES[mail_choice])
+        else:
+            mail_choice, xmail = names[0], xm
+        mail_timings = timings
+
     def step(sync: bool):
         """sync=True is the verifying pass: returns (rows, checksums)"""
         if world == 1:
             rows, cols, _ = join.probe([pk, pv], sync=sync)
             return (rows, check_piece(cols, rows)) if sync else (None, None)
+        if xmail is not None:
+            return mail_step(xmail, sync)
         if xseg is not None:
             # count-free exchange: scatter into the peers' regions -> all-gather of the counts (the barrier) -> segmented
             # probe; everything is enqueued on `stream`, the host never waits inside a step
@@ -358,7 +417,7 @@ def run_gpu(args):
     # ---- timed region: value (device resident) ----------------------------------------------------------------
     sampler = ClockSampler(local)
     l0 = join.stats().kernel_launches
-    lx0 = (sum(x.launches for x in xch_p) if xch_p else 0) + (xseg.launches if xseg else 0)
+    lx0 = (sum(x.launches for x in xch_p) if xch_p else 0) + (xseg.launches if xseg else 0) + (xmail.launches if xmail else 0)
     barrier()
     if rank == 0:
         sampler.start()
@@ -382,9 +441,11 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
-    launches_extra = (sum(x.launches for x in xch_p) if xch_p else 0) + (xseg.launches if xseg else 0)
+    launches_extra = (sum(x.launches for x in xch_p) if xch_p else 0) + (xseg.launches if xseg else 0) + (xmail.launches if xmail else 0)
     if xseg is not None:
         xseg.check_overflow()
+    if xmail is not None:
+        xmail.check()
     launches = (join.stats().kernel_launches - l0) + (launches_extra - lx0)
     value = npb * world / (ms_step * 1e-3)
 
@@ -405,13 +466,26 @@ def run_gpu(args):
                 "algorithmic_bytes_per_launch": BYTES_PER_PROBE_ROW * npb,
                 "read_only_frac": 32 * npb / (ms_step * 1e-3) / 1e9 / hbm_peak}
 
+    else:
+        # N GPUs: same algorithmic bytes per probe row, denominator = N x the per-GPU peak; the exchange adds
+        # NVLink payload = 16 B x (N-1)/N of the rows, per direction per GPU
+        achieved = BYTES_PER_PROBE_ROW * npb * world / (ms_step * 1e-3) / 1e9
+        nvl = 16.0 * npb * (world - 1) / world / (ms_step * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak * world, "unit": "GB/s", "frac": achieved / (hbm_peak * world),
+                "traffic": None, "peak_source": peak_src + f" x {world} GPUs",
+                "kernel": "per rank and step: k_partition_scatter_bulk<0,2,4> (repartition + NVLink bulk stores) | k_partition_scatter_bulk<1,2,4> + k_probe_inner_u1_seg (L2 pass + segment probe)",
+                "algorithmic_bytes_per_launch": BYTES_PER_PROBE_ROW * npb * world,
+                "nvlink": {"payload_gbs_per_direction_per_gpu": nvl, "reference_gbs": 770.0, "frac": nvl / 770.0,
+                           "note": "16 B per exchanged row; reference = measured peer-copy bandwidth per direction (B200_PROFILING.md)"}}
+
     # ---- e2e: host buffers through tg_join_probe_push / tg_join_next (N = 1 path; per rank at N > 1) ---------
     e2e = None
     if not args.skip_e2e:
         if world == 1:
             e2e = run_e2e(args, lib, abi, torch, dev, local, rank, world, bk, bv, pk, pv, barrier)
         else:
-            e2e = run_e2e_multi(args, torch, dist, dev, stream, xstream, rank, world, pk, pv, xch_p, bounds, join, barrier)
+            e2e = (run_e2e_mail(args, torch, dist, dev, stream, xstream, rank, world, pk, pv, xmail, join, barrier, dview) if xmail is not None else
+                   run_e2e_multi(args, torch, dist, dev, stream, xstream, rank, world, pk, pv, xch_p, bounds, join, barrier))
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample on the box's host cores ------------------------------
     cpu = None
@@ -436,12 +510,16 @@ def run_gpu(args):
             "metric": "hash-join probe rows/sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64", "data": "synthetic",
-            "config": {"workload": f"hash join {npb}x{nb} int64 keys per GPU, 8-byte payload, 100% match, output 4 columns (BASELINE configs[1])",
+            "config": {"workload": (f"hash join {npb}x{nb} int64 keys, 8-byte payload, 100% match, output 4 columns (BASELINE configs[1])" if world == 1 else
+                                    f"partitioned hash join {npb * world}x{nb * world} int64 keys over {world} GPUs ({npb}x{nb} per GPU, keys uniform over the global key set), "
+                                    f"8-byte payload, 100% match, output 4 columns, key-hash exchange over NVLink every step (BASELINE configs[4] / 8 per GPU" + ("" if world != 8 else " = the 1Bx100M join") + ")"),
                        "l2": "inputs larger than L2 (1.6 GB probe columns + 3.2 GB output + %.0f MB table per step vs 126 MB L2)" % (bstats.table_slots * 16 / 1e6),
                        "table": {"slots": bstats.table_slots, "mode": bstats.table_mode, "distinct_keys": bstats.distinct_keys, "build_ms": bstats.build_ms},
-                       "exchange": "none" if world == 1 else {"cf": "count-free: k_partition_scatter_bulk appends to this rank's fixed-capacity region on every peer over NVLink (tg_partition_exchange_cf), one all-gather of the counts per step, segmented probe (tg_join_probe_dev_seg)",
+                       "exchange": "none" if world == 1 else {"mail": f"MailboxExchange ({mail_choice}): k_partition_scatter_bulk appends to this rank's fixed-capacity region on every peer with bulk stores over NVLink (tg_partition_exchange_cf_ex), counts and buffer-reuse ACKs through device mailboxes (tg_mail_signal / tg_mail_wait): no NCCL, no copy engine, no host wait in a step; exchange stream one step ahead of the probe stream; segmented probe (tg_join_probe_dev_seg)",
+                                                                    "cf": "count-free: k_partition_scatter_bulk appends to this rank's fixed-capacity region on every peer over NVLink (tg_partition_exchange_cf), one all-gather of the counts per step, segmented probe (tg_join_probe_dev_seg)",
                                                                     "p2p": "k_partition_scatter storing into peer receive buffers over NVLink (tg_partition_exchange), counts all-gathered through the host",
-                                                                    "nccl": "tg_partition_by_key + NCCL all_to_all_single per column"}[args.exchange]},
+                                                                    "nccl": "tg_partition_by_key + NCCL all_to_all_single per column"}["mail" if xmail is not None else args.exchange],
+                       "exchange_calibration_ms": mail_timings or None},
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
         }
         if roof:
@@ -451,6 +529,8 @@ def run_gpu(args):
         print(json.dumps(line))
     join.close()
     if world > 1:
+        if xmail is not None:
+            xmail.close()
         xch_b.close()
         for x in xch_p:
             x.close()
@@ -606,18 +686,79 @@ def run_e2e_multi(args, torch, dist, dev, stream, xstream, rank, world, pk, pv, 
             "timing": "host wall clock, max over ranks, device synchronised on both sides"}
 
 
+def run_e2e_mail(args, torch, dist, dev, stream, xstream, rank, world, pk, pv, xm, join, barrier, dview):
+    """N > 1 end to end through the SAME exchange the device-resident number uses: every rank's probe shard starts in pinned
+    HOST memory; a step = H2D of the shard (exchange stream), MailboxExchange.send, segmented probe, D2H of the joined
+    columns into pinned host memory.  The exchange stream works on step k+1 (H2D + NVLink) while the probe stream
+    finishes step k (probe + D2H): two device input sets."""
+    npb = pk.numel()
+    hk = torch.empty(npb, dtype=torch.int64, pin_memory=True); hk.copy_(pk)
+    hv = torch.empty(npb, dtype=torch.int64, pin_memory=True); hv.copy_(pv)
+    cap_out = int(npb * 1.06) + 65536
+    hout = [torch.empty(cap_out, dtype=torch.int64, pin_memory=True) for _ in range(4)]
+    dk = [torch.empty(npb, dtype=torch.int64, device=dev) for _ in range(2)]
+    dv = [torch.empty(npb, dtype=torch.int64, device=dev) for _ in range(2)]
+    probed = [None, None]
+
+    def enqueue_send(i):
+        with torch.cuda.stream(xstream):
+            if probed[i % 2] is not None:
+                xstream.wait_event(probed[i % 2])     # (the scatter of step i-2 read this input set on xstream itself; nothing else reads it)
+            dk[i % 2].copy_(hk, non_blocking=True); dv[i % 2].copy_(hv, non_blocking=True)
+            xm.send(dk[i % 2], [dk[i % 2], dv[i % 2]])
+
+    def one_pass(steps):
+        total = 0
+        enqueue_send(0)
+        for i in range(steps):
+            if i + 1 < steps:
+                enqueue_send(i + 1)
+            with torch.cuda.stream(stream):
+                cols_in, seg_cnt, cap, s_, ep = xm.recv(stream)
+                rows, cols, _ = join.probe_segments(cols_in, seg_cnt, cap, sync=True)
+                xm.release(stream, s_, ep)
+                for c, p in enumerate(cols):
+                    hout[c][:rows].copy_(dview(p, rows), non_blocking=True)
+                ev = torch.cuda.Event(); ev.record(stream); probed[i % 2] = ev
+            stream.synchronize()       # the consumer owns the host buffers before the next step overwrites them
+            total = rows
+        return total
+
+    steps = max(2, args.steps // 2)
+    rows = one_pass(2)
+    tot = torch.tensor([rows], dtype=torch.int64, device=dev); dist.all_reduce(tot)
+    assert int(tot.item()) == npb * world
+    barrier()
+    t0 = time.perf_counter()
+    one_pass(steps)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    xm.check()
+    sec_step = float(tt.item()) / steps
+    return {"value": npb * world / sec_step, "unit": "rows/s", "h2d_bytes_per_step": 16 * npb * world, "d2h_bytes_per_step": 32 * npb * world,
+            "ms_per_step": sec_step * 1e3, "steps": steps,
+            "path": "per rank: pinned host shard -> H2D -> MailboxExchange (the exchange `value` times) -> tg_join_probe_dev_seg -> D2H of the 4 joined columns into pinned host memory; exchange stream one step ahead",
+            "timing": "host wall clock, max over ranks, device synchronised on both sides"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--build-rows", type=int, default=10_000_000)
-    ap.add_argument("--probe-rows", type=int, default=100_000_000)
+    ap.add_argument("--build-rows", type=int, default=None, help="per GPU; default 10M at N=1 (configs[1]), 12.5M at N>1 (configs[4] / 8)")
+    ap.add_argument("--probe-rows", type=int, default=None, help="per GPU; default 100M at N=1, 125M at N>1")
     ap.add_argument("--cpu-sample-rows", type=int, default=8_000_000)
     ap.add_argument("--ref-sample-rows", type=int, default=8_000_000)
     ap.add_argument("--e2e-chunk-rows", type=int, default=4 << 20)
-    ap.add_argument("--exchange", default="cf", choices=["cf", "p2p", "nccl"], help="N>1 probe-side exchange: cf = count-free peer stores + segmented probe (no host round trip), p2p = counted peer stores, nccl = local scatter + all_to_all")
+    ap.add_argument("--exchange", default="mail", choices=["mail", "mail-dma", "auto", "cf", "p2p", "nccl"],
+                    help="N>1 probe-side exchange: mail = count-free peer bulk stores + device mailboxes (no NCCL / host in a step); mail-dma = same, copy engines "
+                         "move the regions; auto = time mail / mail (2 scatter CTAs per SM) / mail-dma untimed and keep the fastest; cf = round-1 count-free exchange "
+                         "(NCCL all-gather per step); p2p = counted peer stores; nccl = local scatter + all_to_all")
+    ap.add_argument("--scatter-ctas", type=int, default=0, help="N>1, --exchange mail: cap on the exchange kernel's CTAs per SM (0 = as many as fit)")
     ap.add_argument("--overlap", type=int, default=2, help="N>1, --exchange cf: 1: run the exchange of step k+1 on a second stream under the probe of step k; 2: additionally a transfer stream, so regroup / NVLink copy / probe work on three consecutive steps")
     ap.add_argument("--dma", type=int, default=1, help="N>1, --exchange cf: regroup locally, let copy engines move the regions over NVLink")
     ap.add_argument("--xchunks", type=int, default=1, help="N>1: pieces the probe side is exchanged in (overlap with the probe kernel)")

@@ -391,6 +391,29 @@ int tg_partition_exchange_cf(int device, const int64_t* key_dev, int64_t rows, i
                              const void* const* src_cols_dev, void* const* recv_cols_peer, int64_t region_base,
                              int64_t region_cap, int64_t* sent_rows_dev, uint64_t* overflow_dev, void* stream);
 
+/* tg_partition_exchange_cf with a cap on the scatter kernel's CTAs per SM (0 = as many as fit).  When the exchange
+ * is NVLink-bound a few CTAs per SM already saturate the links, and the probe kernel of the previous step — running
+ * next to it on another stream — keeps the SMs' L1 (the bulk-store scatter holds 49 KB of shared memory per CTA).   */
+int tg_partition_exchange_cf_ex(int device, const int64_t* key_dev, int64_t rows, int32_t nparts, int32_t ncols,
+                                const void* const* src_cols_dev, void* const* recv_cols_peer, int64_t region_base,
+                                int64_t region_cap, int64_t* sent_rows_dev, uint64_t* overflow_dev, int32_t ctas_per_sm,
+                                void* stream);
+
+/* Cross-GPU mailboxes — the synchronisation of the count-free exchange without NCCL and without the host: one 8-byte
+ * word per (sender) in a device buffer of the RECEIVER that every sender has mapped with tg_ipc_open.
+ *   tg_mail_signal: after everything already enqueued on `stream` (the scatter kernel whose peer stores it publishes),
+ *                   store  epoch << 40 | values_dev[p]  into targets->slot[p] for every p (values_dev NULL: 0).
+ *   tg_mail_wait  : block `stream` (a spinning 32-thread kernel, the host never waits) until every one of the n words at
+ *                   mail_dev carries an epoch >= `epoch`; the low 40 bits go to values_out_dev[p] (e.g. the fill count of
+ *                   sender p's region = tg_join_probe_dev_seg's seg_cnt_dev).  A sender that stays silent for
+ *                   `timeout_ms` (0 = 10 s) raises *error_flag_dev = 1 + p and the wait ends: the GPU is never hung.
+ * The MPP analogue: the ExchangeReceiver waiting for every sender's stream end (the reference does it over gRPC).   */
+#define TG_MAIL_MAX_PEERS 16
+typedef struct tg_mail_targets { int32_t n, pad; uint64_t* slot[TG_MAIL_MAX_PEERS]; } tg_mail_targets;
+int tg_mail_signal(int device, const tg_mail_targets* targets, const int64_t* values_dev, int64_t epoch, void* stream);
+int tg_mail_wait(int device, const uint64_t* mail_dev, int32_t n, int64_t epoch, int64_t* values_out_dev,
+                 uint64_t* error_flag_dev, int64_t timeout_ms, void* stream);
+
 /* count rows per destination (first half of the exchange: counts are all-gathered by the host) */
 int tg_partition_count(int device, const int64_t* key_dev, int64_t rows, int32_t nparts,
                        int64_t* part_counts_dev, void* stream);

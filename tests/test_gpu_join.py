@@ -311,6 +311,83 @@ def test_concurrent_push_and_next_wait_and_rewind():
     lib.tg_join_close(h)
 
 
+def test_close_during_next_wait_and_double_close():
+    # exec.Executor: "Close may be called ... with Next() at the same time" (executor.go:65).  A consumer parked in
+    # tg_join_next_wait must come back with TG_ERR_CANCELLED when another thread closes the handle; a second close and any
+    # call made with the stale handle afterwards must be harmless (the shell outlives the close, csrc/join.cu).
+    import threading
+    import time
+    from tidb_b200.chunk import MutChunk
+    lib = abi.load_lib()
+    build, probe = _config1(50_000, 200_000)
+    plan = JoinPlan(abi.JOIN_INNER, [INT_NN, INT_NN], [INT_NN, INT_NN], [0], [0])
+    for _round in range(3):
+        desc, keep = plan.to_struct()
+        h = C.c_void_p()
+        abi.check(lib.tg_join_open(C.byref(desc), C.byref(h)))
+        bs = build.to_struct()
+        abi.check(lib.tg_join_build_push(h, C.byref(bs)))
+        abi.check(lib.tg_join_build_finish(h))
+        rcs = []
+
+        def consumer():
+            out = MutChunk([8, 8, 8, 8], 1 << 16)
+            n = C.c_int64(0)
+            while True:   # nothing was pushed and probe_finish is never called: parks on the result queue
+                rc = lib.tg_join_next_wait(h, C.byref(out.struct), C.c_int64(1 << 16), C.byref(n))
+                if rc != abi.TG_OK or n.value == 0:
+                    rcs.append(rc)
+                    return
+
+        th = threading.Thread(target=consumer)
+        th.start()
+        time.sleep(0.05 * (_round + 1))
+        assert lib.tg_join_close(h) == abi.TG_OK
+        th.join(timeout=10)
+        assert not th.is_alive(), "tg_join_next_wait did not return after tg_join_close"
+        assert rcs == [abi.TG_ERR_CANCELLED]
+        assert lib.tg_join_close(h) == abi.TG_OK                      # idempotent
+        ps = probe.to_struct()
+        assert lib.tg_join_probe_push(h, C.byref(ps)) == abi.TG_ERR_CANCELLED
+        st = abi.TgJoinStats()
+        assert lib.tg_join_get_stats(h, C.byref(st)) == abi.TG_ERR_CANCELLED
+
+
+def test_close_while_pusher_is_probing():
+    # close from a second thread while tg_join_probe_push is inside a probe: close waits for the push, later pushes see
+    # TG_ERR_CANCELLED; the pusher never touches freed memory
+    import threading
+    lib = abi.load_lib()
+    build, probe = _config1(100_000, 2_000_000)
+    plan = JoinPlan(abi.JOIN_INNER, [INT_NN, INT_NN], [INT_NN, INT_NN], [0], [0])
+    desc, keep = plan.to_struct()
+    h = C.c_void_p()
+    abi.check(lib.tg_join_open(C.byref(desc), C.byref(h)))
+    bs = build.to_struct()
+    abi.check(lib.tg_join_build_push(h, C.byref(bs)))
+    abi.check(lib.tg_join_build_finish(h))
+    chunks = probe.split(1 << 16)
+    seen = []
+
+    def pusher():
+        for c in chunks * 4:
+            cs = c.to_struct()
+            rc = lib.tg_join_probe_push(h, C.byref(cs))
+            if rc != abi.TG_OK:
+                seen.append(rc)
+                return
+        seen.append(abi.TG_OK)
+
+    th = threading.Thread(target=pusher)
+    th.start()
+    import time
+    time.sleep(0.02)
+    assert lib.tg_join_close(h) == abi.TG_OK
+    th.join(timeout=30)
+    assert not th.is_alive()
+    assert seen and seen[0] in (abi.TG_ERR_CANCELLED, abi.TG_OK)
+
+
 def test_probe_device_segments_matches_dense_probe(monkeypatch):
     # the shape a count-free exchange delivers: `nseg` fixed-capacity regions, each valid for its first seg_cnt[s] rows.
     # The segmented device probe must return exactly what the dense device probe returns for the concatenated valid rows,

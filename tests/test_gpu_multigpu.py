@@ -1,0 +1,58 @@
+"""The N > 1 product path on real GPUs (needs >= 2 devices; `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multigpu.py -m gpu`):
+MailboxExchange (bulk stores into the peers over NVLink + device mailboxes) feeding tg_join_probe_dev_seg, several
+pipelined steps, both transports; the union of the ranks' outputs must equal the oracle's join of the global inputs as
+sorted row multisets (checkChunksEqual, inner_join_probe_test.go:137).  Overflow of a receive region and a silent sender
+must surface as errors on every rank."""
+import os
+import socket
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from nested_loop import columns_sorted
+from tidb_b200 import abi
+from tidb_b200.chunk import Chunk, Column
+from tidb_b200.plan import FieldType, JoinPlan
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+@pytest.mark.parametrize("dma", [0, 1])
+def test_mailbox_exchange_two_ranks_vs_oracle(dma):
+    lib = abi.load_lib()
+    if lib.tg_device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import mgpu_worker as W
+    world, nb, npr, steps = 2, 60_000, 300_000, 4
+    with tempfile.TemporaryDirectory() as td:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+               "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "mgpu_worker.py"), "--out", td,
+               "--build-rows", str(nb), "--probe-rows", str(npr), "--steps", str(steps), "--dma", str(dma)]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+        res = [np.load(os.path.join(td, f"rank{k}.npz")) for k in range(world)]
+    INT = FieldType(abi.TYPE_LONGLONG, abi.FLAG_NOT_NULL)
+    plan = JoinPlan(abi.JOIN_INNER, [INT, INT], [INT, INT], [0], [0], build_is_right=True)
+    shards = [W.gen(k, world, nb, npr, 0) for k in range(world)]
+    build = Chunk([Column(np.concatenate([s[0] for s in shards])), Column(np.concatenate([s[1] for s in shards]))])
+    for s_ in range(steps):
+        ps = [W.gen(k, world, nb, npr, s_) for k in range(world)]
+        probe = Chunk([Column(np.concatenate([p[2] for p in ps])), Column(np.concatenate([p[3] for p in ps]))])
+        n, ocols = O.OracleJoin(plan, 4).run(build.split(4096), probe.split(4096))
+        got = [np.concatenate([res[k][f"s{s_}c{c}"] for k in range(world)]) for c in range(4)]
+        assert len(got[0]) == n, (s_, len(got[0]), n)
+        assert np.array_equal(columns_sorted(ocols), columns_sorted([(g, np.zeros(len(g), dtype=bool)) for g in got])), f"step {s_}"
+    for k in range(world):
+        assert int(res[k]["overflow_detected"][0]) == 1, "a receive-region overflow must be reported on every rank"
+        assert int(res[k]["timeout_detected"][0]) == 1, "a silent sender must end the wait with an error, not a hang"

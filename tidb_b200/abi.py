@@ -79,6 +79,11 @@ class TgJoinStats(C.Structure):
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 
 
+class TgMailTargets(C.Structure):
+    """tg_mail_targets: where this rank's mailbox word lives on every peer (tg_mail_signal)"""
+    _fields_ = [("n", C.c_int32), ("pad", C.c_int32), ("slot", C.c_uint64 * 16)]
+
+
 class TgAggFunc(C.Structure):
     _fields_ = [("name", C.c_int32), ("mode", C.c_int32), ("arg_col", C.c_int32),
                 ("arg_type", C.c_int32), ("arg_flag", C.c_uint32), ("arg_col2", C.c_int32)]
@@ -112,7 +117,8 @@ EXPORTED_SYMBOLS = [
     "tg_agg_next", "tg_agg_close", "tg_agg_result_dev", "tg_agg_get_stats",
     "tg_vec_compare_int", "tg_vec_compare_real", "tg_vec_arith_int", "tg_vec_arith_real",
     "tg_vec_filter",
-    "tg_partition_by_key", "tg_partition_of_key", "tg_partition_exchange", "tg_partition_exchange_cf", "tg_partition_count",
+    "tg_partition_by_key", "tg_partition_of_key", "tg_partition_exchange", "tg_partition_exchange_cf", "tg_partition_exchange_cf_ex", "tg_partition_count",
+    "tg_mail_signal", "tg_mail_wait",
     "tg_ipc_export", "tg_ipc_open", "tg_ipc_close",
 ]
 

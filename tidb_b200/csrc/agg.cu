@@ -455,9 +455,16 @@ struct AggHostStage {
 
 using namespace tg;
 
+struct AggImpl;
+
+// shell + implementation, like tg_join (join.cu): close frees the implementation, the shell stays readable
 struct tg_agg {
   std::mutex mu;
   std::atomic<bool> closed{false};
+  AggImpl* impl = nullptr;
+};
+
+struct AggImpl {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -496,13 +503,13 @@ struct tg_agg {
 
 namespace tg {
 
-static int agrid(const tg_agg* a, int64_t n, int block = 256, int per_sm = 8) {
+static int agrid(const AggImpl* a, int64_t n, int block = 256, int per_sm = 8) {
   int64_t need = (n + block - 1) / block, cap = (int64_t)a->nsm * per_sm;
   if (need < 1) need = 1;
   return (int)(need < cap ? need : cap);
 }
 
-static int agg_setup(tg_agg* a, const tg_agg_desc* d) {
+static int agg_setup(AggImpl* a, const tg_agg_desc* d) {
   if (!d) return fail(TG_ERR_INVALID, "desc is NULL");
   if (d->n_cols <= 0 || d->n_cols > TG_MAX_COLS) return fail(TG_ERR_UNSUPPORTED, "child schema must have 1..16 columns");
   a->ncols = d->n_cols;
@@ -582,7 +589,7 @@ static int agg_setup(tg_agg* a, const tg_agg_desc* d) {
   return TG_OK;
 }
 
-static void layout_table(tg_agg* a, uint8_t* mem, unsigned long long nslots, AggTable& t) {
+static void layout_table(AggImpl* a, uint8_t* mem, unsigned long long nslots, AggTable& t) {
   size_t n = (size_t)nslots + 2;
   t.nslots = nslots;
   t.keys = reinterpret_cast<long long*>(mem);
@@ -590,7 +597,7 @@ static void layout_table(tg_agg* a, uint8_t* mem, unsigned long long nslots, Agg
   for (int s = 0; s < a->nstates; s++) t.state[s] = reinterpret_cast<unsigned long long*>(mem + n * 8 * (2 + s));
 }
 
-static int alloc_table(tg_agg* a, unsigned long long nslots, DevBuf& mem, AggTable& t) {
+static int alloc_table(AggImpl* a, unsigned long long nslots, DevBuf& mem, AggTable& t) {
   size_t n = (size_t)nslots + 2;
   TG_TRY(mem.ensure(a->device, n * 8 * (2 + a->nstates)));
   layout_table(a, mem.as<uint8_t>(), nslots, t);
@@ -599,7 +606,7 @@ static int alloc_table(tg_agg* a, unsigned long long nslots, DevBuf& mem, AggTab
   return TG_OK;
 }
 
-static int grow_table(tg_agg* a, unsigned long long want_slots) {
+static int grow_table(AggImpl* a, unsigned long long want_slots) {
   std::unique_ptr<DevBuf> nm(new DevBuf());
   AggTable nt{};
   TG_TRY(alloc_table(a, want_slots, *nm, nt));
@@ -619,7 +626,7 @@ __global__ void k_mark_range(uint32_t* bits, int64_t lo, int64_t hi) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < hi; i += stride) atomicOr(&bits[i >> 5], 1u << (i & 31));
 }
-static int mark_range_deferred(tg_agg* a, int64_t lo, int64_t hi) {
+static int mark_range_deferred(AggImpl* a, int64_t lo, int64_t hi) {
   // whole 32-bit words with memset, ragged edges with a tiny kernel
   int64_t wlo = (lo + 31) / 32, whi = hi / 32;
   uint32_t* bits = a->deferred.as<uint32_t>();
@@ -632,7 +639,7 @@ static int mark_range_deferred(tg_agg* a, int64_t lo, int64_t hi) {
 }
 
 // rows [lo, hi): CTA-local partial aggregation, then merge of the partial results into the global table
-static int local_partial_pass(tg_agg* a, const GroupKey& gk, const DevCols& cols, int64_t lo, int64_t hi, unsigned long long* sc) {
+static int local_partial_pass(AggImpl* a, const GroupKey& gk, const DevCols& cols, int64_t lo, int64_t hi, unsigned long long* sc) {
   int local_slots = 1024;   // measured best on B200 (tools/bench_ops.py): bigger tables lose more to occupancy than they gain
   if (const char* e = getenv("TG_AGG_LOCAL_SLOTS")) { int v = atoi(e); if (v == 512 || v == 1024 || v == 2048 || v == 4096) local_slots = v; }
   size_t smem_per_cta = (size_t)(local_slots + 2) * 8 * (2 + a->nstates);
@@ -685,7 +692,7 @@ static int local_partial_pass(tg_agg* a, const GroupKey& gk, const DevCols& cols
 }
 
 // aggregate n device-resident rows
-static int update_device(tg_agg* a, const DevCols& cols, int64_t n) {
+static int update_device(AggImpl* a, const DevCols& cols, int64_t n) {
   if (n == 0) return TG_OK;
   a->stats.input_rows += n;
   TG_TRY(a->scalars.ensure(a->device, 64));
@@ -776,7 +783,7 @@ static int update_device(tg_agg* a, const DevCols& cols, int64_t n) {
 
 static int64_t alogical_rows(const tg_chunk* c) { return c->sel ? c->nsel : (c->ncols > 0 ? c->cols[0].length : 0); }
 
-static int avalidate(const tg_agg* a, const tg_chunk* chk) {
+static int avalidate(const AggImpl* a, const tg_chunk* chk) {
   if (!chk || chk->ncols != a->ncols) return fail(TG_ERR_INVALID, "chunk column count does not match the child schema");
   int64_t phys = chk->cols[0].length;
   for (int c = 0; c < a->ncols; c++) {
@@ -787,7 +794,7 @@ static int avalidate(const tg_agg* a, const tg_chunk* chk) {
   return TG_OK;
 }
 
-static int astage_append(tg_agg* a, const tg_chunk* chk) {
+static int astage_append(AggImpl* a, const tg_chunk* chk) {
   AggHostStage& st = a->stage;
   int64_t n = alogical_rows(chk);
   if (n == 0) return TG_OK;
@@ -820,7 +827,7 @@ static int astage_append(tg_agg* a, const tg_chunk* chk) {
   return TG_OK;
 }
 
-static int aflush(tg_agg* a) {
+static int aflush(AggImpl* a) {
   AggHostStage& st = a->stage;
   if (st.rows == 0) return TG_OK;
   DevCols v{};
@@ -847,7 +854,7 @@ static int aflush(tg_agg* a) {
   return rc;
 }
 
-static int afinalize(tg_agg* a) {
+static int afinalize(AggImpl* a) {
   TG_TRY(a->scalars.ensure(a->device, 64));
   unsigned long long* sc = a->scalars.as<unsigned long long>();
   int nf = a->spec.n;
@@ -909,22 +916,24 @@ static int afinalize(tg_agg* a) {
 
 }  // namespace tg
 
-#define TGA_LOCK(a)                                                            \
-  if (!(a)) return tg::fail(TG_ERR_INVALID, "handle is NULL");                 \
-  if ((a)->closed.load()) return tg::fail(TG_ERR_CANCELLED, "handle is closed"); \
-  std::lock_guard<std::mutex> lock__((a)->mu);                                 \
-  if ((a)->closed.load()) return tg::fail(TG_ERR_CANCELLED, "handle is closed"); \
-  tg::DeviceGuard guard__((a)->device);                                        \
+#define TGA_LOCK(h)                                                            \
+  if (!(h)) return tg::fail(TG_ERR_INVALID, "handle is NULL");                 \
+  if ((h)->closed.load()) return tg::fail(TG_ERR_CANCELLED, "handle is closed"); \
+  std::lock_guard<std::mutex> lock__((h)->mu);                                 \
+  if ((h)->closed.load() || !(h)->impl) return tg::fail(TG_ERR_CANCELLED, "handle is closed"); \
+  AggImpl* a = (h)->impl;                                                      \
+  tg::DeviceGuard guard__(a->device);                                          \
   if (!guard__.ok) return tg::fail(TG_ERR_CUDA, "cudaSetDevice failed (no usable CUDA device)")
 
 extern "C" {
 
-int tg_agg_supported(const tg_agg_desc* desc) { tg_agg tmp; return agg_setup(&tmp, desc); }
+int tg_agg_supported(const tg_agg_desc* desc) { AggImpl tmp; return agg_setup(&tmp, desc); }
 
 int tg_agg_open(const tg_agg_desc* desc, tg_agg** out) {
   if (!out) return fail(TG_ERR_INVALID, "out is NULL");
   *out = nullptr;
-  std::unique_ptr<tg_agg> a(new tg_agg());
+  std::unique_ptr<tg_agg> shell(new tg_agg());
+  std::unique_ptr<AggImpl> a(new AggImpl());
   TG_TRY(agg_setup(a.get(), desc));
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(TG_ERR_CUDA, "no CUDA device: the GPU hash aggregation has no CPU fallback"); }
@@ -941,12 +950,13 @@ int tg_agg_open(const tg_agg_desc* desc, tg_agg** out) {
     a->dcols.emplace_back(new DevBuf()); a->dnulls.emplace_back(new DevBuf());
   }
   a->stage.has_nulls.assign(a->ncols, 0);
-  *out = a.release();
+  shell->impl = a.release();
+  *out = shell.release();
   return TG_OK;
 }
 
-int tg_agg_push(tg_agg* a, const tg_chunk* chk) {
-  TGA_LOCK(a);
+int tg_agg_push(tg_agg* h, const tg_chunk* chk) {
+  TGA_LOCK(h);
   if (a->finished) return fail(TG_ERR_STATE, "push after finish");
   TG_TRY(avalidate(a, chk));
   TG_TRY(astage_append(a, chk));
@@ -954,8 +964,8 @@ int tg_agg_push(tg_agg* a, const tg_chunk* chk) {
   return TG_OK;
 }
 
-int tg_agg_push_dev(tg_agg* a, const tg_chunk* chk) {
-  TGA_LOCK(a);
+int tg_agg_push_dev(tg_agg* h, const tg_chunk* chk) {
+  TGA_LOCK(h);
   if (a->finished) return fail(TG_ERR_STATE, "push after finish");
   TG_TRY(avalidate(a, chk));
   if (chk->sel) return fail(TG_ERR_UNSUPPORTED, "device-resident chunks must not carry a sel vector");
@@ -969,8 +979,8 @@ int tg_agg_push_dev(tg_agg* a, const tg_chunk* chk) {
   return update_device(a, v, chk->cols[0].length);
 }
 
-int tg_agg_finish(tg_agg* a) {
-  TGA_LOCK(a);
+int tg_agg_finish(tg_agg* h) {
+  TGA_LOCK(h);
   if (a->finished) return TG_OK;
   TG_TRY(aflush(a));
   TG_TRY(afinalize(a));
@@ -978,8 +988,8 @@ int tg_agg_finish(tg_agg* a) {
   return TG_OK;
 }
 
-int tg_agg_next(tg_agg* a, tg_mut_chunk* out, int64_t max_rows, int64_t* nrows) {
-  TGA_LOCK(a);
+int tg_agg_next(tg_agg* h, tg_mut_chunk* out, int64_t max_rows, int64_t* nrows) {
+  TGA_LOCK(h);
   if (!out || !nrows) return fail(TG_ERR_INVALID, "out / nrows is NULL");
   *nrows = 0;
   if (!a->finished) return fail(TG_ERR_STATE, "next before finish (hash aggregation is a pipeline breaker)");
@@ -1008,8 +1018,8 @@ int tg_agg_next(tg_agg* a, tg_mut_chunk* out, int64_t max_rows, int64_t* nrows) 
   return TG_OK;
 }
 
-int tg_agg_result_dev(tg_agg* a, int64_t* out_rows, void** out_cols, void** out_nulls) {
-  TGA_LOCK(a);
+int tg_agg_result_dev(tg_agg* h, int64_t* out_rows, void** out_cols, void** out_nulls) {
+  TGA_LOCK(h);
   if (!a->finished) return fail(TG_ERR_STATE, "result before finish");
   if (out_rows) *out_rows = a->out_rows;
   for (int k = 0; k < a->spec.n; k++) {
@@ -1019,27 +1029,32 @@ int tg_agg_result_dev(tg_agg* a, int64_t* out_rows, void** out_cols, void** out_
   return TG_OK;
 }
 
-int tg_agg_get_stats(tg_agg* a, tg_agg_stats* out) {
-  TGA_LOCK(a);
+int tg_agg_get_stats(tg_agg* h, tg_agg_stats* out) {
+  TGA_LOCK(h);
   if (!out) return fail(TG_ERR_INVALID, "out is NULL");
   *out = a->stats;
   return TG_OK;
 }
 
-int tg_agg_close(tg_agg* a) {
-  if (!a) return TG_OK;
-  bool was = a->closed.exchange(true);
+int tg_agg_close(tg_agg* h) {
+  if (!h) return TG_OK;
+  bool was = h->closed.exchange(true);
   if (was) return TG_OK;
   {
-    std::lock_guard<std::mutex> lock(a->mu);
-    DeviceGuard g(a->device);
-    if (a->stream) cudaStreamSynchronize(a->stream);
-    if (a->ev0) cudaEventDestroy(a->ev0);
-    if (a->ev1) cudaEventDestroy(a->ev1);
-    if (a->own_stream && a->stream) cudaStreamDestroy(a->stream);
-    cudaGetLastError();
+    std::lock_guard<std::mutex> lock(h->mu);   // waits for an in-flight call; later calls see `closed`
+    AggImpl* a = h->impl;
+    h->impl = nullptr;
+    if (a) {
+      DeviceGuard g(a->device);
+      if (a->stream) cudaStreamSynchronize(a->stream);
+      if (a->ev0) cudaEventDestroy(a->ev0);
+      if (a->ev1) cudaEventDestroy(a->ev1);
+      if (a->own_stream && a->stream) cudaStreamDestroy(a->stream);
+      cudaGetLastError();
+      delete a;
+    }
   }
-  delete a;
+  bury_handle(h);
   return TG_OK;
 }
 

@@ -129,6 +129,20 @@ struct PinBuf {
   }
 };
 
+// ---- handle graveyard ------------------------------------------------------------------------------
+// Closed handle shells (tg_join / tg_agg: two mutexes, a flag and a null impl pointer) stay readable for callers that
+// raced with close; only the oldest is freed once more than kGraveyardDepth have accumulated, so memory stays bounded.
+constexpr size_t kGraveyardDepth = 4096;
+template <typename H>
+inline void bury_handle(H* h) {
+  static std::mutex mu;
+  static std::vector<H*> ring(kGraveyardDepth, nullptr);
+  static size_t pos = 0;
+  H* old = nullptr;
+  { std::lock_guard<std::mutex> lk(mu); old = ring[pos]; ring[pos] = h; pos = (pos + 1) % kGraveyardDepth; }
+  delete old;
+}
+
 // ---- hashing --------------------------------------------------------------------------------------
 // The reference hashes the serialised key with FNV-1 64 (join/row_table_builder.go:103).  The hash only selects a
 // bucket / partition, never a result, so the GPU is free to use something cheaper.  These kernels turned out to be

@@ -72,11 +72,25 @@ struct ResultBatch {
 
 using namespace tg;
 
+struct JoinImpl;
+
+// The C-ABI handle is a small SHELL that outlives tg_join_close: close frees the implementation (GPU buffers, streams,
+// staging) but parks the shell in a bounded graveyard (common.cuh), so a caller that raced with close — parked in
+// tg_join_next_wait, blocked on `mu`, or about to enter with a pointer it read just before the close — finds a live
+// `closed` flag and gets TG_ERR_CANCELLED instead of touching freed memory (exec.Executor: "Close may be called ...
+// with Next() at the same time", executor.go:65).  A second close is a no-op.
 struct tg_join {
   std::mutex mu;                     // build / probe-input side (one pushing thread)
   std::mutex res_mu;                 // result queue (one pulling thread may run concurrently with the pusher, like the
   std::condition_variable res_cv;    //   reference's probe fetcher vs joinResultCh consumer, hash_join_v2.go:840 / :1176)
   std::atomic<bool> closed{false};
+  JoinImpl* impl = nullptr;          // guarded by mu + res_mu; nullptr once closed
+};
+
+struct JoinImpl {
+  std::mutex& res_mu;                // the shell's (see tg_join)
+  std::condition_variable& res_cv;
+  explicit JoinImpl(tg_join& shell) : res_mu(shell.res_mu), res_cv(shell.res_cv) {}
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t d2h_stream = nullptr; // tg_join_next copies results on its own stream: D2H overlaps the next H2D + probe
@@ -132,7 +146,7 @@ namespace tg {
 
 static int env_int(const char* name, int dflt) { const char* v = getenv(name); return (v && *v) ? atoi(v) : dflt; }
 
-static int grid_for(const tg_join* j, int64_t n, int block, int per_sm) {
+static int grid_for(const JoinImpl* j, int64_t n, int block, int per_sm) {
   int64_t need = (n + block - 1) / block;
   int64_t cap = (int64_t)j->nsm * per_sm;
   if (need < 1) need = 1;
@@ -179,7 +193,7 @@ static int check_filter(const Side& s, const tg_filter_item* items, int n, DevFi
   return TG_OK;
 }
 
-static int setup(tg_join* j, const tg_join_desc* d) {
+static int setup(JoinImpl* j, const tg_join_desc* d) {
   if (!d) return fail(TG_ERR_INVALID, "desc is NULL");
   j->join_type = d->join_type;
   j->build_is_right = d->build_is_right != 0;
@@ -315,7 +329,7 @@ static int stage_append(HostStage& st, const Side& s, const tg_chunk* chk) {
 }
 
 // staging → device column store (replaces its contents)
-static int stage_to_device(tg_join* j, HostStage& st, const Side& s, ColStore& cs) {
+static int stage_to_device(JoinImpl* j, HostStage& st, const Side& s, ColStore& cs) {
   cs.rows = st.rows;
   for (int c = 0; c < s.ncols; c++) {
     if (!s.needed[c]) continue;
@@ -333,7 +347,7 @@ static int stage_to_device(tg_join* j, HostStage& st, const Side& s, ColStore& c
 }
 
 // a whole (large) host chunk → device column store, straight from the caller's buffers
-static int chunk_to_device(tg_join* j, const tg_chunk* chk, const Side& s, ColStore& cs) {
+static int chunk_to_device(JoinImpl* j, const tg_chunk* chk, const Side& s, ColStore& cs) {
   int64_t n = chk->cols[0].length;
   cs.rows = n;
   for (int c = 0; c < s.ncols; c++) {
@@ -354,7 +368,7 @@ static int chunk_to_device(tg_join* j, const tg_chunk* chk, const Side& s, ColSt
 }
 
 // device chunk → device column store (device-to-device, appended)
-static int devchunk_append(tg_join* j, const tg_chunk* chk, const Side& s, ColStore& cs) {
+static int devchunk_append(JoinImpl* j, const tg_chunk* chk, const Side& s, ColStore& cs) {
   if (chk->sel) return fail(TG_ERR_UNSUPPORTED, "device-resident chunks must not carry a sel vector");
   int64_t n = chk->ncols ? chk->cols[0].length : 0;
   if (n == 0) return TG_OK;
@@ -395,7 +409,7 @@ static int devchunk_view(const tg_chunk* chk, const Side& s, DevCols& v, int64_t
 }
 
 // ---- build --------------------------------------------------------------------------------------------
-static int build_table(tg_join* j) {
+static int build_table(JoinImpl* j) {
   const Side& b = j->build;
   int64_t n = j->bcols.rows;
   j->stats.build_rows = n;
@@ -500,7 +514,7 @@ static int build_table(tg_join* j) {
 }
 
 // ---- output plumbing -------------------------------------------------------------------------------------
-static int ensure_result(tg_join* j, ResultBatch& rb, int64_t cap_rows, bool preserve, int64_t used_rows) {
+static int ensure_result(JoinImpl* j, ResultBatch& rb, int64_t cap_rows, bool preserve, int64_t used_rows) {
   if ((int)rb.cols.size() != j->n_out) {
     rb.cols.clear(); rb.bitmaps.clear();
     for (int i = 0; i < j->n_out; i++) { rb.cols.emplace_back(new DevBuf()); rb.bitmaps.emplace_back(new DevBuf()); }
@@ -514,7 +528,7 @@ static int ensure_result(tg_join* j, ResultBatch& rb, int64_t cap_rows, bool pre
 }
 
 // which output columns can carry NULLs for this probe batch
-static void out_nullable(const tg_join* j, const DevCols& pview, std::vector<char>& nullable) {
+static void out_nullable(const JoinImpl* j, const DevCols& pview, std::vector<char>& nullable) {
   nullable.assign(j->n_out, 0);
   bool probe_is_left = j->build_is_right;
   int n_l = j->n_lused;
@@ -528,7 +542,7 @@ static void out_nullable(const tg_join* j, const DevCols& pview, std::vector<cha
   }
 }
 
-static void fill_outspec_probe(const tg_join* j, OutCols& oc) {
+static void fill_outspec_probe(const JoinImpl* j, OutCols& oc) {
   bool probe_is_left = j->build_is_right;
   int n_l = j->n_lused;
   oc.n = j->n_out;
@@ -545,7 +559,7 @@ static void fill_outspec_probe(const tg_join* j, OutCols& oc) {
   }
 }
 
-static int scan_counts(tg_join* j, int64_t n, unsigned long long* total_out) {
+static int scan_counts(JoinImpl* j, int64_t n, unsigned long long* total_out) {
   int64_t nblocks = (n + TG_SCAN_BLOCK * TG_SCAN_ITEMS - 1) / (TG_SCAN_BLOCK * TG_SCAN_ITEMS);
   TG_TRY(j->tmp_sums.ensure(j->device, (size_t)(nblocks + 2) * 8));
   TG_TRY(j->tmp_off.ensure(j->device, (size_t)(n + 2) * 8));
@@ -560,7 +574,7 @@ static int scan_counts(tg_join* j, int64_t n, unsigned long long* total_out) {
 }
 
 // valid-byte streams → bitmaps for the nullable output columns
-static int finish_bitmaps(tg_join* j, ResultBatch& rb, const std::vector<char>& nullable) {
+static int finish_bitmaps(JoinImpl* j, ResultBatch& rb, const std::vector<char>& nullable) {
   for (int c = 0; c < j->n_out; c++) {
     if (!nullable[c]) { rb.bitmaps[c]->release(); continue; }
     TG_TRY(rb.bitmaps[c]->ensure(j->device, (size_t)((rb.rows + 7) / 8) + 16));
@@ -572,7 +586,7 @@ static int finish_bitmaps(tg_join* j, ResultBatch& rb, const std::vector<char>& 
   return TG_OK;
 }
 
-static bool fast_path_ok(const tg_join* j, const DevCols& pview) {
+static bool fast_path_ok(const JoinImpl* j, const DevCols& pview) {
   if (j->tv.mode != TABLE_U1 || j->probe_kind != PK_INNER || j->need_scan) return false;
   if (j->probe.filter.n || j->probe_key.kind != KEY_I64 || j->probe_key.reject_negative) return false;
   if (pview.nulls[j->probe.key_col]) return false;
@@ -605,7 +619,7 @@ static ProbeTuning probe_tuning() {
 
 // classify the output columns of the fused fast path by the register that feeds them; false = shape not covered by
 // the templated kernels (the CTA-tile kernel handles it)
-static bool build_fast_out(const tg_join* j, const OutCols& oc, const DevCols& pview, FastOut& fo) {
+static bool build_fast_out(const JoinImpl* j, const OutCols& oc, const DevCols& pview, FastOut& fo) {
   std::memset(&fo, 0, sizeof(fo));
   int pcol_of[TG_FAST_MAX_PCOLS];
   for (int c = 0; c < oc.n; c++) {
@@ -642,7 +656,7 @@ static int dispatch_shape(const FastOut& fo, A&&... a) {
 
 template <int NPC, int NKD, int NMD>
 struct LaunchWarp {
-  static int run(tg_join* j, const int64_t* pkey, int64_t n, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t, const SegSpec& seg) {
+  static int run(JoinImpl* j, const int64_t* pkey, int64_t n, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t, const SegSpec& seg) {
     constexpr int R = 4;
     static int resident = 0;   // CTAs of this instantiation one SM holds (register-bound, 3 on sm_100a)
     if (!resident) {
@@ -661,7 +675,7 @@ struct LaunchWarp {
 };
 template <int NPC, int NKD, int NMD>
 struct LaunchSeg {
-  static int run(tg_join* j, const int64_t* pkey, int64_t n, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t, const SegSpec& seg) {
+  static int run(JoinImpl* j, const int64_t* pkey, int64_t n, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t, const SegSpec& seg) {
     static int resident = 0;
     if (!resident) {
       int nb = 0;
@@ -687,7 +701,7 @@ struct LaunchSeg {
 };
 template <int NPC, int NKD, int NMD>
 struct LaunchTma {
-  static int run(tg_join* j, const int64_t* pkey, int64_t ntiles, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t) {
+  static int run(JoinImpl* j, const int64_t* pkey, int64_t ntiles, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t) {
     int grid = (int)std::min<int64_t>(ntiles, (int64_t)j->nsm * t.tma_ctas);
     if (t.stages >= 4) {
       size_t smem = (size_t)4 * (1 + NPC) * TG_PROBE_TILE * 8 + 4 * 8 + 16;
@@ -705,20 +719,20 @@ struct LaunchTma {
     return TG_OK;
   }
 };
-static int launch_probe_warp(tg_join* j, const int64_t* pkey, int64_t n, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t,
+static int launch_probe_warp(JoinImpl* j, const int64_t* pkey, int64_t n, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t,
                              const SegSpec& seg = SegSpec{nullptr, 0, 0, 0, nullptr}) {
   return dispatch_shape<LaunchWarp>(fo, j, pkey, n, fo, cur, t, seg);
 }
-static int launch_probe_seg(tg_join* j, const int64_t* pkey, int64_t n, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t, const SegSpec& seg) {
+static int launch_probe_seg(JoinImpl* j, const int64_t* pkey, int64_t n, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t, const SegSpec& seg) {
   return dispatch_shape<LaunchSeg>(fo, j, pkey, n, fo, cur, t, seg);
 }
-static int launch_probe_tma(tg_join* j, const int64_t* pkey, int64_t ntiles, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t) {
+static int launch_probe_tma(JoinImpl* j, const int64_t* pkey, int64_t ntiles, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t) {
   return dispatch_shape<LaunchTma>(fo, j, pkey, ntiles, fo, cur, t);
 }
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // probe `n` device-resident rows; results are appended to rb (rb.rows advanced)
-static int probe_device(tg_join* j, const DevCols& pview, int64_t n, ResultBatch& rb, bool sync_count, const SegSpec* in_seg = nullptr) {
+static int probe_device(JoinImpl* j, const DevCols& pview, int64_t n, ResultBatch& rb, bool sync_count, const SegSpec* in_seg = nullptr) {
   const Side& p = j->probe;
   j->stats.probe_rows += n;
   KeySpec ks = j->probe_key;
@@ -909,7 +923,7 @@ static int probe_device(tg_join* j, const DevCols& pview, int64_t n, ResultBatch
 }
 
 // ScanRowTable after the probe side is exhausted (hash_join_v2.go:877)
-static int scan_build_side(tg_join* j, ResultBatch& rb) {
+static int scan_build_side(JoinImpl* j, ResultBatch& rb) {
   const Side& b = j->build;
   int64_t n = j->bcols.rows;
   if (n == 0) { if ((int)rb.cols.size() != j->n_out) TG_TRY(ensure_result(j, rb, 8, false, 0)); return TG_OK; }
@@ -950,7 +964,7 @@ static int scan_build_side(tg_join* j, ResultBatch& rb) {
   return TG_OK;
 }
 
-static std::unique_ptr<ResultBatch> new_batch(tg_join* j) {
+static std::unique_ptr<ResultBatch> new_batch(JoinImpl* j) {
   std::lock_guard<std::mutex> lk(j->res_mu);
   if (!j->free_batches.empty()) {
     std::unique_ptr<ResultBatch> rb = std::move(j->free_batches.back());
@@ -961,13 +975,13 @@ static std::unique_ptr<ResultBatch> new_batch(tg_join* j) {
   return std::unique_ptr<ResultBatch>(new ResultBatch());
 }
 
-static void queue_result(tg_join* j, std::unique_ptr<ResultBatch> rb) {
+static void queue_result(JoinImpl* j, std::unique_ptr<ResultBatch> rb) {
   if (rb->rows <= 0) { std::lock_guard<std::mutex> lk(j->res_mu); j->free_batches.push_back(std::move(rb)); return; }
   { std::lock_guard<std::mutex> lk(j->res_mu); j->results.push_back(std::move(rb)); }
   j->res_cv.notify_all();
 }
 
-static int flush_probe_stage(tg_join* j) {
+static int flush_probe_stage(JoinImpl* j) {
   if (j->pstage.rows == 0) return TG_OK;
   TG_TRY(stage_to_device(j, j->pstage, j->probe, j->pcols_dev));
   std::unique_ptr<ResultBatch> rb = new_batch(j);
@@ -987,25 +1001,28 @@ static int flush_probe_stage(tg_join* j) {
 // ---------------------------------------------------------------------------------------------------
 // C entry points
 // ---------------------------------------------------------------------------------------------------
-#define TG_LOCK(j)                                                             \
-  if (!(j)) return tg::fail(TG_ERR_INVALID, "handle is NULL");                 \
-  if ((j)->closed.load()) return tg::fail(TG_ERR_CANCELLED, "handle is closed"); \
-  std::lock_guard<std::mutex> lock__((j)->mu);                                 \
-  if ((j)->closed.load()) return tg::fail(TG_ERR_CANCELLED, "handle is closed"); \
-  tg::DeviceGuard guard__((j)->device);                                        \
+#define TG_LOCK(h)                                                             \
+  if (!(h)) return tg::fail(TG_ERR_INVALID, "handle is NULL");                 \
+  if ((h)->closed.load()) return tg::fail(TG_ERR_CANCELLED, "handle is closed"); \
+  std::lock_guard<std::mutex> lock__((h)->mu);                                 \
+  if ((h)->closed.load() || !(h)->impl) return tg::fail(TG_ERR_CANCELLED, "handle is closed"); \
+  JoinImpl* j = (h)->impl;                                                     \
+  tg::DeviceGuard guard__(j->device);                                          \
   if (!guard__.ok) return tg::fail(TG_ERR_CUDA, "cudaSetDevice failed (no usable CUDA device)")
 
 extern "C" {
 
 int tg_join_supported(const tg_join_desc* desc) {
-  tg_join tmp;
+  tg_join shell;
+  JoinImpl tmp(shell);
   return setup(&tmp, desc);
 }
 
 int tg_join_open(const tg_join_desc* desc, tg_join** out) {
   if (!out) return fail(TG_ERR_INVALID, "out is NULL");
   *out = nullptr;
-  std::unique_ptr<tg_join> j(new tg_join());
+  std::unique_ptr<tg_join> shell(new tg_join());
+  std::unique_ptr<JoinImpl> j(new JoinImpl(*shell));
   TG_TRY(setup(j.get(), desc));
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(TG_ERR_CUDA, "no CUDA device: the GPU hash join has no CPU fallback"); }
@@ -1027,27 +1044,28 @@ int tg_join_open(const tg_join_desc* desc, tg_join** out) {
   }
   j->bstage.init(j->build.ncols); j->bcols.init(j->build.ncols);
   j->pstage.init(j->probe.ncols); j->pcols_dev.init(j->probe.ncols);
-  *out = j.release();
+  shell->impl = j.release();
+  *out = shell.release();
   return TG_OK;
 }
 
-int tg_join_build_push(tg_join* j, const tg_chunk* chk) {
-  TG_LOCK(j);
+int tg_join_build_push(tg_join* h, const tg_chunk* chk) {
+  TG_LOCK(h);
   if (j->built) return fail(TG_ERR_STATE, "build_push after build_finish");
   TG_TRY(validate_chunk(j->build, chk));
   return stage_append(j->bstage, j->build, chk);
 }
 
-int tg_join_build_push_dev(tg_join* j, const tg_chunk* chk) {
-  TG_LOCK(j);
+int tg_join_build_push_dev(tg_join* h, const tg_chunk* chk) {
+  TG_LOCK(h);
   if (j->built) return fail(TG_ERR_STATE, "build_push after build_finish");
   if (j->bstage.rows) return fail(TG_ERR_STATE, "host and device build pushes cannot be mixed");
   TG_TRY(validate_chunk(j->build, chk));
   return devchunk_append(j, chk, j->build, j->bcols);
 }
 
-int tg_join_build_finish(tg_join* j) {
-  TG_LOCK(j);
+int tg_join_build_finish(tg_join* h) {
+  TG_LOCK(h);
   if (j->built) return fail(TG_ERR_STATE, "build_finish called twice");
   if (j->bstage.rows) { TG_TRY(stage_to_device(j, j->bstage, j->build, j->bcols)); }
   int rc = build_table(j);
@@ -1056,8 +1074,8 @@ int tg_join_build_finish(tg_join* j) {
   return rc;
 }
 
-int tg_join_probe_push(tg_join* j, const tg_chunk* chk) {
-  TG_LOCK(j);
+int tg_join_probe_push(tg_join* h, const tg_chunk* chk) {
+  TG_LOCK(h);
   if (!j->built) return fail(TG_ERR_STATE, "probe_push before build_finish");
   if (j->probe_finished.load()) return fail(TG_ERR_STATE, "probe_push after probe_finish");
   TG_TRY(validate_chunk(j->probe, chk));
@@ -1081,8 +1099,8 @@ int tg_join_probe_push(tg_join* j, const tg_chunk* chk) {
   return TG_OK;
 }
 
-int tg_join_probe_finish(tg_join* j) {
-  TG_LOCK(j);
+int tg_join_probe_finish(tg_join* h) {
+  TG_LOCK(h);
   if (!j->built) return fail(TG_ERR_STATE, "probe_finish before build_finish");
   if (j->probe_finished.load()) return TG_OK;
   TG_TRY(flush_probe_stage(j));
@@ -1096,14 +1114,16 @@ int tg_join_probe_finish(tg_join* j) {
   return TG_OK;
 }
 
-static int join_next_impl(tg_join* j, tg_mut_chunk* out, int64_t max_rows, int64_t* nrows, bool wait) {
-  if (!j) return fail(TG_ERR_INVALID, "handle is NULL");
-  if (j->closed.load()) return fail(TG_ERR_CANCELLED, "handle is closed");
+static int join_next_impl(tg_join* h, tg_mut_chunk* out, int64_t max_rows, int64_t* nrows, bool wait) {
+  if (!h) return fail(TG_ERR_INVALID, "handle is NULL");
+  if (h->closed.load()) return fail(TG_ERR_CANCELLED, "handle is closed");
   if (!out || !nrows) return fail(TG_ERR_INVALID, "out / nrows is NULL");
   *nrows = 0;
+  std::unique_lock<std::mutex> lock__(h->res_mu);
+  if (h->closed.load() || !h->impl) return fail(TG_ERR_CANCELLED, "handle is closed");
+  JoinImpl* j = h->impl;
   if (out->ncols != j->n_out) return fail(TG_ERR_INVALID, "output chunk column count does not match the join schema");
   for (int c = 0; c < j->n_out; c++) if (out->cols[c].elem_len != j->out_elem[c]) return fail(TG_ERR_INVALID, "output column elem_len mismatch");
-  std::unique_lock<std::mutex> lock__(j->res_mu);
   tg::DeviceGuard guard__(j->device);
   if (!guard__.ok) return fail(TG_ERR_CUDA, "cudaSetDevice failed (no usable CUDA device)");
   for (;;) {
@@ -1114,8 +1134,8 @@ static int join_next_impl(tg_join* j, tg_mut_chunk* out, int64_t max_rows, int64
     }
     if (!j->results.empty()) break;
     if (!wait || j->probe_finished.load()) return TG_OK;   // 0 rows: EOF iff probe_finish was called, else "push more"
-    j->res_cv.wait(lock__);
-    if (j->closed.load()) return fail(TG_ERR_CANCELLED, "handle is closed");
+    h->res_cv.wait(lock__);
+    if (h->closed.load() || !h->impl) return fail(TG_ERR_CANCELLED, "handle is closed");
   }
   cudaStream_t cstream = j->d2h_stream;
   ResultBatch& rb = *j->results.front();
@@ -1179,8 +1199,8 @@ static int join_next_impl(tg_join* j, tg_mut_chunk* out, int64_t max_rows, int64
   return TG_OK;
 }
 
-int tg_join_probe_rewind(tg_join* j) {
-  TG_LOCK(j);
+int tg_join_probe_rewind(tg_join* h) {
+  TG_LOCK(h);
   if (!j->built) return fail(TG_ERR_STATE, "rewind before build_finish");
   if (j->need_scan) return fail(TG_ERR_UNSUPPORTED, "joins that scan the build side afterwards cannot be re-probed (used flags accumulate)");
   j->pstage.reset();
@@ -1191,11 +1211,11 @@ int tg_join_probe_rewind(tg_join* j) {
   return TG_OK;
 }
 
-int tg_join_next(tg_join* j, tg_mut_chunk* out, int64_t max_rows, int64_t* nrows) { return join_next_impl(j, out, max_rows, nrows, false); }
-int tg_join_next_wait(tg_join* j, tg_mut_chunk* out, int64_t max_rows, int64_t* nrows) { return join_next_impl(j, out, max_rows, nrows, true); }
+int tg_join_next(tg_join* h, tg_mut_chunk* out, int64_t max_rows, int64_t* nrows) { return join_next_impl(h, out, max_rows, nrows, false); }
+int tg_join_next_wait(tg_join* h, tg_mut_chunk* out, int64_t max_rows, int64_t* nrows) { return join_next_impl(h, out, max_rows, nrows, true); }
 
-int tg_join_probe_dev(tg_join* j, const tg_chunk* dev_chk, int64_t* out_rows, void** out_cols, void** out_nulls) {
-  TG_LOCK(j);
+int tg_join_probe_dev(tg_join* h, const tg_chunk* dev_chk, int64_t* out_rows, void** out_cols, void** out_nulls) {
+  TG_LOCK(h);
   if (!j->built) return fail(TG_ERR_STATE, "probe before build_finish");
   DevCols pview; int64_t n = 0;
   TG_TRY(devchunk_view(dev_chk, j->probe, pview, &n));
@@ -1217,9 +1237,9 @@ int tg_join_probe_dev(tg_join* j, const tg_chunk* dev_chk, int64_t* out_rows, vo
   return TG_OK;
 }
 
-int tg_join_probe_dev_seg(tg_join* j, const tg_chunk* dev_chk, const int64_t* seg_cnt_dev, int32_t nseg, int64_t seg_cap,
+int tg_join_probe_dev_seg(tg_join* h, const tg_chunk* dev_chk, const int64_t* seg_cnt_dev, int32_t nseg, int64_t seg_cap,
                           int64_t* out_rows, void** out_cols, void** out_nulls) {
-  TG_LOCK(j);
+  TG_LOCK(h);
   if (!j->built) return fail(TG_ERR_STATE, "probe before build_finish");
   if (!seg_cnt_dev || nseg < 1 || seg_cap < 1024 || seg_cap % 1024) return fail(TG_ERR_INVALID, "seg_cnt_dev required; seg_cap must be a positive multiple of 1024");
   DevCols pview; int64_t n = 0;
@@ -1245,8 +1265,8 @@ int tg_join_probe_dev_seg(tg_join* j, const tg_chunk* dev_chk, const int64_t* se
   return TG_OK;
 }
 
-int tg_join_get_stats(tg_join* j, tg_join_stats* out) {
-  TG_LOCK(j);
+int tg_join_get_stats(tg_join* h, tg_join_stats* out) {
+  TG_LOCK(h);
   if (!out) return fail(TG_ERR_INVALID, "out is NULL");
   TG_CUDA(cudaStreamSynchronize(j->stream));
   *out = j->stats;
@@ -1254,27 +1274,35 @@ int tg_join_get_stats(tg_join* j, tg_join_stats* out) {
   return TG_OK;
 }
 
-int tg_join_close(tg_join* j) {
-  if (!j) return TG_OK;
-  bool was = j->closed.exchange(true);
+int tg_join_close(tg_join* h) {
+  if (!h) return TG_OK;
+  bool was = h->closed.exchange(true);
   if (was) return TG_OK;
-  j->res_cv.notify_all();
+  // wake a consumer parked in tg_join_next_wait; notifying under res_mu closes the window between its predicate check
+  // and its wait (it holds res_mu across both)
+  { std::lock_guard<std::mutex> rlock(h->res_mu); h->res_cv.notify_all(); }
   {
     // waits for an in-flight push and an in-flight next; later calls see `closed`
-    std::lock_guard<std::mutex> lock(j->mu);
-    std::lock_guard<std::mutex> rlock(j->res_mu);
-    DeviceGuard g(j->device);
-    if (j->stream) cudaStreamSynchronize(j->stream);
-    if (j->d2h_stream) { cudaStreamSynchronize(j->d2h_stream); cudaStreamDestroy(j->d2h_stream); }
-    j->results.clear();
-    j->free_batches.clear();
-    j->dev_result.reset();
-    if (j->ev0) cudaEventDestroy(j->ev0);
-    if (j->ev1) cudaEventDestroy(j->ev1);
-    if (j->own_stream && j->stream) cudaStreamDestroy(j->stream);
-    cudaGetLastError();
+    std::lock_guard<std::mutex> lock(h->mu);
+    std::lock_guard<std::mutex> rlock(h->res_mu);
+    JoinImpl* j = h->impl;
+    h->impl = nullptr;
+    if (j) {
+      DeviceGuard g(j->device);
+      if (j->stream) cudaStreamSynchronize(j->stream);
+      if (j->d2h_stream) { cudaStreamSynchronize(j->d2h_stream); cudaStreamDestroy(j->d2h_stream); }
+      j->results.clear();
+      j->free_batches.clear();
+      j->dev_result.reset();
+      if (j->ev0) cudaEventDestroy(j->ev0);
+      if (j->ev1) cudaEventDestroy(j->ev1);
+      if (j->own_stream && j->stream) cudaStreamDestroy(j->stream);
+      cudaGetLastError();
+      delete j;
+    }
+    h->res_cv.notify_all();
   }
-  delete j;
+  bury_handle(h);   // the shell stays readable for late callers; freed after kGraveyardDepth further closes
   return TG_OK;
 }
 

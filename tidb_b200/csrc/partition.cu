@@ -25,6 +25,16 @@ static int pgrid(int device, int64_t n, int per_block, int per_sm) {
   return (int)(need < cap ? need : cap);
 }
 
+// Per-device scratch of the counted calls (counts | cursors): allocated once, never freed — a DevBuf per call would run
+// pool_free's device-wide synchronisation on every exchange step.  The counted calls synchronise their stream before
+// returning, so holding the device's mutex for the duration of a call makes the shared scratch safe.
+struct PartScratch { std::mutex mu; unsigned long long* p = nullptr; };
+static PartScratch& part_scratch(int device) { static PartScratch s[64]; return s[device & 63]; }
+static int part_scratch_ensure(PartScratch& ps) {
+  if (!ps.p) TG_CUDA(cudaMalloc(&ps.p, (size_t)TG_MAX_PARTS * 8 * 4));
+  return TG_OK;
+}
+
 }  // namespace tg
 
 using namespace tg;
@@ -52,9 +62,10 @@ int tg_partition_by_key(int device, const int64_t* key_dev, const uint8_t* key_n
   DeviceGuard g(device);
   if (!g.ok) return fail(TG_ERR_CUDA, "cudaSetDevice failed (no usable CUDA device)");
   cudaStream_t st = (cudaStream_t)stream;
-  DevBuf scratch;
-  TG_TRY(scratch.ensure(device, (size_t)TG_MAX_PARTS * 8 * 2 + 64));
-  unsigned long long* counts = scratch.as<unsigned long long>();
+  PartScratch& ps = part_scratch(device);
+  std::lock_guard<std::mutex> slk(ps.mu);
+  TG_TRY(part_scratch_ensure(ps));
+  unsigned long long* counts = ps.p;
   unsigned long long* cursors = counts + TG_MAX_PARTS;
   TG_CUDA(cudaMemsetAsync(counts, 0, (size_t)TG_MAX_PARTS * 16, st));
   const long long* key = reinterpret_cast<const long long*>(key_dev);
@@ -66,7 +77,7 @@ int tg_partition_by_key(int device, const int64_t* key_dev, const uint8_t* key_n
   d.dst_base = reinterpret_cast<const long long*>(part_offsets_dev);
   TG_TRY(launch_partition_scatter<false>(device, st, key, key_nulls_dev, rows, d, cursors, nullptr));
   TG_CUDA(cudaGetLastError());
-  TG_CUDA(cudaStreamSynchronize(st));   // scratch is freed on return
+  TG_CUDA(cudaStreamSynchronize(st));   // the shared scratch is released with the lock
   return TG_OK;
 }
 
@@ -78,9 +89,10 @@ int tg_partition_exchange(int device, const int64_t* key_dev, int64_t rows, int3
   DeviceGuard g(device);
   if (!g.ok) return fail(TG_ERR_CUDA, "cudaSetDevice failed (no usable CUDA device)");
   cudaStream_t st = (cudaStream_t)stream;
-  DevBuf scratch;
-  TG_TRY(scratch.ensure(device, (size_t)TG_MAX_PARTS * 8 + 64));
-  unsigned long long* cursors = scratch.as<unsigned long long>();
+  PartScratch& ps = part_scratch(device);
+  std::lock_guard<std::mutex> slk(ps.mu);
+  TG_TRY(part_scratch_ensure(ps));
+  unsigned long long* cursors = ps.p;
   TG_CUDA(cudaMemsetAsync(cursors, 0, (size_t)TG_MAX_PARTS * 8, st));
   PartDst d{};
   d.nparts = nparts; d.ncols = ncols;
@@ -92,49 +104,103 @@ int tg_partition_exchange(int device, const int64_t* key_dev, int64_t rows, int3
   return TG_OK;
 }
 
-static __global__ void k_zero_cf(unsigned long long* sent, unsigned long long* overflow, long long* bases, long long base) {
-  if (threadIdx.x < TG_MAX_PARTS) { sent[threadIdx.x] = 0; bases[threadIdx.x] = base; }
-  (void)overflow;   // sticky: zeroed once by the owner, so an overflow of ANY step is still visible when the host looks
+static __global__ void k_zero_cf(unsigned long long* sent, int nparts) {
+  if ((int)threadIdx.x < nparts) sent[threadIdx.x] = 0;
+  // the overflow flag is sticky: zeroed once by its owner, so an overflow of ANY step is still visible when the host looks
 }
 
-int tg_partition_exchange_cf(int device, const int64_t* key_dev, int64_t rows, int32_t nparts, int32_t ncols,
-                             const void* const* src_cols_dev, void* const* recv_cols_peer, int64_t region_base,
-                             int64_t region_cap, int64_t* sent_rows_dev, uint64_t* overflow_dev, void* stream) {
+static int exchange_cf_impl(int device, const int64_t* key_dev, int64_t rows, int32_t nparts, int32_t ncols,
+                            const void* const* src_cols_dev, void* const* recv_cols_peer, int64_t region_base,
+                            int64_t region_cap, int64_t* sent_rows_dev, uint64_t* overflow_dev, int ctas_per_sm, void* stream) {
   TG_TRY(check_parts(nparts, ncols));
   if (ncols > 4) return fail(TG_ERR_UNSUPPORTED, "count-free exchange moves at most 4 columns per call");
   if (!scatter_bulk_enabled()) return fail(TG_ERR_UNSUPPORTED, "count-free exchange needs the bulk-store scatter kernel (TG_SCATTER_BULK=0 disables it)");
   if (!sent_rows_dev || !overflow_dev || region_cap <= 0) return fail(TG_ERR_INVALID, "sent_rows_dev / overflow_dev / region_cap are required");
   if (src_cols_dev[0] != (const void*)key_dev) return fail(TG_ERR_INVALID, "src_cols_dev[0] must be the key column");
   for (int c = 0; c < ncols; c++) if (!ptr_aligned16(src_cols_dev[c])) return fail(TG_ERR_UNSUPPORTED, "source columns must be 16-byte aligned");
+  for (int i = 0; i < nparts * ncols; i++) if (!ptr_aligned16(recv_cols_peer[i])) return fail(TG_ERR_UNSUPPORTED, "receive columns must be 16-byte aligned");
+  if (region_base & 1) return fail(TG_ERR_UNSUPPORTED, "region_base must be even (16-byte aligned regions)");
   DeviceGuard g(device);
   if (!g.ok) return fail(TG_ERR_CUDA, "cudaSetDevice failed (no usable CUDA device)");
   cudaStream_t st = (cudaStream_t)stream;
-  // per-device scratch for the (identical) region bases: lives as long as the process, so the call never synchronises
-  static std::mutex mu;
-  static long long* bases_of[64];
-  long long* bases = nullptr;
-  {
-    std::lock_guard<std::mutex> lk(mu);
-    if (!bases_of[device & 63]) TG_CUDA(cudaMalloc(&bases_of[device & 63], TG_MAX_PARTS * 8 * 4));
-    bases = bases_of[device & 63];
-  }
-  // NOTE: `bases` is rewritten per call on the caller's stream; concurrent calls on different streams of one device with
-  // different region_base values must not overlap (the exchange is one call per step)
   unsigned long long* cursors = reinterpret_cast<unsigned long long*>(sent_rows_dev);
-  k_zero_cf<<<1, 32, 0, st>>>(cursors, reinterpret_cast<unsigned long long*>(overflow_dev), bases, (long long)region_base);
+  k_zero_cf<<<1, 32, 0, st>>>(cursors, nparts);
   PartDst d{};
   d.nparts = nparts; d.ncols = ncols;
   for (int c = 0; c < ncols; c++) { d.src[c] = src_cols_dev[c]; for (int p = 0; p < nparts; p++) d.dst[p][c] = recv_cols_peer[p * ncols + c]; }
-  d.dst_base = bases; d.capacity = region_cap; d.overflow = reinterpret_cast<unsigned long long*>(overflow_dev);
+  d.dst_base = nullptr; d.base_const = region_base;   // every destination holds this sender's region at the same row offset
+  d.capacity = region_cap; d.overflow = reinterpret_cast<unsigned long long*>(overflow_dev);
   const int64_t TILE = 1024;
   const int64_t n_main = rows / TILE * TILE;
-  if (n_main > 0) TG_TRY(launch_partition_scatter<false>(device, st, reinterpret_cast<const long long*>(key_dev), nullptr, n_main, d, cursors, nullptr));
+  if (n_main > 0) TG_TRY(launch_partition_scatter<false>(device, st, reinterpret_cast<const long long*>(key_dev), nullptr, n_main, d, cursors, nullptr, ctas_per_sm));
   if (n_main < rows) {
     // the last < 1024 rows: LSU kernel, one CTA, same cursors and capacity
     PartDst tail = d;
     for (int c = 0; c < ncols; c++) tail.src[c] = reinterpret_cast<const unsigned long long*>(src_cols_dev[c]) + n_main;
     k_partition_scatter<false><<<1, PT_BLOCK, 0, st>>>(reinterpret_cast<const long long*>(tail.src[0]), nullptr, rows - n_main, tail, cursors);
   }
+  TG_CUDA(cudaGetLastError());
+  return TG_OK;
+}
+
+int tg_partition_exchange_cf(int device, const int64_t* key_dev, int64_t rows, int32_t nparts, int32_t ncols,
+                             const void* const* src_cols_dev, void* const* recv_cols_peer, int64_t region_base,
+                             int64_t region_cap, int64_t* sent_rows_dev, uint64_t* overflow_dev, void* stream) {
+  return exchange_cf_impl(device, key_dev, rows, nparts, ncols, src_cols_dev, recv_cols_peer, region_base, region_cap, sent_rows_dev, overflow_dev, 0, stream);
+}
+
+int tg_partition_exchange_cf_ex(int device, const int64_t* key_dev, int64_t rows, int32_t nparts, int32_t ncols,
+                                const void* const* src_cols_dev, void* const* recv_cols_peer, int64_t region_base,
+                                int64_t region_cap, int64_t* sent_rows_dev, uint64_t* overflow_dev, int32_t ctas_per_sm, void* stream) {
+  return exchange_cf_impl(device, key_dev, rows, nparts, ncols, src_cols_dev, recv_cols_peer, region_base, region_cap, sent_rows_dev, overflow_dev, ctas_per_sm, stream);
+}
+
+// ---- cross-GPU mailboxes: the exchange's only synchronisation, peer stores + spinning loads, no NCCL, no host ------
+// One 8-byte word per (kind, buffer set, sender): epoch << 40 | value.  A single 64-bit store is atomic, so the word needs
+// no second flag.  The signal kernel runs AFTER the kernel whose peer stores it publishes (stream order: kernel
+// completion makes them visible system-wide); the wait kernel runs BEFORE the kernel that consumes them.
+static __global__ void k_mail_signal(tg_mail_targets t, const unsigned long long* values, unsigned long long epoch) {
+  const int p = threadIdx.x;
+  if (p >= t.n) return;
+  unsigned long long v = values ? values[p] : 0ull;
+  if (v >= (1ull << 40)) v = (1ull << 40) - 1;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(t.slot[p]), "l"((epoch << 40) | v) : "memory");
+}
+
+static __global__ void k_mail_wait(const unsigned long long* mail, int n, unsigned long long epoch, unsigned long long* values_out,
+                                   unsigned long long* error_flag, unsigned long long timeout_ns) {
+  const int p = threadIdx.x;
+  if (p >= n) return;
+  unsigned long long t0, now, v;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mail + p) : "memory");
+    if ((v >> 40) >= epoch) break;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+    if (now - t0 > timeout_ns) { atomicExch(error_flag, 1ull + (unsigned long long)p); v = 0; break; }   // never hang the GPU: report and go on
+    __nanosleep(200);
+  }
+  if (values_out) values_out[p] = v & ((1ull << 40) - 1);
+}
+
+int tg_mail_signal(int device, const tg_mail_targets* targets, const int64_t* values_dev, int64_t epoch, void* stream) {
+  if (!targets || targets->n < 1 || targets->n > TG_MAIL_MAX_PEERS) return fail(TG_ERR_INVALID, "1..16 mailbox targets");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(TG_ERR_CUDA, "cudaSetDevice failed (no usable CUDA device)");
+  k_mail_signal<<<1, 32, 0, (cudaStream_t)stream>>>(*targets, reinterpret_cast<const unsigned long long*>(values_dev), (unsigned long long)epoch);
+  TG_CUDA(cudaGetLastError());
+  return TG_OK;
+}
+
+int tg_mail_wait(int device, const uint64_t* mail_dev, int32_t n, int64_t epoch, int64_t* values_out_dev, uint64_t* error_flag_dev,
+                 int64_t timeout_ms, void* stream) {
+  if (!mail_dev || !error_flag_dev || n < 1 || n > TG_MAIL_MAX_PEERS) return fail(TG_ERR_INVALID, "mail_dev / error_flag_dev required, 1..16 senders");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(TG_ERR_CUDA, "cudaSetDevice failed (no usable CUDA device)");
+  k_mail_wait<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(mail_dev), n, (unsigned long long)epoch,
+                                                   reinterpret_cast<unsigned long long*>(values_out_dev), reinterpret_cast<unsigned long long*>(error_flag_dev),
+                                                   (unsigned long long)(timeout_ms > 0 ? timeout_ms : 10000) * 1000000ull);
   TG_CUDA(cudaGetLastError());
   return TG_OK;
 }

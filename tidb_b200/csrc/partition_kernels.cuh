@@ -20,7 +20,8 @@ struct PartDst {
   const void* src[TG_PART_MAX_COLS];
   void* dst[TG_MAX_PARTS][TG_PART_MAX_COLS];   // column base per destination
   // row offset inside the destination buffers where this launch starts writing, per destination
-  const long long* dst_base;                   // device array [nparts]
+  const long long* dst_base;                   // device array [nparts]; nullptr = `base_const` for every destination
+  long long base_const;
   // capacity > 0: destination p may hold at most `capacity` rows (count-free partitioning into fixed-size segments);
   // rows beyond it are dropped and *overflow is set — the caller then falls back to an unpartitioned pass.
   long long capacity;
@@ -128,7 +129,7 @@ k_partition_scatter(const long long* __restrict__ key, const uint8_t* __restrict
     if (threadIdx.x < P) {
       uint32_t c = s_cnt[threadIdx.x];
       unsigned long long old = c ? atomicAdd(&cursors[threadIdx.x], (unsigned long long)c) : 0ull;
-      s_gbase[threadIdx.x] = old + (unsigned long long)d.dst_base[threadIdx.x];
+      s_gbase[threadIdx.x] = old + (unsigned long long)(d.dst_base ? d.dst_base[threadIdx.x] : d.base_const);
       // rows of this tile that still fit the destination's capacity (0 = unbounded)
       unsigned long long room = d.capacity > 0 ? (old < (unsigned long long)d.capacity ? (unsigned long long)d.capacity - old : 0ull) : ~0ull;
       s_room[threadIdx.x] = room > c ? c : (uint32_t)room;
@@ -216,7 +217,7 @@ k_partition_scatter_tma(int64_t ntiles, PartDst d, unsigned long long* __restric
       for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
       if (tid < (int)P) {
         s_off[tid] = incl - c;
-        s_gbase[tid] = (c ? atomicAdd(&cursors[tid], (unsigned long long)c) : 0ull) + (unsigned long long)d.dst_base[tid];
+        s_gbase[tid] = (c ? atomicAdd(&cursors[tid], (unsigned long long)c) : 0ull) + (unsigned long long)(d.dst_base ? d.dst_base[tid] : d.base_const);
       }
     }
     __syncthreads();
@@ -326,7 +327,7 @@ k_partition_scatter_bulk(int64_t ntiles, PartDst d, unsigned long long* __restri
           unsigned long long avail = old < (unsigned long long)d.capacity ? (unsigned long long)d.capacity - old : 0ull;
           if ((unsigned long long)c > avail) { len = (uint32_t)avail; *d.overflow = 1ull; }
         }
-        g = old + (unsigned long long)d.dst_base[tid];
+        g = old + (unsigned long long)(d.dst_base ? d.dst_base[tid] : d.base_const);
       }
       uint32_t w = tid < (int)P ? (((uint32_t)(g & 1) + c + 1) & ~1u) : 0, incl = w;
       for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
@@ -443,7 +444,7 @@ inline int scatter_bulk_enabled() {
 }
 
 template <bool HIGH, int NC>
-inline int launch_scatter_nc(int device, cudaStream_t st, int64_t n, PartDst& d, unsigned long long* cursors, int64_t* launches) {
+inline int launch_scatter_nc(int device, cudaStream_t st, int64_t n, PartDst& d, unsigned long long* cursors, int64_t* launches, int ctas_per_sm = 0) {
   int nsm = device_sm_count(device);
   if (scatter_bulk_enabled()) {
     // 1024-row tiles: 4 CTAs per SM for NC <= 2 (profiles/r1_scatter_bulk.md)
@@ -458,6 +459,7 @@ inline int launch_scatter_nc(int device, cudaStream_t st, int64_t n, PartDst& d,
       static int cap_env = -1;
       if (cap_env < 0) { const char* e = getenv("TG_SCATTER_CTAS_PER_SM"); cap_env = e ? atoi(e) : 0; }
       if (!HIGH && cap_env > 0 && per_sm > cap_env) per_sm = cap_env;
+      if (ctas_per_sm > 0 && per_sm > ctas_per_sm) per_sm = ctas_per_sm;
       int grid = (int)std::min<int64_t>(ntiles, (int64_t)nsm * per_sm);
       k_partition_scatter_bulk<HIGH, NC, ITEMS><<<grid, PT_BLOCK, smem, st>>>(ntiles, d, cursors);
       if (launches) (*launches)++;
@@ -493,16 +495,18 @@ inline int launch_scatter_nc(int device, cudaStream_t st, int64_t n, PartDst& d,
 // d.src[0] must be the key column; falls back to the LSU kernel for NULL-able keys, unaligned sources or > 4 columns
 template <bool HIGH>
 inline int launch_partition_scatter(int device, cudaStream_t st, const long long* key, const uint8_t* nulls, int64_t n, PartDst& d,
-                                    unsigned long long* cursors, int64_t* launches) {
+                                    unsigned long long* cursors, int64_t* launches, int ctas_per_sm = 0) {
   if (n <= 0) return TG_OK;
   bool tma_ok = !nulls && d.ncols <= 4 && d.src[0] == (const void*)key;
   for (int c = 0; c < d.ncols && tma_ok; c++) tma_ok = ptr_aligned16(d.src[c]);
+  // the bulk stores start at dst + (even row): every destination column base must be 16-byte aligned too
+  for (int p = 0; p < d.nparts && tma_ok; p++) for (int c = 0; c < d.ncols && tma_ok; c++) tma_ok = ptr_aligned16(d.dst[p][c]);
   if (tma_ok) {
     switch (d.ncols) {
-      case 1: return launch_scatter_nc<HIGH, 1>(device, st, n, d, cursors, launches);
-      case 2: return launch_scatter_nc<HIGH, 2>(device, st, n, d, cursors, launches);
-      case 3: return launch_scatter_nc<HIGH, 3>(device, st, n, d, cursors, launches);
-      default: return launch_scatter_nc<HIGH, 4>(device, st, n, d, cursors, launches);
+      case 1: return launch_scatter_nc<HIGH, 1>(device, st, n, d, cursors, launches, ctas_per_sm);
+      case 2: return launch_scatter_nc<HIGH, 2>(device, st, n, d, cursors, launches, ctas_per_sm);
+      case 3: return launch_scatter_nc<HIGH, 3>(device, st, n, d, cursors, launches, ctas_per_sm);
+      default: return launch_scatter_nc<HIGH, 4>(device, st, n, d, cursors, launches, ctas_per_sm);
     }
   }
   int nsm = device_sm_count(device);

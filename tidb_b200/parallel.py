@@ -434,3 +434,197 @@ class SegmentExchange:
             self.lib.tg_dev_free(self.device, C.c_void_p(ptr))
         self.recv_ptrs = []
         self.staging = []
+
+
+class MailboxExchange:
+    """Count-free key-hash exchange whose ONLY synchronisation is device-side mailboxes (tg_mail_signal / tg_mail_wait):
+    no NCCL collective, no copy-engine call and no host wait inside a step, so a step is a fixed handful of kernel
+    launches per rank (CUDA-graph capturable) and its cost does not depend on host-side enqueue latency.
+
+      send()    on the exchange stream X:  wait for the peers' ACKs of the step that last used this buffer set,
+                k_partition_scatter_bulk regroups 1024-row tiles by destination and appends each destination's run to
+                this rank's region on that peer with bulk stores over NVLink (one kernel = repartition + all-to-all),
+                then publishes the per-destination fill counts into every peer's COUNT mailbox;
+      recv()    on the probe stream S: spin (on the device) until all `world` senders have published their count for
+                this step; the counts land in seg_cnt, ready for tg_join_probe_dev_seg;
+      release() on S after the probe: ACK to every sender that this buffer set may be overwritten.
+
+    Two buffer sets: X runs one step ahead of S (the NVLink-bound scatter of step k+1 overlaps the probe of step k).
+    dma=True keeps the SMs out of the transfer: the kernel regroups into a local staging copy of the region layout and
+    copy engines push region p to peer p on several streams (fill is unknown to the host, so whole regions move).
+    Reference analogue: MPP ExchangeSender/Receiver with HashPartition (physical_exchange_sender.go:115)."""
+
+    KIND_COUNT, KIND_ACK = 0, 1
+    SLOTS = 16   # TG_MAIL_MAX_PEERS
+
+    def __init__(self, rank: int, world: int, device: int, xstream, ncols: int, rows_per_step: int, slack: float = 1.06,
+                 dma: bool = False, ctas_per_sm: int = 0, timeout_ms: int = 10000):
+        import torch
+        import torch.distributed as dist
+        from . import abi
+        self.torch, self.dist, self.abi = torch, dist, abi
+        self.lib = abi.load_lib()
+        self.rank, self.world, self.device, self.stream, self.ncols = rank, world, device, xstream, ncols
+        self.dev = torch.device("cuda", device)
+        self.dma = bool(dma) and world > 1
+        self.ctas_per_sm = int(ctas_per_sm)
+        self.timeout_ms = int(timeout_ms)
+        self.cap = region_capacity(rows_per_step, world, slack)
+        self.sets = 2
+        self.sent_steps = 0
+        self.recv_steps = 0
+        self.launches = 0
+        lib = self.lib
+        self.sent = [torch.zeros(self.SLOTS, dtype=torch.int64, device=self.dev) for _ in range(self.sets)]
+        self.seg_cnt = [torch.zeros(world, dtype=torch.int64, device=self.dev) for _ in range(self.sets)]
+        self.overflow = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.errflag = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        # receive buffers [set][col] and the mailbox block [kind][set][SLOTS] of this rank, all IPC-exported
+        self.recv_ptrs, handles = [], []
+        for _ in range(self.sets):
+            row = []
+            for _c in range(ncols):
+                row.append(self._alloc(world * self.cap * 8 + 64, handles))
+            self.recv_ptrs.append(row)
+        self.mail_ptr = self._alloc(2 << 20, handles)   # a whole 2 MiB allocation: IPC handles map at allocation granularity
+        abi.check(lib.tg_memcpy_h2d(device, C.c_void_p(self.mail_ptr), (C.c_uint64 * (2 * self.sets * self.SLOTS))(), C.c_size_t(2 * self.sets * self.SLOTS * 8)))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, handles)
+        self._mapped = []
+        def peer_ptr(p, idx):
+            if p == rank:
+                return ([q for row in self.recv_ptrs for q in row] + [self.mail_ptr])[idx]
+            mp = C.c_void_p()
+            hb = (C.c_uint8 * 64).from_buffer_copy(gathered[p][idx])
+            abi.check(lib.tg_ipc_open(device, hb, C.byref(mp)))
+            self._mapped.append(mp.value)
+            return mp.value
+        self.peer_recv = [[[peer_ptr(p, s_ * ncols + c) for c in range(ncols)] for p in range(world)] for s_ in range(self.sets)]   # [set][peer][col]
+        self.peer_mail = [peer_ptr(p, self.sets * ncols) for p in range(world)]
+        self.peer_arr = []
+        for s_ in range(self.sets):
+            flat = [self.peer_recv[s_][p][c] for p in range(world) for c in range(ncols)]
+            self.peer_arr.append((C.c_void_p * len(flat))(*flat))
+        # where this rank's words live inside every peer's mailbox block
+        self.targets = {}
+        for kind in (self.KIND_COUNT, self.KIND_ACK):
+            for s_ in range(self.sets):
+                t = abi.TgMailTargets()
+                t.n = world
+                for p in range(world):
+                    t.slot[p] = self.peer_mail[p] + ((kind * self.sets + s_) * self.SLOTS + rank) * 8
+                self.targets[(kind, s_)] = t
+        if self.dma:
+            self.staging, self.stage_arr, self.staged_free = [], [], [None] * self.sets
+            for s_ in range(self.sets):
+                row = [self._alloc(world * self.cap * 8 + 64, None) for _c in range(ncols)]
+                self.staging.append(row)
+                # the kernel writes destination p at rows [rank*cap, ...) of the pointer it is given: bias the staging
+                # pointer so that this lands in staging region p; own rows go straight into the own receive set
+                flat = [self.recv_ptrs[s_][c] if p == rank else row[c] + (p - rank) * self.cap * 8 for p in range(world) for c in range(ncols)]
+                self.stage_arr.append((C.c_void_p * len(flat))(*flat))
+            self.copy_streams = [torch.cuda.Stream(device=self.dev) for _ in range(min(4, world - 1))]
+            self.dstream = torch.cuda.Stream(device=self.dev)
+        torch.cuda.synchronize(self.dev)
+        dist.barrier()    # every mailbox is zeroed and mapped before anybody signals
+
+    def _alloc(self, nbytes, handles):
+        p = C.c_void_p()
+        self.abi.check(self.lib.tg_dev_alloc(self.device, C.c_size_t(nbytes), C.byref(p)))
+        if handles is not None:
+            h = (C.c_uint8 * 64)()
+            self.abi.check(self.lib.tg_ipc_export(self.device, p, h))
+            handles.append(bytes(h))
+        return p.value
+
+    def _mail(self, kind, s_):
+        return self.mail_ptr + (kind * self.sets + s_) * self.SLOTS * 8
+
+    def _view(self, ptr: int, n: int):
+        class _A:
+            pass
+        a = _A()
+        a.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+        return self.torch.as_tensor(a, device=self.dev)
+
+    def send(self, key, cols):
+        """enqueue step k's repartition + transfer + count publication on the exchange stream; cols[0] must be `key`"""
+        lib, abi, torch = self.lib, self.abi, self.torch
+        k = self.sent_steps
+        self.sent_steps += 1
+        s_, epoch = k % self.sets, k + 1
+        X = C.c_void_p(self.stream.cuda_stream)
+        src_p = (C.c_void_p * len(cols))(*[c.data_ptr() for c in cols])
+        err = C.c_void_p(self.errflag.data_ptr())
+        if not self.dma:
+            if k >= self.sets:   # every peer has finished probing the step that used this buffer set
+                abi.check(lib.tg_mail_wait(self.device, C.c_void_p(self._mail(self.KIND_ACK, s_)), self.world, C.c_int64(epoch - self.sets), None, err, C.c_int64(self.timeout_ms), X))
+            abi.check(lib.tg_partition_exchange_cf_ex(self.device, C.c_void_p(key.data_ptr()), C.c_int64(key.numel()), self.world, len(cols), src_p,
+                                                      self.peer_arr[s_], C.c_int64(self.rank * self.cap), C.c_int64(self.cap),
+                                                      C.c_void_p(self.sent[s_].data_ptr()), C.c_void_p(self.overflow.data_ptr()), C.c_int32(self.ctas_per_sm), X))
+            abi.check(lib.tg_mail_signal(self.device, C.byref(self.targets[(self.KIND_COUNT, s_)]), C.c_void_p(self.sent[s_].data_ptr()), C.c_int64(epoch), X))
+            self.launches += 4 if k >= self.sets else 3
+            return
+        D = self.dstream
+        with torch.cuda.stream(self.stream):
+            if self.staged_free[s_] is not None:
+                self.stream.wait_event(self.staged_free[s_])      # the copies of step k-2 have left staging set s_
+            if k >= self.sets:   # own rows go straight into the own receive set: the own probe of step k-2 must be done
+                abi.check(lib.tg_mail_wait(self.device, C.c_void_p(self._mail(self.KIND_ACK, s_)), self.world, C.c_int64(epoch - self.sets), None, err, C.c_int64(self.timeout_ms), X))
+            abi.check(lib.tg_partition_exchange_cf_ex(self.device, C.c_void_p(key.data_ptr()), C.c_int64(key.numel()), self.world, len(cols), src_p,
+                                                      self.stage_arr[s_], C.c_int64(self.rank * self.cap), C.c_int64(self.cap),
+                                                      C.c_void_p(self.sent[s_].data_ptr()), C.c_void_p(self.overflow.data_ptr()), C.c_int32(self.ctas_per_sm), X))
+            regrouped = torch.cuda.Event(); regrouped.record(self.stream)
+        for cs in self.copy_streams:
+            cs.wait_event(regrouped)
+        for i in range(1, self.world):
+            p = (self.rank + i) % self.world      # ring order spreads the peers' NVLink ingress
+            cs = self.copy_streams[(i - 1) % len(self.copy_streams)]
+            for c in range(len(cols)):
+                abi.check(lib.tg_memcpy_d2d_async(self.device, C.c_void_p(self.peer_recv[s_][p][c] + self.rank * self.cap * 8),
+                                                  C.c_void_p(self.staging[s_][c] + p * self.cap * 8), C.c_size_t(self.cap * 8), C.c_void_p(cs.cuda_stream)))
+        with torch.cuda.stream(D):
+            for cs in self.copy_streams:
+                e = torch.cuda.Event(); e.record(cs); D.wait_event(e)
+            abi.check(lib.tg_mail_signal(self.device, C.byref(self.targets[(self.KIND_COUNT, s_)]), C.c_void_p(self.sent[s_].data_ptr()), C.c_int64(epoch), C.c_void_p(D.cuda_stream)))
+            done = torch.cuda.Event(); done.record(D)
+            self.staged_free[s_] = done
+        self.launches += 4 if k >= self.sets else 3
+
+    def recv(self, probe_stream):
+        """enqueue on `probe_stream` the wait for step k's counts -> (received columns, seg_cnt tensor, cap, set, epoch)"""
+        k = self.recv_steps
+        self.recv_steps += 1
+        s_, epoch = k % self.sets, k + 1
+        self.abi.check(self.lib.tg_mail_wait(self.device, C.c_void_p(self._mail(self.KIND_COUNT, s_)), self.world, C.c_int64(epoch),
+                                             C.c_void_p(self.seg_cnt[s_].data_ptr()), C.c_void_p(self.errflag.data_ptr()), C.c_int64(self.timeout_ms),
+                                             C.c_void_p(probe_stream.cuda_stream)))
+        self.launches += 1
+        return [self._view(self.recv_ptrs[s_][c], self.world * self.cap) for c in range(self.ncols)], self.seg_cnt[s_], self.cap, s_, epoch
+
+    def release(self, probe_stream, s_, epoch):
+        """enqueue on `probe_stream`, after the consumer of set `s_`: tell every sender the set may be overwritten"""
+        self.abi.check(self.lib.tg_mail_signal(self.device, C.byref(self.targets[(self.KIND_ACK, s_)]), None, C.c_int64(epoch), C.c_void_p(probe_stream.cuda_stream)))
+        self.launches += 1
+
+    def check(self):
+        """host check (synchronises): a region overflow or a mailbox timeout anywhere fails the run on every rank"""
+        self.torch.cuda.synchronize(self.dev)
+        flag = self.torch.stack([self.overflow[0], self.errflag[0]]).clone()
+        flag = (flag != 0).to(self.torch.int64)
+        self.dist.all_reduce(flag)
+        if int(flag[1].item()):
+            raise RuntimeError("mailbox wait timed out on some rank: a peer never published its step (see tg_mail_wait)")
+        if int(flag[0].item()):
+            raise RuntimeError("count-free exchange overflowed a receive region: raise `slack` or use KeyExchange (counted)")
+
+    def close(self):
+        self.torch.cuda.synchronize(self.dev)
+        self.dist.barrier()
+        for mp in self._mapped:
+            self.lib.tg_ipc_close(self.device, C.c_void_p(mp))
+        for row in self.recv_ptrs + (self.staging if self.dma else []):
+            for ptr in row:
+                self.lib.tg_dev_free(self.device, C.c_void_p(ptr))
+        self.lib.tg_dev_free(self.device, C.c_void_p(self.mail_ptr))
+        self.recv_ptrs, self._mapped = [], []
