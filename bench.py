@@ -309,24 +309,41 @@ def run_gpu(args):
     xmail = None
     mail_choice = None
     mail_timings = {}
-    MAIL_CANDIDATES = {"mail": dict(dma=False, ctas_per_sm=args.scatter_ctas), "mail-c2": dict(dma=False, ctas_per_sm=2), "mail-dma": dict(dma=True, ctas_per_sm=0)}
+    MAIL_CANDIDATES = {"mail": dict(dma=False, ctas_per_sm=args.scatter_ctas), "mail-dma": dict(dma=True, ctas_per_sm=args.scatter_ctas)}
 
     def mail_step(xm, sync: bool):
-        with torch.cuda.stream(xstream):
-            xm.send(pk, [pk, pv])
+        """ALL SM kernels of a rank on ONE stream, in the order regroup(k+1), probe(k): the shared-memory-heavy scatter never
+        shares an SM with the L1-hungry probe kernel.  With dma the copy engines move step k+1 over NVLink under probe(k);
+        without it the scatter stores into the peers itself (NVLink-bound at N = 8, no overlap)."""
+        def mark(name):
+            if TRACE is not None:
+                e = torch.cuda.Event(enable_timing=True); e.record(stream); TRACE.append((name, e))
         with torch.cuda.stream(stream):
+            if not getattr(xm, "_primed", False):
+                xm.send(pk, [pk, pv], stream)      # pipeline prologue: step 0
+                xm._primed = True
+            mark("step begin")
+            xm.send(pk, [pk, pv], stream)          # step k+1
+            mark("regroup(k+1) done")
             cols_in, seg_cnt, cap, s_, ep = xm.recv(stream)
+            mark("counts(k) arrived")
             rows, cols, _ = join.probe_segments(cols_in, seg_cnt, cap, sync=sync)
+            mark("probe(k) done")
             out = (rows, check_piece(cols, rows)) if sync else (None, None)
             xm.release(stream, s_, ep)     # the probe has consumed receive set s_: the senders may overwrite it
         return out
 
+    def mail_drain(xm):
+        """before the closing event: the transfer of the step sent last must have left this rank (its regroup already ran)"""
+        if xm.last_transfer is not None:
+            stream.wait_event(xm.last_transfer)
+
     if world > 1 and args.exchange in ("mail", "mail-dma", "auto"):
         from tidb_b200.parallel import MailboxExchange
-        names = ["mail", "mail-c2", "mail-dma"] if args.exchange == "auto" else [args.exchange]
+        names = ["mail", "mail-dma"] if args.exchange == "auto" else [args.exchange]
         timings = {}
         for nm in names:
-            xm = MailboxExchange(rank, world, local, xstream, 2, npb, **MAIL_CANDIDATES[nm])
+            xm = MailboxExchange(rank, world, local, xstream, 2, npb, slack=args.slack, **MAIL_CANDIDATES[nm])
             if len(names) > 1:
                 for _ in range(2):
                     mail_step(xm, False)
@@ -336,6 +353,7 @@ def run_gpu(args):
                     c0.record(stream); xstream.wait_event(c0)
                     for _ in range(4):
                         mail_step(xm, False)
+                    mail_drain(xm)
                     c1.record(stream)
                 stream.synchronize(); xm.check()
                 tt = torch.tensor([c0.elapsed_time(c1) / 4], dtype=torch.float64, device=dev)
@@ -344,7 +362,7 @@ def run_gpu(args):
                 xm.close()
         if len(names) > 1:
             mail_choice = min(timings, key=timings.get)
-            xmail = MailboxExchange(rank, world, local, xstream, 2, npb, **MAIL_CANDIDATES[mail_choice])
+            xmail = MailboxExchange(rank, world, local, xstream, 2, npb, slack=args.slack, **MAIL_CANDIDATES[mail_choice])
         else:
             mail_choice, xmail = names[0], xm
         mail_timings = timings
@@ -428,12 +446,14 @@ def run_gpu(args):
             xstream.wait_event(ev0)
         for _ in range(args.steps):
             step(False)
+        if xmail is not None:
+            mail_drain(xmail)
         ev1.record(stream)
     stream.synchronize()
     barrier()
     if TRACE and rank == 0:
         t0 = ev0
-        for name, e in TRACE[-7 * min(args.steps, 4):]:
+        for name, e in TRACE[-(4 if xmail is not None else 7) * min(args.steps, 4):]:
             print(f"[trace] {t0.elapsed_time(e):9.3f} ms  {name}", file=sys.stderr)
     clocks = sampler.stop() if rank == 0 else None
     ms_total = ev0.elapsed_time(ev1)
@@ -758,6 +778,7 @@ def main():
                     help="N>1 probe-side exchange: mail = count-free peer bulk stores + device mailboxes (no NCCL / host in a step); mail-dma = same, copy engines "
                          "move the regions; auto = time mail / mail (2 scatter CTAs per SM) / mail-dma untimed and keep the fastest; cf = round-1 count-free exchange "
                          "(NCCL all-gather per step); p2p = counted peer stores; nccl = local scatter + all_to_all")
+    ap.add_argument("--slack", type=float, default=1.03, help="N>1, mailbox exchange: receive-region capacity = expected share x slack + 8192 rows (uniform keys: 3 %% is > 100 sigma)")
     ap.add_argument("--scatter-ctas", type=int, default=0, help="N>1, --exchange mail: cap on the exchange kernel's CTAs per SM (0 = as many as fit)")
     ap.add_argument("--overlap", type=int, default=2, help="N>1, --exchange cf: 1: run the exchange of step k+1 on a second stream under the probe of step k; 2: additionally a transfer stream, so regroup / NVLink copy / probe work on three consecutive steps")
     ap.add_argument("--dma", type=int, default=1, help="N>1, --exchange cf: regroup locally, let copy engines move the regions over NVLink")

@@ -175,10 +175,24 @@ typedef struct tg_filter_item {
   int32_t rhs_col;     /* -1 = compare with constant                                     */
   int32_t is_real;     /* 0: int64 compare (signed unless lhs_unsigned), 1: float64      */
   int32_t lhs_unsigned;
-  int32_t reserved;
+  int32_t rhs_unsigned; /* signedness of the right column / constant (types.CompareInt takes both flags) */
   int64_t const_i64;   /* constant when rhs_col < 0 and !is_real                         */
   double const_f64;    /* constant when rhs_col < 0 and is_real                          */
 } tg_filter_item;
+
+/* One CNF item of HashJoinV2Exec.OtherCondition (inner_join_probe.go:72-79, base_join_probe.go:758
+ * buildResultAfterOtherCondition): `operand OP operand` over the JOINED row, each operand a column of the left or the
+ * right child (side 0 / 1), the right operand optionally a constant (rhs_side = -1).  A candidate pair (equal keys)
+ * is a match only if every item is non-NULL true (VectorizedFilter semantics).                                     */
+typedef struct tg_other_item {
+  int32_t op;            /* TG_CMP_*                                                      */
+  int32_t is_real;       /* 0: int64 compare, 1: float64                                  */
+  int32_t lhs_side, lhs_col;
+  int32_t rhs_side, rhs_col;   /* rhs_side = -1: constant                                 */
+  int32_t lhs_unsigned, rhs_unsigned;
+  int64_t const_i64;
+  double const_f64;
+} tg_other_item;
 
 typedef struct tg_join_desc {
   int32_t join_type;          /* TG_JOIN_*                                                       */
@@ -206,6 +220,10 @@ typedef struct tg_join_desc {
   int32_t reserved1;
   void* stream;               /* cudaStream_t to launch on; NULL = library-owned stream          */
   double load_factor;         /* 0 = default                                                     */
+  /* OtherCondition (non-equi residual evaluated on candidate pairs); offloaded for inner, probe-side outer, semi and
+   * anti-semi joins with the right child as build side (the gate declines the rest)              */
+  int32_t n_other_cond; int32_t reserved2;
+  const tg_other_item* other_cond;
 } tg_join_desc;
 
 /* planner gate: 0 if this descriptor can run on the GPU, TG_ERR_UNSUPPORTED otherwise        */

@@ -135,6 +135,79 @@ def test_agg_config3_shape_reduced():
         assert np.allclose(s, exp_sum[gk], rtol=REL, atol=0)
 
 
+@pytest.mark.parametrize("hint,local_env", [(0, None), (300, None), (200_000, None), (0, "0"), (200_000, "2")])
+def test_agg_two_level_paths_vs_oracle(hint, local_env, monkeypatch):
+    # the round-2 two-level update (csrc/agg_update.cuh): CTA-local tables + global table, every combination of
+    # hint / forced mode, on skewed keys (a few hot groups + a long tail), NULL groups, the sentinel-valued key, 1 % NULL x
+    if local_env is not None:
+        monkeypatch.setenv("TG_AGG_LOCAL", local_env)
+    rng = np.random.default_rng(11 + hint)
+    n = 400_000
+    hot = rng.integers(0, 8, n)
+    tail = rng.integers(-60_000, 60_000, n)
+    g = np.where(rng.random(n) < 0.5, hot, tail).astype(np.int64)
+    g[:3] = -(1 << 63)
+    gn = rng.random(n) < 0.02
+    x = np.floor(rng.random(n) * 1e7); xn = rng.random(n) < 0.01
+    y = rng.integers(-(1 << 40), 1 << 40, n).astype(np.int64)
+    chunks = Chunk([Column(g, gn), Column(x, xn), Column(y)]).split(1 << 16)
+    plan = AggPlan([INT, DBL, INT_NN], [0], [
+        AggFunc(abi.AGG_FIRSTROW, 0), AggFunc(abi.AGG_SUM, 1, abi.TYPE_DOUBLE), AggFunc(abi.AGG_COUNT, 1, abi.TYPE_DOUBLE),
+        AggFunc(abi.AGG_COUNT, -1), AggFunc(abi.AGG_MAX, 2), AggFunc(abi.AGG_MIN, 1, abi.TYPE_DOUBLE)], expected_groups=hint)
+    assert_agg_equal(run_orc_agg(plan, chunks), run_gpu_agg(plan, chunks), {1})
+
+
+@pytest.mark.parametrize("ncols,nullable", [(2, False), (3, True), (4, True)])
+def test_agg_multi_column_group_by_vs_oracle(ncols, nullable):
+    # GetGroupKey concatenates the encodings of every GROUP BY item (agg_util.go:106, codec.go:1761): groups differ when ANY
+    # column differs, NULL is a value of its own in every column, -0.0 groups with +0.0.  Tag-claimed multi-word slots
+    # (csrc/agg.cu k_agg_update_mk), tiny hint -> several table growths.
+    rng = np.random.default_rng(100 + ncols)
+    n = 300_000
+    cols, types = [], []
+    for c in range(ncols):
+        if c == 1:
+            v = rng.integers(-3, 4, n).astype(np.float64) * 0.5
+            v[rng.random(n) < 0.1] = -0.0
+            tp = FieldType(abi.TYPE_DOUBLE, 0 if nullable else abi.FLAG_NOT_NULL)
+        else:
+            v = rng.integers(0, 40 if c else 300, n).astype(np.int64)
+            if c == 0:
+                v[:5] = -(1 << 63)
+            tp = FieldType(abi.TYPE_LONGLONG, 0 if nullable else abi.FLAG_NOT_NULL)
+        nl = (rng.random(n) < 0.05) if nullable else None
+        cols.append(Column(v, nl)); types.append(tp)
+    x = np.floor(rng.random(n) * 1e6); xn = rng.random(n) < 0.02
+    cols.append(Column(x, xn)); types.append(DBL)
+    chunks = Chunk(cols).split(1 << 15)
+    funcs = [AggFunc(abi.AGG_FIRSTROW, c, types[c].tp) for c in range(ncols)] + [
+        AggFunc(abi.AGG_SUM, ncols, abi.TYPE_DOUBLE), AggFunc(abi.AGG_COUNT, ncols, abi.TYPE_DOUBLE), AggFunc(abi.AGG_COUNT, -1),
+        AggFunc(abi.AGG_MAX, ncols, abi.TYPE_DOUBLE)]
+    plan = AggPlan(types, list(range(ncols)), funcs, expected_groups=64)
+    assert_agg_equal(run_orc_agg(plan, chunks), run_gpu_agg(plan, chunks), {ncols})
+
+
+def test_agg_multi_push_same_table():
+    # several device batches into one handle (fetchChildData loop, agg_hash_executor.go:449): later batches find the groups
+    # of earlier ones; the table grows between batches
+    rng = np.random.default_rng(5)
+    parts = []
+    for b in range(3):
+        n = 5_000_000 if b == 1 else 70_000       # the middle batch is large enough to be flushed on its own (4M-row staging)
+        g = rng.integers(0, 3000 * (b + 1), n).astype(np.int64)
+        x = np.floor(rng.random(n) * 1000)
+        parts.append(Chunk([Column(g), Column(x)]))
+    chunks = [c for p_ in parts for c in p_.split(1 << 18)]
+    plan = AggPlan([INT_NN, DBL_NN], [0], [AggFunc(abi.AGG_FIRSTROW, 0), AggFunc(abi.AGG_SUM, 1, abi.TYPE_DOUBLE), AggFunc(abi.AGG_COUNT, 1, abi.TYPE_DOUBLE)])
+    out = drain(HashAggExec(plan, MockDataSource(plan.col_types, chunks)), 1 << 16)
+    gk = np.concatenate([c.columns[0].data for c in out]); s_ = np.concatenate([c.columns[1].data for c in out]); cnt = np.concatenate([c.columns[2].data for c in out])
+    gall = np.concatenate([p_.columns[0].data for p_ in parts]); xall = np.concatenate([p_.columns[1].data for p_ in parts])
+    G = 9000
+    assert np.array_equal(np.sort(gk), np.flatnonzero(np.bincount(gall, minlength=G)))
+    assert np.array_equal(cnt, np.bincount(gall, minlength=G)[gk])
+    assert np.allclose(s_, np.bincount(gall, weights=xall, minlength=G)[gk], rtol=REL, atol=0)
+
+
 # ---- VecEval ----------------------------------------------------------------------------------------------
 def _call_vec(fn, *args):
     return fn(*args)

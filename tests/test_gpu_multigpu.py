@@ -40,7 +40,9 @@ def test_mailbox_exchange_two_ranks_vs_oracle(dma):
                "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "mgpu_worker.py"), "--out", td,
                "--build-rows", str(nb), "--probe-rows", str(npr), "--steps", str(steps), "--dma", str(dma)]
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+        if r.returncode != 0 and os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+            open(os.path.join(ROOT, "gpurun_out", f"mgpu_worker_dma{dma}.log"), "w").write(r.stdout + "\n==== stderr ====\n" + r.stderr)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-6000:]
         res = [np.load(os.path.join(td, f"rank{k}.npz")) for k in range(world)]
     INT = FieldType(abi.TYPE_LONGLONG, abi.FLAG_NOT_NULL)
     plan = JoinPlan(abi.JOIN_INNER, [INT, INT], [INT, INT], [0], [0], build_is_right=True)

@@ -51,7 +51,14 @@ class TgMutChunk(C.Structure):
 
 class TgFilterItem(C.Structure):
     _fields_ = [("op", C.c_int32), ("lhs_col", C.c_int32), ("rhs_col", C.c_int32),
-                ("is_real", C.c_int32), ("lhs_unsigned", C.c_int32), ("reserved", C.c_int32),
+                ("is_real", C.c_int32), ("lhs_unsigned", C.c_int32), ("rhs_unsigned", C.c_int32),
+                ("const_i64", C.c_int64), ("const_f64", C.c_double)]
+
+
+class TgOtherItem(C.Structure):
+    """tg_other_item: one CNF item of OtherCondition over the joined row (side 0 = left child, 1 = right, -1 = constant)"""
+    _fields_ = [("op", C.c_int32), ("is_real", C.c_int32), ("lhs_side", C.c_int32), ("lhs_col", C.c_int32),
+                ("rhs_side", C.c_int32), ("rhs_col", C.c_int32), ("lhs_unsigned", C.c_int32), ("rhs_unsigned", C.c_int32),
                 ("const_i64", C.c_int64), ("const_f64", C.c_double)]
 
 
@@ -67,7 +74,8 @@ class TgJoinDesc(C.Structure):
                 ("n_build_filter", C.c_int32), ("n_probe_filter", C.c_int32),
                 ("build_filter", C.POINTER(TgFilterItem)), ("probe_filter", C.POINTER(TgFilterItem)),
                 ("device", C.c_int32), ("reserved1", C.c_int32),
-                ("stream", C.c_void_p), ("load_factor", C.c_double)]
+                ("stream", C.c_void_p), ("load_factor", C.c_double),
+                ("n_other_cond", C.c_int32), ("reserved2", C.c_int32), ("other_cond", C.POINTER(TgOtherItem))]
 
 
 class TgJoinStats(C.Structure):

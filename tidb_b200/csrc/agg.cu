@@ -15,6 +15,7 @@
 #include <memory>
 #include <algorithm>
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace tg {
 
@@ -31,13 +32,21 @@ struct AggFuncDev {
   int32_t arg_col2;
 };
 struct AggSpec { int32_t n; int32_t pad; AggFuncDev f[TG_MAX_AGG]; };
+#define TG_MAX_GROUP_COLS 4
 struct AggTable {
-  long long* keys;
+  long long* keys;                       // single GROUP BY column: the key itself (kEmptyKey = unoccupied)
   unsigned long long* rows;
   unsigned long long* state[2 * TG_MAX_AGG];
   unsigned long long nslots;
+  // several GROUP BY columns (GetGroupKey concatenates their encodings, agg_util.go:106 / codec.go:1761): a slot is claimed
+  // through its 64-bit TAG word (0 empty, hash|1 being written, hash|3 published) and holds nkw key words — one per
+  // column (NULL stored as 0) plus, when a column is nullable, a word with the columns' NULL bits
+  unsigned long long* tags;
+  long long* keyw[TG_MAX_GROUP_COLS + 1];
+  int32_t nkw, pad;
 };
 struct GroupKey { const void* data; const uint8_t* nulls; int32_t kind; int32_t pad; };
+struct GroupKeys { int32_t n, nkw; const void* data[TG_MAX_GROUP_COLS]; const uint8_t* nulls[TG_MAX_GROUP_COLS]; int32_t kind[TG_MAX_GROUP_COLS]; };
 
 // order-preserving map double → u64 so that MIN/MAX(double) can use integer atomics
 __device__ __forceinline__ unsigned long long f64_to_ordered(double d) {
@@ -54,7 +63,7 @@ __global__ void k_agg_init(AggTable t, AggSpec spec, unsigned long long n_total)
   unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
   unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   for (; i < n_total; i += stride) {
-    t.keys[i] = kEmptyKey;
+    if (t.nkw) t.tags[i] = 0; else t.keys[i] = kEmptyKey;
     t.rows[i] = 0;
     for (int k = 0; k < spec.n; k++) {
       const AggFuncDev& f = spec.f[k];
@@ -374,7 +383,7 @@ __global__ void k_agg_count(AggTable t, unsigned long long* count) {
   unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
   unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   unsigned long long c = 0;
-  for (; i < n_total; i += stride) c += i < t.nslots ? (t.keys[i] != kEmptyKey) : (t.rows[i] != 0);
+  for (; i < n_total; i += stride) c += i < t.nslots ? (t.nkw ? t.tags[i] != 0 : t.keys[i] != kEmptyKey) : (t.rows[i] != 0);
   for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
 }
@@ -392,7 +401,7 @@ k_agg_finalize(AggTable t, AggSpec spec, int gk_kind, AggOut out, unsigned long 
   for (; base < n_total; base += stride) {
     unsigned long long i = base + threadIdx.x;
     bool occ = false;
-    if (i < t.nslots) occ = t.keys[i] != kEmptyKey;
+    if (i < t.nslots) occ = t.nkw ? t.tags[i] != 0 : t.keys[i] != kEmptyKey;
     else if (i < n_total) occ = t.rows[i] != 0;
     unsigned b = __ballot_sync(0xffffffffu, occ);
     unsigned long long wbase = 0;
@@ -422,7 +431,12 @@ k_agg_finalize(AggTable t, AggSpec spec, int gk_kind, AggOut out, unsigned long 
           break;
         }
         default:   // FIRSTROW(group column): the group key itself (firstRow4Int func_first_row.go:140)
-          if (i == t.nslots) valid = false;                       // NULL group
+          if (t.nkw) {   // f.arg_col2 = index of the column among the GROUP BY items | word with the NULL bits << 8 (0 = none)
+            const int g = f.arg_col2 & 0xff, nullword = (f.arg_col2 >> 8) & 0xff;
+            if (nullword && ((unsigned long long)t.keyw[nullword][i] >> g) & 1ull) valid = false;
+            else v = (unsigned long long)t.keyw[g][i];
+          }
+          else if (i == t.nslots) valid = false;                       // NULL group
           else if (i == t.nslots + 1) v = (unsigned long long)kEmptyKey;
           else v = (unsigned long long)t.keys[i];
           (void)gk_kind;
@@ -444,6 +458,93 @@ __global__ void k_pack_bitmap_agg(const uint8_t* __restrict__ valid, int64_t n, 
     bitmap[b] = v;
   }
 }
+
+
+// ---- several GROUP BY columns: tag-claimed slots, global table only -------------------------------------------------
+struct KeyWords { long long w[TG_MAX_GROUP_COLS + 1]; };
+__device__ __forceinline__ unsigned long long hash_words(const KeyWords& k, int nkw) {
+  unsigned long long h = hash64((unsigned long long)k.w[0]);
+  for (int j = 1; j < nkw; j++) h = hash64(h ^ ((unsigned long long)k.w[j] * 0xD6E8FEB86659FD93ull + (unsigned long long)j));
+  return h;
+}
+__device__ __forceinline__ void load_key_words(const GroupKeys& gk, int64_t i, KeyWords& k) {
+  unsigned long long nullbits = 0;
+  for (int j = 0; j < gk.n; j++) {
+    long long v = 0;
+    if (gk.nulls[j] && !bit_not_null(gk.nulls[j], i)) nullbits |= 1ull << j;
+    else {
+      v = __ldcs(reinterpret_cast<const long long*>(gk.data[j]) + i);
+      if (gk.kind[j] == GK_F64) { double d = __longlong_as_double(v); if (d == 0) d = 0; v = __double_as_longlong(d); }
+    }
+    k.w[j] = v;
+  }
+  if (gk.nkw > gk.n) k.w[gk.n] = (long long)nullbits;
+}
+// find-or-insert; returns the slot or ~0 when the probe sequence is longer than max_probe (overfull: defer)
+__device__ __forceinline__ unsigned long long mk_find_or_insert(const AggTable& t, const KeyWords& k, unsigned long long h, uint32_t max_probe) {
+  const unsigned long long ready = h | 3ull, busy = (h & ~3ull) | 1ull;
+  uint32_t s = slot32(h, (uint32_t)t.nslots), steps = 0;
+  for (;;) {
+    unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&t.tags[s]);
+    if (cur == 0) {
+      cur = atomicCAS(&t.tags[s], 0ull, busy);
+      if (cur == 0) {
+        for (int j = 0; j < t.nkw; j++) t.keyw[j][s] = k.w[j];
+        __threadfence();
+        *reinterpret_cast<volatile unsigned long long*>(&t.tags[s]) = ready;   // publish
+        return s;
+      }
+    }
+    if ((cur | 2ull) == ready) {
+      while (cur != ready) cur = *reinterpret_cast<volatile unsigned long long*>(&t.tags[s]);   // the claimer is still writing the key words
+      bool eq = true;
+      for (int j = 0; j < t.nkw; j++) eq &= *reinterpret_cast<volatile long long*>(&t.keyw[j][s]) == k.w[j];
+      if (eq) return s;
+    }
+    if (++steps > max_probe) return ~0ull;
+    if (++s == (uint32_t)t.nslots) s = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_agg_update_mk(GroupKeys gk, DevCols cols, int64_t n, AggTable t, AggSpec spec, uint32_t max_probe,
+                uint32_t* deferred, const uint32_t* only, unsigned long long* n_deferred) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  unsigned long long my_deferred = 0;
+  for (; i < n; i += stride) {
+    if (only && !((only[i >> 5] >> (i & 31)) & 1u)) continue;
+    KeyWords k;
+    load_key_words(gk, i, k);
+    const unsigned long long s = mk_find_or_insert(t, k, hash_words(k, t.nkw), max_probe);
+    if (s == ~0ull) { atomicOr(&deferred[i >> 5], 1u << (i & 31)); my_deferred++; continue; }
+    agg_apply(t, spec, cols, i, s);
+  }
+  for (int o = 16; o; o >>= 1) my_deferred += __shfl_xor_sync(0xffffffffu, my_deferred, o);
+  if ((threadIdx.x & 31) == 0 && my_deferred) atomicAdd(n_deferred, my_deferred);
+}
+
+// re-insert every group of an old multi-key table into a bigger one (keys are distinct: claim with the published tag)
+__global__ void k_agg_rehash_mk(AggTable oldt, AggTable newt, int nstates) {
+  unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (; i < oldt.nslots; i += stride) {
+    const unsigned long long tag = oldt.tags[i];
+    if (tag == 0) continue;
+    uint32_t s = slot32(tag, (uint32_t)newt.nslots);
+    for (;;) {
+      if (atomicCAS(&newt.tags[s], 0ull, tag) == 0ull) break;
+      if (++s == (uint32_t)newt.nslots) s = 0;
+    }
+    for (int j = 0; j < oldt.nkw; j++) newt.keyw[j][s] = oldt.keyw[j][i];
+    newt.rows[s] = oldt.rows[i];
+    for (int a = 0; a < nstates; a++) newt.state[a][s] = oldt.state[a][i];
+  }
+}
+
+}  // namespace tg
+#include "agg_update.cuh"
+namespace tg {
 
 struct AggHostStage {
   std::vector<std::unique_ptr<PinBuf>> data, nulls;
@@ -475,8 +576,10 @@ struct AggImpl {
   std::vector<int> types, elem;
   std::vector<uint32_t> flags;
   std::vector<char> needed;
-  int group_col = -1;          // -1: no GROUP BY
+  int group_col = -1;          // -1: no GROUP BY (several GROUP BY columns: the first one)
   int gk_kind = GK_NONE;
+  std::vector<int> group_cols, group_kinds;   // all GROUP BY columns
+  int nkw = 0;                 // > 0: multi-key table (key words per slot)
   AggSpec spec{};
   int nstates = 0;
   std::vector<char> out_nullable;
@@ -519,17 +622,24 @@ static int agg_setup(AggImpl* a, const tg_agg_desc* d) {
   a->elem.resize(d->n_cols);
   for (int i = 0; i < d->n_cols; i++) a->elem[i] = fixed_len(a->types[i]);
   a->needed.assign(d->n_cols, 0);
-  if (d->n_group_by > 1) return fail(TG_ERR_UNSUPPORTED, "GPU hash aggregation handles zero or one GROUP BY column");
-  a->group_col = -1; a->gk_kind = GK_NONE;
-  if (d->n_group_by == 1) {
-    int g = d->group_by_cols[0];
+  if (d->n_group_by > TG_MAX_GROUP_COLS) return fail(TG_ERR_UNSUPPORTED, "GPU hash aggregation handles up to 4 GROUP BY columns");
+  a->group_col = -1; a->gk_kind = GK_NONE; a->nkw = 0;
+  a->group_cols.clear(); a->group_kinds.clear();
+  bool any_nullable = false;
+  for (int q = 0; q < d->n_group_by; q++) {
+    int g = d->group_by_cols[q];
     if (g < 0 || g >= a->ncols) return fail(TG_ERR_INVALID, "group-by column out of range");
-    if (is_int_family(a->types[g])) a->gk_kind = GK_I64;
-    else if (a->types[g] == TG_TYPE_DOUBLE) a->gk_kind = GK_F64;
+    int kind;
+    if (is_int_family(a->types[g])) kind = GK_I64;
+    else if (a->types[g] == TG_TYPE_DOUBLE) kind = GK_F64;
     else return fail(TG_ERR_UNSUPPORTED, "GROUP BY column type is not offloaded (int family / double only)");
-    a->group_col = g;
+    if (a->elem[g] != 8) return fail(TG_ERR_UNSUPPORTED, "GROUP BY columns must be 8-byte columns");
+    if (q == 0) { a->group_col = g; a->gk_kind = kind; }
+    a->group_cols.push_back(g); a->group_kinds.push_back(kind);
+    any_nullable |= !(a->flags[g] & TG_FLAG_NOT_NULL);
     a->needed[g] = 1;
   }
+  if (d->n_group_by > 1) a->nkw = d->n_group_by + (any_nullable ? 1 : 0);
   if (d->n_funcs <= 0 || d->n_funcs > TG_MAX_AGG) return fail(TG_ERR_UNSUPPORTED, "1..12 aggregate functions are offloaded");
   a->spec.n = d->n_funcs;
   a->nstates = 0;
@@ -577,10 +687,14 @@ static int agg_setup(AggImpl* a, const tg_agg_desc* d) {
         if (arg_nullable) o.s1 = a->nstates++;
         a->out_nullable[k] = 1;
         break;
-      case TG_AGG_FIRSTROW:
-        if (f.arg_col < 0 || f.arg_col != a->group_col) return fail(TG_ERR_UNSUPPORTED, "FIRSTROW is offloaded only for the GROUP BY column (deterministic)");
+      case TG_AGG_FIRSTROW: {
+        int gi = -1;
+        for (size_t q = 0; q < a->group_cols.size(); q++) if (a->group_cols[q] == f.arg_col) gi = (int)q;
+        if (f.arg_col < 0 || gi < 0) return fail(TG_ERR_UNSUPPORTED, "FIRSTROW is offloaded only for GROUP BY columns (deterministic)");
         a->out_nullable[k] = !(a->flags[f.arg_col] & TG_FLAG_NOT_NULL);
+        o.arg_col2 = gi | ((a->nkw > (int)a->group_cols.size() ? (int)a->group_cols.size() : 0) << 8);
         break;
+      }
       default: return fail(TG_ERR_UNSUPPORTED, "aggregate function is not offloaded");
     }
   }
@@ -592,14 +706,17 @@ static int agg_setup(AggImpl* a, const tg_agg_desc* d) {
 static void layout_table(AggImpl* a, uint8_t* mem, unsigned long long nslots, AggTable& t) {
   size_t n = (size_t)nslots + 2;
   t.nslots = nslots;
+  t.nkw = a->nkw;
   t.keys = reinterpret_cast<long long*>(mem);
+  t.tags = reinterpret_cast<unsigned long long*>(mem);          // multi-key tables: the tag array takes the place of keys[]
   t.rows = reinterpret_cast<unsigned long long*>(mem + n * 8);
   for (int s = 0; s < a->nstates; s++) t.state[s] = reinterpret_cast<unsigned long long*>(mem + n * 8 * (2 + s));
+  for (int j = 0; j < a->nkw; j++) t.keyw[j] = reinterpret_cast<long long*>(mem + n * 8 * (2 + a->nstates + j));
 }
 
 static int alloc_table(AggImpl* a, unsigned long long nslots, DevBuf& mem, AggTable& t) {
   size_t n = (size_t)nslots + 2;
-  TG_TRY(mem.ensure(a->device, n * 8 * (2 + a->nstates)));
+  TG_TRY(mem.ensure(a->device, n * 8 * (2 + a->nstates + a->nkw)));
   layout_table(a, mem.as<uint8_t>(), nslots, t);
   k_agg_init<<<agrid(a, (int64_t)n), 256, 0, a->stream>>>(t, a->spec, n);
   a->stats.kernel_launches++;
@@ -612,7 +729,8 @@ static int grow_table(AggImpl* a, unsigned long long want_slots) {
   TG_TRY(alloc_table(a, want_slots, *nm, nt));
   unsigned long long* sc = a->scalars.as<unsigned long long>();
   TG_CUDA(cudaMemsetAsync(sc, 0, 8, a->stream));
-  k_agg_rehash<<<agrid(a, (int64_t)a->tbl.nslots + 2), 256, 0, a->stream>>>(a->tbl, nt, a->spec, a->nstates, sc);
+  if (a->nkw) k_agg_rehash_mk<<<agrid(a, (int64_t)a->tbl.nslots), 256, 0, a->stream>>>(a->tbl, nt, a->nstates);
+  else k_agg_rehash<<<agrid(a, (int64_t)a->tbl.nslots + 2), 256, 0, a->stream>>>(a->tbl, nt, a->spec, a->nstates, sc);
   a->stats.kernel_launches++;
   TG_CUDA(cudaStreamSynchronize(a->stream));
   std::swap(a->tbl_mem.p, nm->p); std::swap(a->tbl_mem.cap, nm->cap); std::swap(a->tbl_mem.device, nm->device);
@@ -635,6 +753,128 @@ static int mark_range_deferred(AggImpl* a, int64_t lo, int64_t hi) {
   if (lo < e1) { k_mark_range<<<1, 64, 0, a->stream>>>(bits, lo, e1); a->stats.kernel_launches++; }
   int64_t s2 = std::max<int64_t>(std::max<int64_t>(lo, e1), whi * 32);
   if (s2 < hi) { k_mark_range<<<1, 64, 0, a->stream>>>(bits, s2, hi); a->stats.kernel_launches++; }
+  return TG_OK;
+}
+
+// fold `m` partial-result tuples into the global table, growing it until every tuple found a slot
+static int grow_table(AggImpl* a, unsigned long long want_slots);
+static int merge_partials(AggImpl* a, const AggPartials& pp, unsigned long long m, unsigned long long* sc) {
+  if (m == 0) return TG_OK;
+  DevBuf mdef, mprev;
+  size_t dwords = (size_t)((m + 31) / 32);
+  TG_TRY(mdef.ensure(a->device, dwords * 4 + 16));
+  TG_CUDA(cudaMemsetAsync(mdef.p, 0, dwords * 4, a->stream));
+  TG_CUDA(cudaMemsetAsync(sc + 4, 0, 8, a->stream));
+  const uint32_t* only = nullptr;
+  for (int round = 0; round < 40; round++) {
+    unsigned long long max_fill = 48;   // probe-length limit (see k_agg_update)
+    k_agg_merge<<<agrid(a, (int64_t)m), 256, 0, a->stream>>>(pp, (int64_t)m, a->tbl, a->spec, max_fill, sc, mdef.as<uint32_t>(), only, sc + 4);
+    a->stats.kernel_launches++;
+    unsigned long long nd = 0;
+    TG_CUDA(cudaMemcpyAsync(&nd, sc + 4, 8, cudaMemcpyDeviceToHost, a->stream));
+    TG_CUDA(cudaStreamSynchronize(a->stream));
+    if (nd == 0) break;
+    unsigned long long want = std::max<unsigned long long>(a->nslots * 4, (unsigned long long)((a->nslots * 0.6 + (double)nd) * 2));
+    TG_TRY(grow_table(a, want));
+    TG_TRY(mprev.ensure(a->device, dwords * 4 + 16));
+    TG_CUDA(cudaMemcpyAsync(mprev.p, mdef.p, dwords * 4, cudaMemcpyDeviceToDevice, a->stream));
+    TG_CUDA(cudaMemsetAsync(mdef.p, 0, dwords * 4, a->stream));
+    TG_CUDA(cudaMemsetAsync(sc + 4, 0, 8, a->stream));
+    only = mprev.as<uint32_t>();
+    if (round == 39) return fail(TG_ERR_CUDA, "internal: aggregation merge failed to converge");
+  }
+  return TG_OK;
+}
+
+static void layout_partials(uint8_t* base, size_t cap, int nstates, unsigned long long* count, AggPartials& pp) {
+  pp.keys = reinterpret_cast<long long*>(base); base += cap * 8;
+  pp.rows = reinterpret_cast<unsigned long long*>(base); base += cap * 8;
+  for (int s = 0; s < nstates; s++) { pp.state[s] = reinterpret_cast<unsigned long long*>(base); base += cap * 8; }
+  pp.kind = base;
+  pp.count = count;
+}
+
+// several GROUP BY columns: global tag-claimed table only (k_agg_update_mk), same grow-and-retry protocol
+static int update_grouped_mk(AggImpl* a, const DevCols& cols, int64_t n, unsigned long long* sc) {
+  size_t dwords = (size_t)((n + 31) / 32);
+  TG_TRY(a->deferred.ensure(a->device, dwords * 4 + 16));
+  TG_CUDA(cudaMemsetAsync(a->deferred.p, 0, dwords * 4, a->stream));
+  GroupKeys gk{};
+  gk.n = (int)a->group_cols.size(); gk.nkw = a->nkw;
+  for (int q = 0; q < gk.n; q++) { gk.data[q] = cols.data[a->group_cols[q]]; gk.nulls[q] = cols.nulls[a->group_cols[q]]; gk.kind[q] = a->group_kinds[q]; }
+  DevBuf prev_deferred;
+  const uint32_t* only = nullptr;
+  for (int round = 0; round < 40; round++) {
+    TG_CUDA(cudaMemsetAsync(sc + 1, 0, 8, a->stream));
+    k_agg_update_mk<<<agrid(a, n), 256, 0, a->stream>>>(gk, cols, n, a->tbl, a->spec, 48u, a->deferred.as<uint32_t>(), only, sc + 1);
+    a->stats.kernel_launches++;
+    unsigned long long nd = 0;
+    TG_CUDA(cudaMemcpyAsync(&nd, sc + 1, 8, cudaMemcpyDeviceToHost, a->stream));
+    TG_CUDA(cudaStreamSynchronize(a->stream));
+    if (nd == 0) break;
+    unsigned long long want = std::max<unsigned long long>(a->nslots * 4, (unsigned long long)((a->nslots * 0.6 + (double)nd) * 2));
+    TG_TRY(grow_table(a, want));
+    TG_TRY(prev_deferred.ensure(a->device, dwords * 4 + 16));
+    TG_CUDA(cudaMemcpyAsync(prev_deferred.p, a->deferred.p, dwords * 4, cudaMemcpyDeviceToDevice, a->stream));
+    TG_CUDA(cudaMemsetAsync(a->deferred.p, 0, dwords * 4, a->stream));
+    only = prev_deferred.as<uint32_t>();
+    if (round == 39) return fail(TG_ERR_CUDA, "internal: aggregation table failed to converge");
+  }
+  return TG_OK;
+}
+
+// Round-2 update path (agg_update.cuh): one two-level kernel per round; rows / local groups that found no slot are re-run
+// after the table has grown.
+static int update_grouped_v2(AggImpl* a, const GroupKey& gk, const DevCols& cols, int64_t n, unsigned long long* sc) {
+  size_t dwords = (size_t)((n + 31) / 32);
+  TG_TRY(a->deferred.ensure(a->device, dwords * 4 + 16));
+  TG_CUDA(cudaMemsetAsync(a->deferred.p, 0, dwords * 4, a->stream));
+  // CTA-local level: on for small / unknown cardinalities (a CTA turns it off by itself when its hit rate is low)
+  static int env_local = -1, env_slots = 0;
+  if (env_local < 0) { const char* e = getenv("TG_AGG_LOCAL"); env_local = e ? atoi(e) : 1; const char* s2 = getenv("TG_AGG_LOCAL_SLOTS"); env_slots = s2 ? atoi(s2) : 0; }
+  bool local = env_local != 0 && a->nstates <= AGG_LOCAL_MAX_STATES && (a->expected_groups == 0 || a->expected_groups <= 4096);
+  if (env_local == 2) local = a->nstates <= AGG_LOCAL_MAX_STATES;
+  int local_slots = (env_slots == 512 || env_slots == 1024 || env_slots == 2048 || env_slots == 4096) ? env_slots : 2048;
+  size_t smem = (size_t)(local_slots + 2) * 8 * (2 + a->nstates);
+  while (local && smem > (100u << 10) && local_slots > 512) { local_slots /= 2; smem = (size_t)(local_slots + 2) * 8 * (2 + a->nstates); }
+  int per_sm = local ? (int)std::max<size_t>(1, std::min<size_t>(4, (200u << 10) / smem)) : 8;
+  int grid = (int)std::min<int64_t>((n + AGG2_TILE - 1) / AGG2_TILE, (int64_t)a->nsm * per_sm);
+  if (grid < 1) grid = 1;
+  Agg2Params p{};
+  p.gk = gk; p.n = n; p.max_probe = 48; p.nstates = a->nstates; p.local_slots = local ? local_slots : 0;
+  p.deferred = a->deferred.as<uint32_t>(); p.only = nullptr; p.n_deferred = sc + 1; p.local_rows = sc + 6;
+  if (local) {
+    p.spill_cap = (unsigned long long)grid * (size_t)(local_slots + 2);
+    size_t per = 8 + 8 + 8 * (size_t)a->nstates + 1;
+    TG_TRY(a->partials_mem.ensure(a->device, (size_t)p.spill_cap * per + 256));
+    layout_partials(a->partials_mem.as<uint8_t>(), (size_t)p.spill_cap, a->nstates, sc + 5, p.spill);
+    TG_CUDA(cudaFuncSetAttribute(k_agg_update2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  DevBuf prev_deferred;
+  for (int round = 0; round < 40; round++) {
+    TG_CUDA(cudaMemsetAsync(sc + 1, 0, 8, a->stream));
+    TG_CUDA(cudaMemsetAsync(sc + 5, 0, 8, a->stream));
+    if (local && round == 0) k_agg_update2<true><<<grid, AGG2_BLOCK, smem, a->stream>>>(p, cols, a->tbl, a->spec);
+    else k_agg_update2<false><<<grid, AGG2_BLOCK, 0, a->stream>>>(p, cols, a->tbl, a->spec);
+    a->stats.kernel_launches++;
+    unsigned long long back[8] = {0};
+    TG_CUDA(cudaMemcpyAsync(back, sc, 64, cudaMemcpyDeviceToHost, a->stream));
+    TG_CUDA(cudaStreamSynchronize(a->stream));
+    const unsigned long long nd = back[1], spilled = (local && round == 0) ? back[5] : 0;
+    if (nd == 0 && spilled == 0) break;
+    if (spilled > p.spill_cap) return fail(TG_ERR_CUDA, "internal: aggregation spill buffer overflow");
+    // grow x4 (at least enough for every deferred row / spilled group to be a new group), then re-run just those
+    unsigned long long want = std::max<unsigned long long>(a->nslots * 4, (unsigned long long)((a->nslots * 0.6 + (double)(nd + spilled)) * 2));
+    TG_TRY(grow_table(a, want));
+    p.max_probe = 48;
+    if (spilled) TG_TRY(merge_partials(a, p.spill, spilled, sc));
+    if (nd == 0) break;
+    TG_TRY(prev_deferred.ensure(a->device, dwords * 4 + 16));
+    TG_CUDA(cudaMemcpyAsync(prev_deferred.p, a->deferred.p, dwords * 4, cudaMemcpyDeviceToDevice, a->stream));
+    TG_CUDA(cudaMemsetAsync(a->deferred.p, 0, dwords * 4, a->stream));
+    p.only = prev_deferred.as<uint32_t>();
+    if (round == 39) return fail(TG_ERR_CUDA, "internal: aggregation table failed to converge");
+  }
   return TG_OK;
 }
 
@@ -712,7 +952,25 @@ static int update_device(AggImpl* a, const DevCols& cols, int64_t n) {
     k_agg_update_nogroup<<<agrid(a, n, 256, 4), 256, 0, a->stream>>>(cols, n, a->tbl, a->spec);
     a->stats.kernel_launches++;
   } else {
+    if (a->nkw) {
+      TG_TRY(update_grouped_mk(a, cols, n, sc));
+      TG_CUDA(cudaEventRecord(a->ev1, a->stream));
+      TG_CUDA(cudaStreamSynchronize(a->stream));
+      TG_CUDA(cudaGetLastError());
+      float ms3 = 0; cudaEventElapsedTime(&ms3, a->ev0, a->ev1); a->stats.update_ms += ms3;
+      return TG_OK;
+    }
     GroupKey gk{cols.data[a->group_col], cols.nulls[a->group_col], a->gk_kind, 0};
+    static int v1 = -1;
+    if (v1 < 0) { const char* e = getenv("TG_AGG_V1"); v1 = e ? atoi(e) : 0; }
+    if (!v1) {
+      TG_TRY(update_grouped_v2(a, gk, cols, n, sc));
+      TG_CUDA(cudaEventRecord(a->ev1, a->stream));
+      TG_CUDA(cudaStreamSynchronize(a->stream));
+      TG_CUDA(cudaGetLastError());
+      float ms2 = 0; cudaEventElapsedTime(&ms2, a->ev0, a->ev1); a->stats.update_ms += ms2;
+      return TG_OK;
+    }
     size_t dwords = (size_t)((n + 31) / 32);
     TG_TRY(a->deferred.ensure(a->device, dwords * 4 + 16));
     TG_CUDA(cudaMemsetAsync(a->deferred.p, 0, dwords * 4, a->stream));

@@ -258,7 +258,7 @@ __device__ __forceinline__ bool eval_filter(const DevFilter& f, const DevCols& c
     } else {
       int64_t x = reinterpret_cast<const int64_t*>(c.data[it.lhs_col])[row];
       int64_t y = it.rhs_col >= 0 ? reinterpret_cast<const int64_t*>(c.data[it.rhs_col])[row] : it.const_i64;
-      r = cmp_int(x, it.lhs_unsigned != 0, y, false);
+      r = cmp_int(x, it.lhs_unsigned != 0, y, it.rhs_unsigned != 0);
     }
     if (!apply_cmp(it.op, r)) return false;
   }

@@ -111,6 +111,9 @@ struct JoinImpl {
   int n_out = 0;
   std::vector<int> out_elem;
   KeySpec build_key{}, probe_key{};   // data pointers filled per launch
+  std::vector<tg_other_item> other;   // OtherCondition (sides already mapped: 0 = probe child, 1 = build child)
+  std::vector<int> other_build_cols;  // build columns it reads (kept in the row store although they may not be output)
+  DevOther dev_other{};               // compiled after the build (row-store word of every build operand)
 
   // build state
   HostStage bstage;
@@ -182,9 +185,14 @@ static bool key_unsigned(int tp, uint32_t flag) {
 static int check_filter(const Side& s, const tg_filter_item* items, int n, DevFilter& out) {
   if (n < 0 || n > TG_MAX_FILTER) return fail(TG_ERR_UNSUPPORTED, "at most 8 CNF filter items are offloaded");
   out.n = n;
+  if (n > 0 && !items) return fail(TG_ERR_INVALID, "filter items are NULL");
   for (int i = 0; i < n; i++) {
     const tg_filter_item& it = items[i];
     if (it.lhs_col < 0 || it.lhs_col >= s.ncols || it.rhs_col >= s.ncols) return fail(TG_ERR_INVALID, "filter column out of range");
+    // the compare family must fit the column types: a real compare on integer columns (or the reverse) would reinterpret bits
+    const bool lreal = s.types[it.lhs_col] == TG_TYPE_DOUBLE;
+    if ((it.is_real != 0) != lreal || (it.rhs_col >= 0 && (s.types[it.rhs_col] == TG_TYPE_DOUBLE) != lreal))
+      return fail(TG_ERR_UNSUPPORTED, "filter compares columns of different families (the planner casts before the filter)");
     if (s.elem[it.lhs_col] != 8 || (it.rhs_col >= 0 && s.elem[it.rhs_col] != 8))
       return fail(TG_ERR_UNSUPPORTED, "filters are offloaded on 8-byte columns only");
     if (it.op < TG_CMP_LT || it.op > TG_CMP_NE) return fail(TG_ERR_INVALID, "bad filter op");
@@ -243,6 +251,35 @@ static int setup(JoinImpl* j, const tg_join_desc* d) {
   j->probe = brt ? left : right;
   TG_TRY(check_filter(j->build, d->build_filter, d->n_build_filter, j->build.filter));
   TG_TRY(check_filter(j->probe, d->probe_filter, d->n_probe_filter, j->probe.filter));
+  // OtherCondition (inner_join_probe.go:72-79): sides re-mapped to probe (0) / build (1)
+  j->other.clear(); j->other_build_cols.clear();
+  if (d->n_other_cond < 0 || d->n_other_cond > TG_MAX_OTHER) return fail(TG_ERR_UNSUPPORTED, "at most 8 OtherCondition items are offloaded");
+  if (d->n_other_cond > 0) {
+    if (!d->other_cond) return fail(TG_ERR_INVALID, "other_cond is NULL");
+    if (j->need_scan || j->probe_kind == PK_MARK_ONLY) return fail(TG_ERR_UNSUPPORTED, "OtherCondition with a build-side scan (outer side / left side is the build side) is not offloaded");
+    if (j->has_flag_col) return fail(TG_ERR_UNSUPPORTED, "OtherCondition on left outer semi joins (NULL-aware match flag) is not offloaded");
+    for (int i = 0; i < d->n_other_cond; i++) {
+      tg_other_item it = d->other_cond[i];
+      if (it.op < TG_CMP_LT || it.op > TG_CMP_NE) return fail(TG_ERR_INVALID, "bad OtherCondition op");
+      auto remap = [&](int32_t& side, int32_t col, bool may_be_const) -> int {
+        if (side < 0) return may_be_const ? TG_OK : fail(TG_ERR_INVALID, "OtherCondition: the left operand must be a column");
+        if (side > 1) return fail(TG_ERR_INVALID, "OtherCondition side must be 0 (left) or 1 (right)");
+        const Side& sd = side == 0 ? left : right;
+        if (col < 0 || col >= sd.ncols) return fail(TG_ERR_INVALID, "OtherCondition column out of range");
+        if (sd.elem[col] != 8) return fail(TG_ERR_UNSUPPORTED, "OtherCondition is offloaded on 8-byte columns only");
+        if ((sd.types[col] == TG_TYPE_DOUBLE) != (it.is_real != 0)) return fail(TG_ERR_UNSUPPORTED, "OtherCondition compares columns of different families (the planner casts first)");
+        const bool is_build = (side == 1) == brt;
+        Side& mine = is_build ? j->build : j->probe;
+        mine.needed[col] = 1;
+        if (is_build && std::find(j->other_build_cols.begin(), j->other_build_cols.end(), col) == j->other_build_cols.end()) j->other_build_cols.push_back(col);
+        side = is_build ? 1 : 0;
+        return TG_OK;
+      };
+      TG_TRY(remap(it.lhs_side, it.lhs_col, false));
+      TG_TRY(remap(it.rhs_side, it.rhs_col, true));
+      j->other.push_back(it);
+    }
+  }
   for (Side* s : {&j->build, &j->probe}) {
     s->needed[s->key_col] = 1;
     for (int c : s->used) {
@@ -450,7 +487,7 @@ static int build_table(JoinImpl* j) {
   std::vector<int> payload;   // used build columns other than the key
   bool key_out = false;
   for (int c : b.used) { if (c == b.key_col) key_out = true; else if (std::find(payload.begin(), payload.end(), c) == payload.end()) payload.push_back(c); }
-  bool u1 = host_sc[1] <= 1 && !j->need_scan && payload.size() <= 1 && (!key_out || j->build_key.kind == KEY_I64);
+  bool u1 = host_sc[1] <= 1 && !j->need_scan && payload.size() <= 1 && (!key_out || j->build_key.kind == KEY_I64) && j->other.empty();
   if (u1 && payload.size() == 1) {
     int pc = payload[0];
     if (b.elem[pc] != 8 || j->bcols.has_nulls[pc]) u1 = false;
@@ -471,6 +508,7 @@ static int build_table(JoinImpl* j) {
     bool any_nullable = false;
     std::vector<int> cols;
     for (int c : b.used) if (std::find(cols.begin(), cols.end(), c) == cols.end()) cols.push_back(c);
+    for (int c : j->other_build_cols) if (std::find(cols.begin(), cols.end(), c) == cols.end()) cols.push_back(c);   // read by OtherCondition only
     if ((int)cols.size() + 1 > TG_MAX_COLS) return fail(TG_ERR_UNSUPPORTED, "too many build columns");
     for (int c : cols) {
       rs.col[w] = c; rs.elem_len[w] = b.elem[c];
@@ -495,6 +533,23 @@ static int build_table(JoinImpl* j) {
     j->tv.rows = j->rows_store.as<unsigned long long>();
     j->tv.row_words = rs.nwords;
     j->tv.null_word = rs.null_word;
+    // compile OtherCondition against the row store
+    j->dev_other = DevOther{};
+    j->dev_other.n = (int)j->other.size();
+    for (size_t q = 0; q < j->other.size(); q++) {
+      const tg_other_item& it = j->other[q];
+      OtherItemDev& o = j->dev_other.it[q];
+      o.op = it.op; o.is_real = it.is_real; o.l_unsigned = it.lhs_unsigned; o.r_unsigned = it.rhs_unsigned;
+      o.const_i64 = it.const_i64; o.const_f64 = it.const_f64;
+      auto operand = [&](int side, int col, int32_t& src, int32_t& idx, int32_t& nbit) {
+        nbit = -1;
+        if (side < 0) { src = OSRC_CONST; idx = 0; }
+        else if (side == 0) { src = OSRC_PROBE; idx = col; }
+        else { src = OSRC_BUILD; idx = j->build_word_of_col[col]; nbit = rs.null_bit[idx]; }
+      };
+      operand(it.lhs_side, it.lhs_col, o.l_src, o.l_idx, o.l_null_bit);
+      operand(it.rhs_side, it.rhs_col, o.r_src, o.r_idx, o.r_null_bit);
+    }
   }
   if (j->need_scan) {
     TG_TRY(j->slot_used.ensure(j->device, (size_t)nslots + 1));
@@ -608,7 +663,7 @@ static ProbeTuning probe_tuning() {
   t.part_min_mb = env_int("TG_PROBE_PART_MIN_MB", 64);
   t.part_min_rows = env_int("TG_PROBE_PART_MIN_ROWS", 1 << 22);
   t.seg_vec = env_int("TG_PROBE_SEG_VEC", 1);            // 128-bit loads/stores in the segment probe
-  t.seg_lean = env_int("TG_PROBE_SEG_LEAN", 0);          // EXPERIMENTAL: 1 = lean full-tile path, 2 = + register prefetch (round-2 A/B)
+  t.seg_lean = env_int("TG_PROBE_SEG_LEAN", 1);          // 1 = lean full-tile path (default: 1.954 vs 2.089 ms per step, profiles/r2_sweep_probe.jsonl), 0 = round-1 kernel, 2 = + register prefetch (2.01 ms)
   t.carveout = env_int("TG_PROBE_CARVEOUT", -1);         // EXPERIMENTAL: preferred shared-memory carve-out (%) of the segment probe kernels, -1 = driver default
   t.tma = env_int("TG_PROBE_TMA", 0);               // TMA-fed kernels (cp.async.bulk ring) for the streamed inputs
   t.stages = env_int("TG_PROBE_STAGES", 4);
@@ -685,7 +740,7 @@ struct LaunchSeg {
     int64_t ctas = (n / 128 + 7) / 8;
     int per_sm = t.ctas_per_sm > 0 ? t.ctas_per_sm : resident;
     int grid = (int)std::min<int64_t>(ctas, (int64_t)j->nsm * per_sm);
-    if (t.seg_lean && j->tv.pair_home) {   // experimental lean variants (see join_kernels.cuh); 3 CTAs per SM as well
+    if (t.seg_lean && j->tv.pair_home) {   // lean variants (see join_kernels.cuh); 3 CTAs per SM as well
       if (t.carveout >= 0) {
         cudaFuncSetAttribute(k_probe_inner_u1_seg_lean<NPC, NKD, NMD, false>, cudaFuncAttributePreferredSharedMemoryCarveout, t.carveout);
         cudaFuncSetAttribute(k_probe_inner_u1_seg_lean<NPC, NKD, NMD, true>, cudaFuncAttributePreferredSharedMemoryCarveout, t.carveout);
@@ -795,15 +850,11 @@ static int probe_device(JoinImpl* j, const DevCols& pview, int64_t n, ResultBatc
             // number of rows fall back to the 8-byte kernel
             if (tune.seg_vec && (rb.rows & 1) == 0) TG_TRY(launch_probe_seg(j, j->part_cols[0]->as<int64_t>(), (int64_t)P * C, pf, cur, tune, SegSpec{cursors, (uint32_t)(C / 128), 0, C, flag}));
             else TG_TRY(launch_probe_warp(j, j->part_cols[0]->as<int64_t>(), (int64_t)P * C, pf, cur, tune, SegSpec{cursors, (uint32_t)(C / 128), 0, C, flag}));
-            TG_TRY(launch_probe_warp(j, pkey, n_main, fo, cur, tune,
-                                     in_seg ? SegSpec{in_seg->cnt, in_seg->tiles_per_seg, 1, in_seg->cap, flag} : SegSpec{nullptr, 0, 1, 0, flag}));   // runs only after an overflow
+            // gated fallback: probes the ORIGINAL input only after an overflow; the < 1024-row tail the scatter left behind
+            // (dense input only) rides on the same launch — it is probed whatever the flag says
+            if (in_seg) TG_TRY(launch_probe_warp(j, pkey, n_main, fo, cur, tune, SegSpec{in_seg->cnt, in_seg->tiles_per_seg, 1, in_seg->cap, flag, 0}));
+            else TG_TRY(launch_probe_warp(j, pkey, n, fo, cur, tune, SegSpec{nullptr, 0, 1, 0, flag, n_main < n ? n_main : 0}));
             j->stats.kernel_launches += 3;
-            if (n_main < n) {
-              FastOut tail = fo;
-              for (int c = 0; c < fo.n_pcols; c++) tail.psrc[c] = fo.psrc[c] + n_main;
-              TG_TRY(launch_probe_warp(j, pkey + n_main, n - n_main, tail, cur, tune));
-              j->stats.kernel_launches++;
-            }
             partitioned = true;
           }
         }
@@ -889,7 +940,7 @@ static int probe_device(JoinImpl* j, const DevCols& pview, int64_t n, ResultBatc
     sks.data = sub.data[p.key_col]; sks.nulls = sub.nulls[p.key_col];
     TG_TRY(j->tmp_cnt.ensure(j->device, (size_t)(m + 1) * 4));
     TG_TRY(j->tmp_slot.ensure(j->device, (size_t)(m + 1) * 4));
-    k_probe_count<<<grid_for(j, m, 256, 8), 256, 0, j->stream>>>(sks, sub, p.filter, m, j->tv, j->probe_kind, j->tmp_cnt.as<uint32_t>(),
+    k_probe_count<<<grid_for(j, m, 256, 8), 256, 0, j->stream>>>(sks, sub, p.filter, j->dev_other, m, j->tv, j->probe_kind, j->tmp_cnt.as<uint32_t>(),
                                                                  j->tmp_slot.as<uint32_t>(), j->need_scan ? j->slot_used.as<uint8_t>() : nullptr);
     j->stats.kernel_launches++;
     unsigned long long total = 0;
@@ -908,7 +959,7 @@ static int probe_device(JoinImpl* j, const DevCols& pview, int64_t n, ResultBatc
       }
       k_probe_write<<<grid_for(j, m, 256, 8), 256, 0, j->stream>>>(m, j->tmp_off.as<unsigned long long>(), j->tmp_slot.as<uint32_t>(),
                                                                    reinterpret_cast<const int64_t*>(sks.data), sks, j->tv, sub, oc, j->probe_kind,
-                                                                   (unsigned long long)rb.rows);
+                                                                   (unsigned long long)rb.rows, j->dev_other);
       j->stats.kernel_launches++;
       rb.rows += (int64_t)total;
       j->stats.output_rows += (int64_t)total;

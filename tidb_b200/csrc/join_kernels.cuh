@@ -81,6 +81,18 @@ struct RowSpec {
   int32_t null_bit[TG_MAX_COLS];
 };
 
+// OtherCondition compiled for the probe kernels: operands are probe columns, words of the build row store, or a constant
+enum { OSRC_PROBE = 0, OSRC_BUILD = 1, OSRC_CONST = 2 };
+#define TG_MAX_OTHER 8
+struct OtherItemDev {
+  int32_t op, is_real;
+  int32_t l_src, l_idx, l_null_bit, l_unsigned;
+  int32_t r_src, r_idx, r_null_bit, r_unsigned;
+  int64_t const_i64;
+  double const_f64;
+};
+struct DevOther { int32_t n, pad; OtherItemDev it[TG_MAX_OTHER]; };
+
 // join kinds as the probe kernels see them
 enum {
   PK_INNER = 0,            // emit cnt rows per probe row (also outer join whose OUTER side is the build side)
@@ -483,6 +495,9 @@ struct SegSpec {
   int32_t gate_want;                 // run iff (*gate != 0) == gate_want
   long long cap;
   const unsigned long long* gate;    // nullptr = unconditional
+  long long ungated_from;            // k_probe_inner_u1_w, dense input: when the gate says "do not run", rows >= ungated_from
+                                     // (a multiple of 128) are probed all the same — the < 1024-row tail the partition pass
+                                     // leaves behind rides on the gated fallback launch instead of costing a launch of its own
 };
 
 // warp-autonomous: no shared memory, no block barrier; each warp owns tiles of 32×R rows.
@@ -492,13 +507,17 @@ template <int R, int NPC, int NKD, int NMD>
 __global__ void __launch_bounds__(256)
 k_probe_inner_u1_w(const int64_t* __restrict__ pkey, int64_t n, TableView t, FastOut out,
                    unsigned long long* __restrict__ out_cursor, SegSpec seg) {
-  if (seg.gate && ((*seg.gate != 0ull) != (seg.gate_want != 0))) return;
+  const int64_t tile_rows = 32 * R;
+  int64_t first_tile = 0;
+  if (seg.gate && ((*seg.gate != 0ull) != (seg.gate_want != 0))) {
+    if (seg.ungated_from <= 0 || seg.cnt) return;
+    first_tile = seg.ungated_from / tile_rows;
+  }
   const int lane = threadIdx.x & 31;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int64_t tile_rows = 32 * R;
   const int64_t ntiles = (n + tile_rows - 1) / tile_rows;
-  for (int64_t tile = warp_id; tile < ntiles; tile += warps_total) {
+  for (int64_t tile = first_tile + warp_id; tile < ntiles; tile += warps_total) {
     const int64_t base = tile * tile_rows;
     int64_t limit = n;
     if (seg.cnt) {
@@ -589,8 +608,8 @@ k_probe_inner_u1_seg(const int64_t* __restrict__ pkey, int64_t n, TableView t, F
 }
 
 // ---------------------------------------------------------------------------------------------
-// EXPERIMENTAL (TG_PROBE_SEG_LEAN=1|2, off by default; measured in tools/scratch/probe_lab.cu as P2b / P6, not yet on the
-// library's data): the same segment probe with a lean full-tile path — no per-row `in` flags, no slot array, sentinel-valued
+// DEFAULT since round 2 (TG_PROBE_SEG_LEAN=1; 0 = the kernel above, 2 = + register prefetch; measured on the library's data:
+// step 2.089 -> 1.954 ms, profiles/r2_sweep_probe.jsonl): the same segment probe with a lean full-tile path — no per-row `in` flags, no slot array, sentinel-valued
 // keys detected once per tile (then the tile takes the generic path) — and, with PREFETCH, the next tile's keys/payloads
 // requested before the current tile's gathers are issued.  ncu: the production kernel executes 551 M warp instructions per
 // 100 M rows, the lab kernel 351 M.
@@ -798,11 +817,42 @@ k_probe_inner_u1_tma(const int64_t* __restrict__ pkey, int64_t ntiles, TableView
   }
 }
 
+// OtherCondition on ONE candidate pair (probe row i, build row `brow` of the row store): true iff every CNF item is
+// non-NULL true (expression.VectorizedFilter over the joined chunk, inner_join_probe.go:72-79)
+__device__ __forceinline__ bool other_operand(const OtherItemDev& it, bool lhs, const DevCols& pcols, int64_t i, const unsigned long long* brow,
+                                              int null_word, unsigned long long& raw) {
+  const int src = lhs ? it.l_src : it.r_src, idx = lhs ? it.l_idx : it.r_idx, nbit = lhs ? it.l_null_bit : it.r_null_bit;
+  if (src == OSRC_PROBE) {
+    const uint8_t* nb = pcols.nulls[idx];
+    if (nb && !bit_not_null(nb, i)) return false;
+    raw = reinterpret_cast<const unsigned long long*>(pcols.data[idx])[i];
+    return true;
+  }
+  if (src == OSRC_BUILD) {
+    if (nbit >= 0 && ((brow[null_word] >> nbit) & 1ull)) return false;
+    raw = brow[idx];
+    return true;
+  }
+  raw = it.is_real ? (unsigned long long)__double_as_longlong(it.const_f64) : (unsigned long long)it.const_i64;
+  return true;
+}
+__device__ __forceinline__ bool eval_other(const DevOther& o, const DevCols& pcols, int64_t i, const unsigned long long* brow, int null_word) {
+  for (int q = 0; q < o.n; q++) {
+    const OtherItemDev& it = o.it[q];
+    unsigned long long a, b;
+    if (!other_operand(it, true, pcols, i, brow, null_word, a) || !other_operand(it, false, pcols, i, brow, null_word, b)) return false;
+    int r = it.is_real ? cmp_real(__longlong_as_double((long long)a), __longlong_as_double((long long)b))
+                       : cmp_int((int64_t)a, it.l_unsigned != 0, (int64_t)b, it.r_unsigned != 0);
+    if (!apply_cmp(it.op, r)) return false;
+  }
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // probe — general path (any join type, NULLs, filters, duplicates): count → scan → write
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_probe_count(KeySpec key, DevCols pcols, DevFilter filt, int64_t n, TableView t, int kind,
+k_probe_count(KeySpec key, DevCols pcols, DevFilter filt, DevOther oth, int64_t n, TableView t, int kind,
               uint32_t* __restrict__ row_cnt, uint32_t* __restrict__ row_slot, uint8_t* slot_used) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -815,6 +865,12 @@ k_probe_count(KeySpec key, DevCols pcols, DevFilter filt, int64_t n, TableView t
     if (valid) s = table_find(t, k, &meta);
     uint32_t cnt = 0;
     if (s != kInvalidSlot) cnt = t.mode == TABLE_U1 ? 1u : (uint32_t)(meta & kCntMask);
+    if (oth.n && cnt) {   // OtherCondition: only the candidate pairs that pass it count (host forces mode G when it is present)
+      const unsigned long long roff = meta >> 28;
+      uint32_t pass = 0;
+      for (uint32_t r = 0; r < cnt; r++) pass += eval_other(oth, pcols, i, t.rows + (roff + r) * t.row_words, t.null_word) ? 1u : 0u;
+      cnt = pass;
+    }
     bool matched = cnt > 0;
     if (slot_used && matched) slot_used[s] = 1;
     uint32_t c;
@@ -912,7 +968,7 @@ __device__ __forceinline__ void store_out(const OutCols& out, int c, unsigned lo
 __global__ void __launch_bounds__(256)
 k_probe_write(int64_t n, const unsigned long long* __restrict__ off, const uint32_t* __restrict__ row_slot,
               const int64_t* __restrict__ pkey_i64, KeySpec key, TableView t, DevCols pcols, OutCols out, int kind,
-              unsigned long long out_base) {
+              unsigned long long out_base, DevOther oth) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -925,9 +981,13 @@ k_probe_write(int64_t n, const unsigned long long* __restrict__ off, const uint3
     unsigned long long roff = meta >> 28;
     int64_t k = 0;
     if (matched) load_key(key, i, k);
+    // with an OtherCondition the c emitted rows are the PASSING ones among the key's (meta & kCntMask) candidates
+    unsigned long long cand = 0;
     for (unsigned long long r = 0; r < c; r++) {
       unsigned long long o = o0 + r;
-      const unsigned long long* brow = (matched && t.mode == TABLE_G) ? t.rows + (roff + r) * t.row_words : nullptr;
+      if (oth.n && matched) { while (!eval_other(oth, pcols, i, t.rows + (roff + cand) * t.row_words, t.null_word)) cand++; }
+      const unsigned long long* brow = (matched && t.mode == TABLE_G) ? t.rows + (roff + (oth.n ? cand : r)) * t.row_words : nullptr;
+      cand++;
       for (int cc = 0; cc < out.n; cc++) {
         const OutSpec sp = out.spec[cc];
         unsigned long long val = 0;

@@ -207,6 +207,164 @@ class HashAggExec(Executor):
         super().close()
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# SelectionExec / ProjectionExec: the two operators that call the VecEval layer around joins and aggregates
+# ---------------------------------------------------------------------------------------------------------------
+def _concat_chunks(chunks: Sequence[Chunk]) -> Chunk:
+    """child chunks -> one dense chunk (sel vectors applied), the batch a device call works on"""
+    cols = []
+    for c in range(chunks[0].num_cols()):
+        vals, nls, any_null = [], [], False
+        for ck in chunks:
+            col = ck.columns[c]
+            idx = ck.sel if ck.sel is not None else slice(None)
+            vals.append(col.data[idx])
+            nl = col.nulls()[idx]
+            any_null |= bool(nl.any())
+            nls.append(nl)
+        cols.append(Column(np.concatenate(vals), np.concatenate(nls) if any_null else None))
+    return Chunk(cols)
+
+
+class SelectionExec(Executor):
+    """GPU replacement of executor.SelectionExec (pkg/executor/select.go:746-785): pulls child chunks, evaluates the
+    CNF filter list with expression.VectorizedFilter semantics (chunk_executor.go:413: a row is selected iff every item is
+    non-NULL true) on the device (tg_vec_filter) and hands the selected rows on, at most `required_rows` per Next.
+    Child chunks are batched (`batch_rows`) so that one launch filters many 1024-row chunks."""
+
+    def __init__(self, child: Executor, filters: Sequence, device: int = 0, batch_rows: int = 64 * MAX_CHUNK_SIZE):
+        super().__init__(child.schema, [child])
+        self.filters, self.device, self.batch_rows = list(filters), device, batch_rows
+        self._lib = None
+        self._pending: List[Chunk] = []     # selected rows not handed out yet
+        self._eof = False
+        self.launches = 0
+
+    def open(self) -> None:
+        super().open()
+        self._lib = abi.load_lib()
+        if self._lib.tg_device_count() <= 0:
+            raise RuntimeError("SelectionExec: no CUDA device (the GPU operators have no CPU fallback)")
+        self._pending, self._eof = [], False
+
+    def _fill(self) -> None:
+        from .plan import filter_array
+        batch, rows = [], 0
+        while rows < self.batch_rows:
+            chk = self.children[0].next(MAX_CHUNK_SIZE)
+            if chk.num_rows() == 0:
+                self._eof = True
+                break
+            batch.append(chk); rows += chk.num_rows()
+        if not batch:
+            return
+        dense = _concat_chunks(batch)
+        n = dense.num_rows()
+        selected = np.zeros(n, dtype=np.uint8)
+        nsel = C.c_int64(0)
+        cs = dense.to_struct()
+        arr = filter_array(self.filters)
+        abi.check(self._lib.tg_vec_filter(self.device, 0, C.byref(cs), arr, len(self.filters), selected.ctypes.data_as(C.c_void_p), C.byref(nsel), None))
+        self.launches += 1
+        keep = selected.astype(bool)
+        assert int(keep.sum()) == nsel.value
+        if nsel.value:
+            self._pending.append(Chunk([Column(c.data[keep], c.nulls()[keep] if c.nulls().any() else None) for c in dense.columns]))
+
+    def next(self, required_rows: int = MAX_CHUNK_SIZE) -> Chunk:
+        while not self._pending and not self._eof:
+            self._fill()
+        if not self._pending:
+            return self.empty_chunk()
+        head = self._pending[0]
+        if head.num_rows() <= required_rows:
+            self._pending.pop(0)
+            return head
+        out = Chunk([Column(c.data[:required_rows], c.nulls()[:required_rows] if c.nulls().any() else None) for c in head.columns])
+        self._pending[0] = Chunk([Column(c.data[required_rows:], c.nulls()[required_rows:] if c.nulls().any() else None) for c in head.columns])
+        return out
+
+
+class ProjectionExec(Executor):
+    """GPU replacement of executor.ProjectionExec (pkg/executor/projection.go:450-483 -> EvaluatorSuite.Run,
+    expression/evaluator.go:128): plain column references are passed through (the reference SWAPS them, ColumnSwapHelper),
+    scalar functions are evaluated column-at-a-time by the VecEval kernels (tg_vec_arith_* / tg_vec_compare_*), constants
+    are scalars (the reference materialises them as columns, vectorized.go:23).  Errors keep the reference's meaning:
+    overflow on a non-NULL row fails the Next call (types.ErrOverflow <-> TG_ERR_OVERFLOW)."""
+
+    def __init__(self, child: Executor, exprs: Sequence, device: int = 0, batch_rows: int = 64 * MAX_CHUNK_SIZE):
+        from .plan import Expr
+        self.exprs = list(exprs)
+        super().__init__([e.ret_type(child.schema) for e in self.exprs], [child])
+        self.device, self.batch_rows = device, batch_rows
+        self._lib = None
+        self._pending: List[Chunk] = []
+        self._eof = False
+        self.launches = 0
+
+    def open(self) -> None:
+        super().open()
+        self._lib = abi.load_lib()
+        if self._lib.tg_device_count() <= 0:
+            raise RuntimeError("ProjectionExec: no CUDA device (the GPU operators have no CPU fallback)")
+        self._pending, self._eof = [], False
+
+    def _eval(self, e, chk: Chunk) -> Column:
+        from .plan import ColRef, Const, ScalarFunc
+        if isinstance(e, ColRef):
+            return chk.columns[e.idx]
+        if isinstance(e, Const):
+            raise abi.TgError(abi.TG_ERR_UNSUPPORTED, "a bare constant projection is not offloaded")
+        assert isinstance(e, ScalarFunc)
+        a, b = e.args
+        n = chk.num_rows()
+        if isinstance(a, Const):
+            raise abi.TgError(abi.TG_ERR_UNSUPPORTED, "constant on the left of a scalar function is not offloaded (the planner folds or swaps it)")
+        ca = self._eval(a, chk)
+        cb = None if isinstance(b, Const) else self._eval(b, chk)
+        real = e.is_real
+        res = np.zeros(n, dtype=np.float64 if (real and e.kind == "arith") else np.int64)
+        nulls = np.zeros((n + 7) // 8, dtype=np.uint8)
+        sa = ca.to_struct(); sb = cb.to_struct() if cb is not None else None
+        pb = C.byref(sb) if sb is not None else None
+        rp, np_ = res.ctypes.data_as(C.c_void_p), nulls.ctypes.data_as(C.c_void_p)
+        k = b.value if isinstance(b, Const) else 0
+        if e.kind == "arith" and real:
+            rc = self._lib.tg_vec_arith_real(self.device, 0, e.op, C.byref(sa), pb, C.c_double(float(k)), rp, np_, None)
+        elif e.kind == "arith":
+            rc = self._lib.tg_vec_arith_int(self.device, 0, e.op, int(e.a_unsigned), int(e.b_unsigned), C.byref(sa), pb, C.c_int64(int(k)), rp, np_, None)
+        elif real:
+            rc = self._lib.tg_vec_compare_real(self.device, 0, e.op, C.byref(sa), pb, C.c_double(float(k)), rp, np_, None)
+        else:
+            rc = self._lib.tg_vec_compare_int(self.device, 0, e.op, int(e.a_unsigned), int(e.b_unsigned), C.byref(sa), pb, C.c_int64(int(k)), rp, np_, None)
+        abi.check(rc)
+        self.launches += 1
+        isnull = np.unpackbits(nulls, bitorder="little")[:n] == 0
+        return Column(res, isnull if isnull.any() else None)
+
+    def next(self, required_rows: int = MAX_CHUNK_SIZE) -> Chunk:
+        while not self._pending and not self._eof:
+            batch, rows = [], 0
+            while rows < self.batch_rows:
+                chk = self.children[0].next(MAX_CHUNK_SIZE)
+                if chk.num_rows() == 0:
+                    self._eof = True
+                    break
+                batch.append(chk); rows += chk.num_rows()
+            if batch:
+                dense = _concat_chunks(batch)
+                self._pending.append(Chunk([self._eval(e, dense) for e in self.exprs]))
+        if not self._pending:
+            return self.empty_chunk()
+        head = self._pending[0]
+        if head.num_rows() <= required_rows:
+            self._pending.pop(0)
+            return head
+        out = Chunk([Column(c.data[:required_rows], c.nulls()[:required_rows] if c.nulls().any() else None) for c in head.columns])
+        self._pending[0] = Chunk([Column(c.data[required_rows:], c.nulls()[required_rows:] if c.nulls().any() else None) for c in head.columns])
+        return out
+
+
 def drain(e: Executor, required_rows: int = MAX_CHUNK_SIZE) -> List[Chunk]:
     """open → next until EOF → close, like the reference's test helpers."""
     e.open()

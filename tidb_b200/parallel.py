@@ -473,6 +473,7 @@ class MailboxExchange:
         self.sets = 2
         self.sent_steps = 0
         self.recv_steps = 0
+        self.last_transfer = None    # event: the most recent step's transfer has been handed to the peers (dma mode)
         self.launches = 0
         lib = self.lib
         self.sent = [torch.zeros(self.SLOTS, dtype=torch.int64, device=self.dev) for _ in range(self.sets)]
@@ -547,13 +548,18 @@ class MailboxExchange:
         a.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
         return self.torch.as_tensor(a, device=self.dev)
 
-    def send(self, key, cols):
-        """enqueue step k's repartition + transfer + count publication on the exchange stream; cols[0] must be `key`"""
+    def send(self, key, cols, compute_stream=None):
+        """enqueue step k's repartition + transfer + count publication; cols[0] must be `key`.
+        The SM kernel (regroup / scatter) goes on `compute_stream` (default: the exchange stream given to the constructor).
+        Putting it on the SAME stream as the probe keeps the shared-memory-heavy scatter and the L1-hungry probe kernel
+        from ever sharing an SM (profiles/r1_probe_lab.md: the probe runs 2.3x slower under a large carve-out); with
+        dma=True the NVLink transfer then overlaps the probe on the copy engines."""
         lib, abi, torch = self.lib, self.abi, self.torch
         k = self.sent_steps
         self.sent_steps += 1
         s_, epoch = k % self.sets, k + 1
-        X = C.c_void_p(self.stream.cuda_stream)
+        cs_ = compute_stream if compute_stream is not None else self.stream
+        X = C.c_void_p(cs_.cuda_stream)
         src_p = (C.c_void_p * len(cols))(*[c.data_ptr() for c in cols])
         err = C.c_void_p(self.errflag.data_ptr())
         if not self.dma:
@@ -566,17 +572,24 @@ class MailboxExchange:
             self.launches += 4 if k >= self.sets else 3
             return
         D = self.dstream
-        with torch.cuda.stream(self.stream):
+        with torch.cuda.stream(cs_):
             if self.staged_free[s_] is not None:
-                self.stream.wait_event(self.staged_free[s_])      # the copies of step k-2 have left staging set s_
-            if k >= self.sets:   # own rows go straight into the own receive set: the own probe of step k-2 must be done
+                cs_.wait_event(self.staged_free[s_])      # the copies of step k-2 have left staging set s_
+            if k >= self.sets and cs_ is self.stream:
+                # own rows go straight into the own receive set: the own probe of step k-2 must be done.  (On the probe's own
+                # stream that is stream order; on a separate exchange stream it is the ACK mailbox, which includes this rank.)
                 abi.check(lib.tg_mail_wait(self.device, C.c_void_p(self._mail(self.KIND_ACK, s_)), self.world, C.c_int64(epoch - self.sets), None, err, C.c_int64(self.timeout_ms), X))
             abi.check(lib.tg_partition_exchange_cf_ex(self.device, C.c_void_p(key.data_ptr()), C.c_int64(key.numel()), self.world, len(cols), src_p,
                                                       self.stage_arr[s_], C.c_int64(self.rank * self.cap), C.c_int64(self.cap),
                                                       C.c_void_p(self.sent[s_].data_ptr()), C.c_void_p(self.overflow.data_ptr()), C.c_int32(self.ctas_per_sm), X))
-            regrouped = torch.cuda.Event(); regrouped.record(self.stream)
+            regrouped = torch.cuda.Event(); regrouped.record(cs_)
+        with torch.cuda.stream(D):
+            D.wait_event(regrouped)
+            if k >= self.sets:   # the peers have finished probing the step that used the receive set the copies overwrite
+                abi.check(lib.tg_mail_wait(self.device, C.c_void_p(self._mail(self.KIND_ACK, s_)), self.world, C.c_int64(epoch - self.sets), None, err, C.c_int64(self.timeout_ms), C.c_void_p(D.cuda_stream)))
+            ready = torch.cuda.Event(); ready.record(D)
         for cs in self.copy_streams:
-            cs.wait_event(regrouped)
+            cs.wait_event(ready)
         for i in range(1, self.world):
             p = (self.rank + i) % self.world      # ring order spreads the peers' NVLink ingress
             cs = self.copy_streams[(i - 1) % len(self.copy_streams)]
@@ -589,6 +602,7 @@ class MailboxExchange:
             abi.check(lib.tg_mail_signal(self.device, C.byref(self.targets[(self.KIND_COUNT, s_)]), C.c_void_p(self.sent[s_].data_ptr()), C.c_int64(epoch), C.c_void_p(D.cuda_stream)))
             done = torch.cuda.Event(); done.record(D)
             self.staged_free[s_] = done
+            self.last_transfer = done
         self.launches += 4 if k >= self.sets else 3
 
     def recv(self, probe_stream):

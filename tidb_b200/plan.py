@@ -48,11 +48,13 @@ class FilterItem:
     lhs_unsigned: bool = False
     const_i64: int = 0
     const_f64: float = 0.0
+    rhs_unsigned: bool = False
 
     def to_struct(self) -> abi.TgFilterItem:
         s = abi.TgFilterItem()
         s.op, s.lhs_col, s.rhs_col = self.op, self.lhs_col, self.rhs_col
         s.is_real, s.lhs_unsigned = int(self.is_real), int(self.lhs_unsigned)
+        s.rhs_unsigned = int(self.rhs_unsigned)
         s.const_i64, s.const_f64 = self.const_i64, self.const_f64
         return s
 
@@ -62,6 +64,30 @@ def filter_array(items: Sequence[FilterItem]):
     for i, it in enumerate(items):
         arr[i] = it.to_struct()
     return arr
+
+
+@dataclass
+class OtherCond:
+    """One CNF item of HashJoinV2Exec.OtherCondition: `side.col OP side.col` (or a constant with rhs_side = -1) over the
+    joined row; side 0 = left child, 1 = right child (tg_other_item)."""
+    op: int
+    lhs_side: int
+    lhs_col: int
+    rhs_side: int = -1
+    rhs_col: int = -1
+    is_real: bool = False
+    lhs_unsigned: bool = False
+    rhs_unsigned: bool = False
+    const_i64: int = 0
+    const_f64: float = 0.0
+
+    def to_struct(self) -> abi.TgOtherItem:
+        s = abi.TgOtherItem()
+        s.op, s.is_real = self.op, int(self.is_real)
+        s.lhs_side, s.lhs_col, s.rhs_side, s.rhs_col = self.lhs_side, self.lhs_col, self.rhs_side, self.rhs_col
+        s.lhs_unsigned, s.rhs_unsigned = int(self.lhs_unsigned), int(self.rhs_unsigned)
+        s.const_i64, s.const_f64 = self.const_i64, self.const_f64
+        return s
 
 
 @dataclass
@@ -79,6 +105,7 @@ class JoinPlan:
     device: int = 0
     stream: int = 0
     load_factor: float = 0.0
+    other_cond: List[OtherCond] = field(default_factory=list)
 
     def out_schema(self) -> List[FieldType]:
         lu = self.lused if self.lused is not None else list(range(len(self.left_types)))
@@ -120,6 +147,9 @@ class JoinPlan:
         d.device = self.device
         d.stream = self.stream or None
         d.load_factor = self.load_factor
+        d.n_other_cond = len(self.other_cond)
+        if self.other_cond:
+            arr = (abi.TgOtherItem * len(self.other_cond))(*[o.to_struct() for o in self.other_cond]); keep.append(arr); d.other_cond = arr
         return d, keep
 
 
@@ -160,3 +190,47 @@ class AggPlan:
         d.stream = self.stream or None
         d.expected_groups = self.expected_groups
         return d, keep
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Scalar expressions for ProjectionExec (expression.Expression reduced to what the VecEval kernels offload)
+# ---------------------------------------------------------------------------------------------------------------
+class Expr:
+    def ret_type(self, schema: Sequence[FieldType]) -> FieldType:
+        raise NotImplementedError
+
+
+@dataclass
+class ColRef(Expr):
+    """expression.Column: passed through (EvaluatorSuite swaps plain column references, evaluator.go:128)"""
+    idx: int
+
+    def ret_type(self, schema):
+        return schema[self.idx]
+
+
+@dataclass
+class Const(Expr):
+    """expression.Constant: handed to the kernels as a scalar (the reference materialises a column, vectorized.go:23)"""
+    value: float
+    is_real: bool = False
+
+    def ret_type(self, schema):
+        return FieldType(abi.TYPE_DOUBLE if self.is_real else abi.TYPE_LONGLONG, abi.FLAG_NOT_NULL)
+
+
+@dataclass
+class ScalarFunc(Expr):
+    """builtinArithmetic{Plus,Minus,Multiply}{Int,Real}Sig / builtin{LT,LE,GT,GE,EQ,NE}{Int,Real}Sig over two arguments
+    (kind "arith": op = abi.ARITH_*, kind "cmp": op = abi.CMP_*); the right argument may be a Const"""
+    kind: str
+    op: int
+    args: Tuple[Expr, Expr]
+    is_real: bool = False
+    a_unsigned: bool = False
+    b_unsigned: bool = False
+
+    def ret_type(self, schema):
+        if self.kind == "arith":
+            return FieldType(abi.TYPE_DOUBLE if self.is_real else abi.TYPE_LONGLONG, 0)
+        return FieldType(abi.TYPE_LONGLONG, 0)
