@@ -376,6 +376,18 @@ int tg_vec_filter(int device, int on_device, const tg_chunk* chk,
                   uint8_t* selected, int64_t* n_selected, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * TopN                         replaces sortexec.TopNExec (pkg/executor/sortexec/topn.go:74, :230)
+ * ORDER BY items over plain columns, LIMIT offset, count.  Rows [offset, offset + count) of the child's rows in item
+ * order (NULL sorts before every value, DESC reverses: chunk.GetCompareFunc) are written to `out` (child schema, host
+ * buffers, capacity >= count); ties are broken arbitrarily, as by the reference's heap.  `on_device` as in the VecEval
+ * calls.  8-byte int-family / double / time columns.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct tg_sort_item { int32_t col; int32_t desc; } tg_sort_item;
+int tg_topn(int device, int on_device, const tg_chunk* chk, const int32_t* col_types, const uint32_t* col_flags,
+            const tg_sort_item* items, int32_t n_items, int64_t offset, int64_t count,
+            tg_mut_chunk* out, int64_t* nrows, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Key-hash repartition for the multi-GPU exchange (the B200 analogue of the MPP
  * ExchangeSender HashPartition, pkg/planner/core/operator/physicalop/physical_exchange_sender.go:115;
  * in-process analogue: partitionHashSplitter.split, pkg/executor/shuffle.go:450).

@@ -15,7 +15,8 @@
 // and pkg/util/codec/codec.go SerializeKeys :822 / serializeKeysImpl :622.
 //
 // Scope: fixed-width columns (elem_len 4/8/40), integer-family / float / double join keys (one or
-// many), build/probe filters as tg_filter_item CNF, no OtherCondition, no spill.
+// many), build/probe filters as tg_filter_item CNF, OtherCondition as tg_other_item CNF on candidate pairs
+// (inner_join_probe.go:72-79 / base_join_probe.go:758, for the join shapes the GPU gate accepts), no spill.
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -399,6 +400,8 @@ struct Join {
   std::vector<int> leftKeyIdx, rightKeyIdx;
   std::vector<int> lUsed, rUsed;
   std::vector<tg_filter_item> buildFilter, probeFilter;
+  std::vector<tg_other_item> otherCond;          // sides as given: 0 = left child, 1 = right child
+  std::vector<int> otherBuildCols;               // build columns OtherCondition reads (stored first in the row, join_table_meta.go:217)
   uint32_t concurrency = 5;
   // derived
   std::vector<FieldType> buildTypes, probeTypes, buildKeyTypes, probeKeyTypes;
@@ -455,8 +458,22 @@ static bool setup_join(Join& j, std::string& err) {
     default: err = "unsupported join type"; return false;
   }
   // OpenSelf hash_join_v2.go:700-711
-  j.meta = new_table_meta(j.buildKeyIdx, j.buildTypes, j.buildKeyTypes, j.probeKeyTypes, nullptr,
-                          &j.buildUsed, j.needScanRowTable);
+  if (!j.otherCond.empty()) {
+    if (j.needScanRowTable || j.joinType == TG_JOIN_LEFT_OUTER_SEMI || j.joinType == TG_JOIN_ANTI_LEFT_OUTER_SEMI ||
+        ((j.joinType == TG_JOIN_SEMI || j.joinType == TG_JOIN_ANTI_SEMI) && is_left_side_build(j))) {
+      err = "oracle: OtherCondition is restated for inner / probe-side outer / right-build semi and anti-semi joins only"; return false;
+    }
+    for (const tg_other_item& it : j.otherCond) {
+      for (int q = 0; q < 2; q++) {
+        int side = q ? it.rhs_side : it.lhs_side, col = q ? it.rhs_col : it.lhs_col;
+        if (side < 0) continue;
+        bool is_build = (side == 1) == j.rightAsBuild;
+        if (is_build && std::find(j.otherBuildCols.begin(), j.otherBuildCols.end(), col) == j.otherBuildCols.end()) j.otherBuildCols.push_back(col);
+      }
+    }
+  }
+  j.meta = new_table_meta(j.buildKeyIdx, j.buildTypes, j.buildKeyTypes, j.probeKeyTypes,
+                          j.otherCond.empty() ? nullptr : &j.otherBuildCols, &j.buildUsed, j.needScanRowTable);
   if (!j.meta.isFixedLength || !j.meta.isJoinKeysFixedLength) {
     err = "oracle: var-len columns/keys are out of scope"; return false;
   }
@@ -705,6 +722,40 @@ struct ProbeWorker {
     }
   }
   void append_probe_nulls() { for (size_t k = 0; k < j.probeUsed.size(); k++) out[j.probeColOffsetInResult + k].append_null(); }
+  // value of build column `col` inside a build row: false = NULL
+  bool build_value(const uint8_t* row, int col, uint64_t& raw) const {
+    const Meta& m = j.meta;
+    int pos = -1;
+    for (size_t i = 0; i < m.rowColumnsOrder.size(); i++) if (m.rowColumnsOrder[i] == col) pos = (int)i;
+    if (pos < 0) return false;
+    if (m.nullMapLength > 0 && row_col_is_null(m, row, pos)) return false;
+    std::memcpy(&raw, row + m.rowDataOffset + rowColOffset[pos], 8);
+    return true;
+  }
+  // OtherCondition on one candidate pair (probe row `phys` of chk, build row): every CNF item non-NULL true
+  // (expression.VectorizedFilter on the joined chunk, inner_join_probe.go:72-79)
+  bool other_ok(const tg_chunk& chk, int64_t phys, const uint8_t* row) const {
+    for (const tg_other_item& it : j.otherCond) {
+      uint64_t v[2] = {0, 0};
+      for (int q = 0; q < 2; q++) {
+        int side = q ? it.rhs_side : it.lhs_side, col = q ? it.rhs_col : it.lhs_col;
+        if (side < 0) { if (it.is_real) std::memcpy(&v[q], &it.const_f64, 8); else v[q] = (uint64_t)it.const_i64; continue; }
+        bool is_build = (side == 1) == j.rightAsBuild;
+        if (is_build) { if (!build_value(row, col, v[q])) return false; }
+        else { const tg_column& c = chk.cols[col]; if (col_is_null(c, phys)) return false; std::memcpy(&v[q], col_raw(c, phys), 8); }
+      }
+      int c;
+      if (it.is_real) { double a, b; std::memcpy(&a, &v[0], 8); std::memcpy(&b, &v[1], 8); c = compare_real(a, b); }
+      else c = compare_int((int64_t)v[0], it.lhs_unsigned != 0, (int64_t)v[1], it.rhs_unsigned != 0);
+      bool ok;
+      switch (it.op) {
+        case TG_CMP_LT: ok = c < 0; break; case TG_CMP_LE: ok = c <= 0; break; case TG_CMP_GT: ok = c > 0; break;
+        case TG_CMP_GE: ok = c >= 0; break; case TG_CMP_EQ: ok = c == 0; break; default: ok = c != 0; break;
+      }
+      if (!ok) return false;
+    }
+    return true;
+  }
 
   bool process_chunk(const tg_chunk& chk) {
     // SetChunkForProbe base_join_probe.go:179
@@ -740,7 +791,7 @@ struct ProbeWorker {
       uint64_t hdr = headers[l];
       while (hdr != 0) {
         uint8_t* cand = th.to_ptr(hdr);
-        if (is_key_matched(meta, keys.key(l), keys.len(l), cand)) { if (!fn(cand)) break; }
+        if (is_key_matched(meta, keys.key(l), keys.len(l), cand) && (j.otherCond.empty() || other_ok(chk, usedRows[l], cand))) { if (!fn(cand)) break; }
         hdr = next_row_address(cand, th, hashes[l]);
       }
     };
@@ -963,6 +1014,7 @@ int orc_join_open(const tg_join_desc* d, int32_t concurrency, orc_join** out) {
   else j.rUsed.assign(d->rused, d->rused + d->n_rused);
   if (d->n_build_filter > 0) j.buildFilter.assign(d->build_filter, d->build_filter + d->n_build_filter);
   if (d->n_probe_filter > 0) j.probeFilter.assign(d->probe_filter, d->probe_filter + d->n_probe_filter);
+  if (d->n_other_cond > 0 && d->other_cond) j.otherCond.assign(d->other_cond, d->other_cond + d->n_other_cond);
   j.concurrency = (uint32_t)std::max(1, concurrency);
   std::string err;
   if (!setup_join(j, err)) { set_error(err); delete h; return TG_ERR_UNSUPPORTED; }

@@ -58,7 +58,7 @@ static int eval_item(const tg_chunk& chk, int64_t p, const tg_filter_item& it) {
     c = compare_real(col_f64(a, p), y);
   } else {
     int64_t y = it.rhs_col >= 0 ? col_i64(chk.cols[it.rhs_col], p) : it.const_i64;
-    c = compare_int(col_i64(a, p), it.lhs_unsigned != 0, y, false);
+    c = compare_int(col_i64(a, p), it.lhs_unsigned != 0, y, it.rhs_unsigned != 0);
   }
   return apply_cmp(it.op, c) ? 1 : 0;
 }

@@ -70,14 +70,16 @@ def main():
         inputs.append((t(pk), t(pv)))
     torch.cuda.synchronize(dev)
     dist.barrier()
-    # pipelined like bench.py: all sends are enqueued up front (the exchange stream throttles itself on the ACK
-    # mailboxes), the probes follow on their own stream
+    # pipelined exactly like bench.py: every SM kernel on ONE stream, the exchange one step ahead of the probe.  Rule of the
+    # mailbox protocol: a wait may only depend on signals enqueued EARLIER in program order on every rank (send(k+1)'s ACK
+    # wait needs release(k-1), recv(k) needs send(k)) — then no host-side synchronisation can deadlock against a spinning
+    # wait kernel.
     outs = []
-    for s in range(a.steps):
-        with torch.cuda.stream(xstream):
-            xm.send(inputs[s][0], [inputs[s][0], inputs[s][1]])
-    for s in range(a.steps):
-        with torch.cuda.stream(stream):
+    with torch.cuda.stream(stream):
+        xm.send(inputs[0][0], [inputs[0][0], inputs[0][1]], stream)
+        for s in range(a.steps):
+            if s + 1 < a.steps:
+                xm.send(inputs[s + 1][0], [inputs[s + 1][0], inputs[s + 1][1]], stream)
             cols_in, seg_cnt, cap, set_, ep = xm.recv(stream)
             rows, cols, _ = join.probe_segments(cols_in, seg_cnt, cap, sync=True)
             outs.append([view(p, rows).cpu().numpy().copy() for p in cols])
@@ -87,9 +89,8 @@ def main():
     res = {f"s{s}c{c}": outs[s][c] for s in range(a.steps) for c in range(4)}
     # forced overflow: regions far too small for the rows that arrive -> every rank must see the error
     xo = MailboxExchange(rank, world, local, xstream, 2, 4096, slack=1.0)
-    with torch.cuda.stream(xstream):
-        xo.send(inputs[0][0], [inputs[0][0], inputs[0][1]])
     with torch.cuda.stream(stream):
+        xo.send(inputs[0][0], [inputs[0][0], inputs[0][1]], stream)
         _c, _n, _cap, set_, ep = xo.recv(stream)
         xo.release(stream, set_, ep)
     try:

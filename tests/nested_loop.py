@@ -94,6 +94,16 @@ def nested_loop_join(plan: JoinPlan, left: Sequence[Chunk], right: Sequence[Chun
         b = tuple(r[i] for i in ru) if r is not None else tuple(None for _ in ru)
         return a + b
 
+    def pair_ok(l: Row, r: Row) -> bool:
+        """OtherCondition on one candidate pair: every CNF item non-NULL true (inner_join_probe_test.go builds its expected
+        rows the same way: key equality AND the other condition on the joined row)"""
+        for it in getattr(plan, "other_cond", []) or []:
+            a = (l if it.lhs_side == 0 else r)[it.lhs_col]
+            b = ((l if it.rhs_side == 0 else r)[it.rhs_col]) if it.rhs_side >= 0 else (it.const_f64 if it.is_real else it.const_i64)
+            if a is None or b is None or not _cmp(it.op, a, b):
+                return False
+        return True
+
     jt = plan.join_type
     res: List[Row] = []
     rindex = {}
@@ -103,10 +113,12 @@ def nested_loop_join(plan: JoinPlan, left: Sequence[Chunk], right: Sequence[Chun
     if jt == abi.JOIN_INNER:
         for i, l in enumerate(lrows):
             for j in rindex.get(lkeys[i], []) if lkeys[i] is not None else []:
-                res.append(out_row(l, rrows[j]))
+                if pair_ok(l, rrows[j]):
+                    res.append(out_row(l, rrows[j]))
     elif jt == abi.JOIN_LEFT_OUTER:
         for i, l in enumerate(lrows):
             ms = rindex.get(lkeys[i], []) if lkeys[i] is not None else []
+            ms = [j for j in ms if pair_ok(l, rrows[j])]
             for j in ms:
                 res.append(out_row(l, rrows[j]))
             if not ms:
@@ -118,13 +130,14 @@ def nested_loop_join(plan: JoinPlan, left: Sequence[Chunk], right: Sequence[Chun
                 lindex.setdefault(k, []).append(i)
         for j, r in enumerate(rrows):
             ms = lindex.get(rkeys[j], []) if rkeys[j] is not None else []
+            ms = [i for i in ms if pair_ok(lrows[i], r)]
             for i in ms:
                 res.append(out_row(lrows[i], r))
             if not ms:
                 res.append(out_row(None, r))
     elif jt in (abi.JOIN_SEMI, abi.JOIN_ANTI_SEMI):
         for i, l in enumerate(lrows):
-            m = lkeys[i] is not None and lkeys[i] in rindex
+            m = lkeys[i] is not None and any(pair_ok(l, rrows[j]) for j in rindex.get(lkeys[i], []))
             if (jt == abi.JOIN_SEMI) == m:
                 # semi: left rows removed by the left filter never match; anti: they are results
                 res.append(tuple(l[c] for c in lu))

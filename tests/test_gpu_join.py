@@ -90,6 +90,35 @@ def test_gpu_filters(jt):
         assert_rows_equal(run_oracle(plan, l, r), run_gpu(plan, l, r))
 
 
+@pytest.mark.parametrize("jt,build_is_right", [(abi.JOIN_INNER, True), (abi.JOIN_INNER, False), (abi.JOIN_LEFT_OUTER, True),
+                                               (abi.JOIN_RIGHT_OUTER, False), (abi.JOIN_SEMI, True), (abi.JOIN_ANTI_SEMI, True)])
+@pytest.mark.parametrize("nulls,dup,with_sel", [(0.0, False, False), (0.12, True, True)])
+def test_gpu_other_condition(jt, build_is_right, nulls, dup, with_sel):
+    # OtherCondition evaluated on candidate pairs on the device (k_probe_count / k_probe_write, csrc/join_kernels.cuh):
+    # column-vs-column across the two sides plus a constant item, NULL operands never pass; unique and duplicate build keys
+    from tidb_b200.plan import OtherCond
+    rng = np.random.default_rng(31 + jt + 10 * int(build_is_right))
+    ltypes, rtypes, l, r = make_case(rng, 3000, 4000, nulls, dup, with_sel)
+    semi = jt >= abi.JOIN_SEMI
+    other = [OtherCond(abi.CMP_LE, 0, 0, 1, 1), OtherCond(abi.CMP_NE, 1, 2, -1, -1, const_i64=7)]
+    plan = JoinPlan(jt, ltypes, rtypes, [1], [0], build_is_right=build_is_right, lused=[0, 1, 2], rused=[] if semi else [2, 0], other_cond=other)
+    assert_rows_equal(run_oracle(plan, l, r), run_gpu(plan, l, r))
+
+
+def test_gpu_other_condition_gate():
+    # shapes whose OtherCondition the device does not evaluate are declined by the planner gate, never mis-evaluated
+    from tidb_b200.plan import OtherCond
+    lib = abi.load_lib()
+    other = [OtherCond(abi.CMP_LT, 0, 0, 1, 1)]
+    for jt, brt in ((abi.JOIN_LEFT_OUTER, False), (abi.JOIN_SEMI, False), (abi.JOIN_LEFT_OUTER_SEMI, True)):
+        plan = JoinPlan(jt, [INT, INT], [INT, INT], [0], [0], build_is_right=brt, lused=[0, 1], rused=[] if jt >= abi.JOIN_SEMI else [1], other_cond=other)
+        d, keep = plan.to_struct()
+        assert lib.tg_join_supported(C.byref(d)) == abi.TG_ERR_UNSUPPORTED
+    mixed = JoinPlan(abi.JOIN_INNER, [INT, DBL], [INT, INT], [0], [0], other_cond=[OtherCond(abi.CMP_LT, 0, 1, 1, 1)])   # double vs int
+    d, keep = mixed.to_struct()
+    assert lib.tg_join_supported(C.byref(d)) == abi.TG_ERR_UNSUPPORTED
+
+
 def test_gpu_double_keys_and_mixed_sign():
     rng = np.random.default_rng(5)
     ltypes, rtypes, l, r = make_case(rng, 1500, 2000, 0.1, True, False, key_dtype=np.float64)

@@ -219,3 +219,17 @@ def test_row_layout_alignment_and_table_size():
     j.run([Chunk([Column(keys), Column(keys * 3)])], [Chunk([Column(keys[:10]), Column(keys[:10])])])
     assert j.stat("partitions") == 8
     j.close()
+
+
+@pytest.mark.parametrize("jt,build_is_right", [(abi.JOIN_INNER, True), (abi.JOIN_INNER, False), (abi.JOIN_LEFT_OUTER, True),
+                                               (abi.JOIN_RIGHT_OUTER, False), (abi.JOIN_SEMI, True), (abi.JOIN_ANTI_SEMI, True)])
+def test_oracle_other_condition_vs_nested_loop(jt, build_is_right):
+    # OtherCondition: a candidate pair (equal keys) is a match only if every residual item is non-NULL true
+    # (inner_join_probe.go:72-79, base_join_probe.go:758); the oracle's restatement against the independent nested loop
+    from tidb_b200.plan import OtherCond
+    rng = np.random.default_rng(900 + jt)
+    ltypes, rtypes, l, r = make_case(rng, 600, 800, 0.1, True, False)
+    semi = jt >= abi.JOIN_SEMI
+    other = [OtherCond(abi.CMP_LT, 0, 0, 1, 1), OtherCond(abi.CMP_NE, 1, 2, -1, -1, const_i64=3)]
+    plan = JoinPlan(jt, ltypes, rtypes, [1], [0], build_is_right=build_is_right, lused=[0, 1, 2], rused=[] if semi else [2, 0], other_cond=other)
+    assert_rows_equal(nested_loop_join(plan, l, r), run_oracle(plan, l, r))

@@ -87,6 +87,10 @@ class TgJoinStats(C.Structure):
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 
 
+class TgSortItem(C.Structure):
+    _fields_ = [("col", C.c_int32), ("desc", C.c_int32)]
+
+
 class TgMailTargets(C.Structure):
     """tg_mail_targets: where this rank's mailbox word lives on every peer (tg_mail_signal)"""
     _fields_ = [("n", C.c_int32), ("pad", C.c_int32), ("slot", C.c_uint64 * 16)]
@@ -124,7 +128,7 @@ EXPORTED_SYMBOLS = [
     "tg_agg_supported", "tg_agg_open", "tg_agg_push", "tg_agg_push_dev", "tg_agg_finish",
     "tg_agg_next", "tg_agg_close", "tg_agg_result_dev", "tg_agg_get_stats",
     "tg_vec_compare_int", "tg_vec_compare_real", "tg_vec_arith_int", "tg_vec_arith_real",
-    "tg_vec_filter",
+    "tg_vec_filter", "tg_topn",
     "tg_partition_by_key", "tg_partition_of_key", "tg_partition_exchange", "tg_partition_exchange_cf", "tg_partition_exchange_cf_ex", "tg_partition_count",
     "tg_mail_signal", "tg_mail_wait",
     "tg_ipc_export", "tg_ipc_open", "tg_ipc_close",

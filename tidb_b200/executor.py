@@ -365,6 +365,53 @@ class ProjectionExec(Executor):
         return out
 
 
+class TopNExec(Executor):
+    """GPU replacement of sortexec.TopNExec (pkg/executor/sortexec/topn.go:74; Next :230 executeTopN): a pipeline breaker that
+    drains the child, selects rows [offset, offset + count) in ORDER BY order on the device (tg_topn: rank pass, radix
+    select, gather) and hands them out chunk by chunk.  by_items = [(column, desc)]."""
+
+    def __init__(self, child: Executor, by_items: Sequence, offset: int, count: int, device: int = 0):
+        super().__init__(child.schema, [child])
+        self.by_items, self.offset, self.count, self.device = list(by_items), int(offset), int(count), device
+        self._result: Optional[Chunk] = None
+        self._pos = 0
+
+    def open(self) -> None:
+        super().open()
+        self._lib = abi.load_lib()
+        self._result, self._pos = None, 0
+
+    def _execute(self) -> None:
+        chunks = []
+        while True:
+            chk = self.children[0].next(MAX_CHUNK_SIZE)
+            if chk.num_rows() == 0:
+                break
+            chunks.append(chk)
+        if not chunks or self.count == 0:
+            self._result = self.empty_chunk()
+            return
+        dense = _concat_chunks(chunks)
+        out = _out_chunk(self.schema, max(self.count, 8))
+        items = (abi.TgSortItem * len(self.by_items))(*[abi.TgSortItem(c, int(bool(d))) for c, d in self.by_items])
+        tps = (C.c_int32 * len(self.schema))(*[t.tp for t in self.schema])
+        fls = (C.c_uint32 * len(self.schema))(*[t.flag for t in self.schema])
+        n = C.c_int64(0)
+        cs = dense.to_struct()
+        abi.check(self._lib.tg_topn(self.device, 0, C.byref(cs), tps, fls, items, len(self.by_items), C.c_int64(self.offset), C.c_int64(self.count),
+                                    C.byref(out.struct), C.byref(n), None))
+        self._result = Chunk([Column(v.copy(), nl.copy() if nl.any() else None) for v, nl in out.columns(n.value)])
+
+    def next(self, required_rows: int = MAX_CHUNK_SIZE) -> Chunk:
+        if self._result is None:
+            self._execute()
+        lo, hi = self._pos, min(self._pos + required_rows, self._result.num_rows())
+        self._pos = hi
+        if hi <= lo:
+            return self.empty_chunk()
+        return Chunk([Column(c.data[lo:hi], c.nulls()[lo:hi] if c.nulls().any() else None) for c in self._result.columns])
+
+
 def drain(e: Executor, required_rows: int = MAX_CHUNK_SIZE) -> List[Chunk]:
     """open → next until EOF → close, like the reference's test helpers."""
     e.open()

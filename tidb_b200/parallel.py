@@ -449,7 +449,9 @@ class MailboxExchange:
                 this step; the counts land in seg_cnt, ready for tg_join_probe_dev_seg;
       release() on S after the probe: ACK to every sender that this buffer set may be overwritten.
 
-    Two buffer sets: X runs one step ahead of S (the NVLink-bound scatter of step k+1 overlaps the probe of step k).
+    Two buffer sets: the exchange runs one step ahead of the probe.  PROTOCOL RULE: on every rank a wait may only depend
+    on signals that were enqueued EARLIER in program order (send(k+1) waits for release(k-1), recv(k) for send(k)); a host
+    call that synchronises the device can then never deadlock against a spinning wait kernel.
     dma=True keeps the SMs out of the transfer: the kernel regroups into a local staging copy of the region layout and
     copy engines push region p to peer p on several streams (fill is unknown to the host, so whole regions move).
     Reference analogue: MPP ExchangeSender/Receiver with HashPartition (physical_exchange_sender.go:115)."""
