@@ -303,8 +303,20 @@ typedef struct tg_agg_func {
   int32_t arg_col;   /* input column index; -1 for COUNT(*) / count(constant)                  */
   int32_t arg_type;  /* MySQL type of the argument (TG_TYPE_DOUBLE / TG_TYPE_LONGLONG ...)      */
   uint32_t arg_flag;
-  int32_t arg_col2;  /* Final/Partial2 AVG: second input column (count, then sum: func_avg.go:444) */
+  int32_t arg_col2;  /* Final/Partial2 AVG: second input column (count, then sum: func_avg.go:444);
+                      * arg_expr != 0: the second column of the argument expression                */
+  /* The argument as a small scalar expression instead of a plain column (AggFuncDesc.Args[0] is an expression.Expression
+   * evaluated per row: args[0].EvalReal, func_sum.go:90).  Fused into the update kernel — no projected column is
+   * materialised.  DOUBLE columns, SUM / AVG in Complete mode.  NULL if either column is NULL; a non-finite intermediate
+   * on a non-NULL row fails the call with TG_ERR_OVERFLOW (builtinArithmetic{Minus,Multiply}RealSig).
+   *   TG_ARGEXPR_COL        arg_col
+   *   TG_ARGEXPR_MUL        arg_col * arg_col2
+   *   TG_ARGEXPR_MUL_CSUB   arg_col * (arg_const - arg_col2)      e.g. l_extendedprice * (1 - l_discount)            */
+  int32_t arg_expr;
+  int32_t reserved;
+  double arg_const;
 } tg_agg_func;
+enum { TG_ARGEXPR_COL = 0, TG_ARGEXPR_MUL = 1, TG_ARGEXPR_MUL_CSUB = 2 };
 
 typedef struct tg_agg_desc {
   int32_t n_cols;                 /* child schema                                               */

@@ -118,6 +118,24 @@ static bool check_supported(const Agg& a, std::string& err) {
 
 // af.UpdatePartialResult for one row (Complete mode: original input) or af.MergePartialResult-like
 // consumption of a partial-result input row (Final mode)
+// AggFuncDesc.Args[0] as the fused scalar expression (tg_agg_func.arg_expr): args[0].EvalReal(row) through
+// builtinArithmeticMinusRealSig / MultiplyRealSig (builtin_arithmetic.go evalReal: NULL if an operand is NULL, ErrOverflow
+// when the result leaves the DOUBLE range).  Returns false for NULL; sets *overflow.
+static bool arg_real(const tg_chunk& chk, const tg_agg_func& f, int64_t p, double& v, bool* overflow) {
+  if (col_is_null(chk.cols[f.arg_col], p)) return false;
+  double x = col_f64(chk.cols[f.arg_col], p);
+  if (f.arg_expr == TG_ARGEXPR_COL) { v = x; return true; }
+  if (col_is_null(chk.cols[f.arg_col2], p)) return false;
+  double y = col_f64(chk.cols[f.arg_col2], p);
+  volatile double t = f.arg_expr == TG_ARGEXPR_MUL_CSUB ? f.arg_const - y : y;
+  volatile double r = x * t;
+  if (!std::isfinite((double)t) || !std::isfinite((double)r)) *overflow = true;
+  v = r;
+  return true;
+}
+static std::atomic<bool> g_arg_overflow_any{false};
+static thread_local bool g_arg_overflow = false;
+
 static void update_row(const Agg& a, const tg_chunk& chk, int64_t p, std::vector<PR>& prs) {
   for (size_t k = 0; k < a.funcs.size(); k++) {
     const tg_agg_func& f = a.funcs[k];
@@ -130,15 +148,18 @@ static void update_row(const Agg& a, const tg_chunk& chk, int64_t p, std::vector
         } else if (f.arg_col < 0) pr.ival++;   // COUNT(*) / count(1)
         else if (!col_is_null(chk.cols[f.arg_col], p)) pr.ival++;   // countOriginal4*.Update :73
         break;
-      case TG_AGG_SUM:   // sum4Float64.UpdatePartialResult func_sum.go:90
-        if (!col_is_null(chk.cols[f.arg_col], p)) { pr.fval += col_f64(chk.cols[f.arg_col], p); pr.ival++; }
+      case TG_AGG_SUM: {   // sum4Float64.UpdatePartialResult func_sum.go:90
+        double v;
+        if (arg_real(chk, f, p, v, &g_arg_overflow)) { pr.fval += v; pr.ival++; }
         break;
+      }
       case TG_AGG_AVG:
         if (final_mode) {   // avgPartial4Float64 func_avg.go:405: args[0]=count, args[1]=sum
           const tg_column& cc = chk.cols[f.arg_col]; const tg_column& sc = chk.cols[f.arg_col2];
           if (!col_is_null(sc, p) && !col_is_null(cc, p)) { pr.fval += col_f64(sc, p); pr.ival += col_i64(cc, p); }
-        } else if (!col_is_null(chk.cols[f.arg_col], p)) {   // avgOriginal4Float64 :366
-          pr.fval += col_f64(chk.cols[f.arg_col], p); pr.ival++;
+        } else {   // avgOriginal4Float64 :366
+          double v;
+          if (arg_real(chk, f, p, v, &g_arg_overflow)) { pr.fval += v; pr.ival++; }
         }
         break;
       case TG_AGG_MIN: case TG_AGG_MAX: {   // maxMin4Int / maxMin4Float64 func_max_min.go
@@ -228,6 +249,7 @@ static void group_key_of(const Agg& a, const tg_chunk& chk, int64_t p, std::stri
 static bool run_agg(Agg& a, const tg_chunk* chunks, int64_t nchunks) {
   auto t0 = std::chrono::steady_clock::now();
   int M = a.partialConcurrency, N = a.finalConcurrency;
+  g_arg_overflow_any = false;
   // partial workers: partialResultsMap[finalWorkerIdx] (agg_hash_partial_worker.go:219)
   std::vector<std::vector<GroupMap>> partial(M, std::vector<GroupMap>(N));
   std::atomic<int64_t> next{0};
@@ -236,9 +258,10 @@ static bool run_agg(Agg& a, const tg_chunk* chunks, int64_t nchunks) {
     std::vector<std::thread> th;
     for (int w = 0; w < M; w++) th.emplace_back([&, w] {
       std::string key;
+      g_arg_overflow = false;
       for (;;) {
         int64_t i = next.fetch_add(1);
-        if (i >= nchunks) break;
+        if (i >= nchunks) { if (g_arg_overflow) g_arg_overflow_any = true; break; }
         const tg_chunk& chk = chunks[i];
         int64_t n = chunk_logical_rows(chk);
         totalRows += n;
@@ -255,6 +278,7 @@ static bool run_agg(Agg& a, const tg_chunk* chunks, int64_t nchunks) {
     });
     for (auto& t : th) t.join();
   }
+  if (g_arg_overflow_any.load()) { set_error("ErrOverflow: DOUBLE value is out of range in an aggregate argument expression"); return false; }
   // final workers: merge the M partial maps destined to them, then generate results
   a.results.clear(); a.results.resize(N);
   for (auto& r : a.results) for (int el : a.outElemLen) r.emplace_back(el);

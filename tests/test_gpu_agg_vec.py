@@ -187,6 +187,33 @@ def test_agg_multi_column_group_by_vs_oracle(ncols, nullable):
     assert_agg_equal(run_orc_agg(plan, chunks), run_gpu_agg(plan, chunks), {ncols})
 
 
+@pytest.mark.parametrize("group_cols", [[], [0], [0, 1]])
+def test_agg_fused_argument_expression(group_cols):
+    # SUM(l_extendedprice * (1 - l_discount)) with the projection fused into the update kernels (tg_agg_func.arg_expr): the
+    # reference evaluates Args[0] per row (func_sum.go:90 through builtinArithmeticMinusRealSig / MultiplyRealSig): NULL when
+    # an operand is NULL; ErrOverflow when a non-NULL row leaves the DOUBLE range
+    rng = np.random.default_rng(21 + len(group_cols))
+    n = 150_000
+    g0 = rng.integers(0, 700, n).astype(np.int64); g1 = rng.integers(0, 3, n).astype(np.int64)
+    price = np.floor(rng.random(n) * 1e7) / 100; pn = rng.random(n) < 0.03
+    disc = np.floor(rng.random(n) * 11) / 100; dn = rng.random(n) < 0.03
+    chunks = Chunk([Column(g0), Column(g1), Column(price, pn), Column(disc, dn)]).split(1 << 14)
+    funcs = [AggFunc(abi.AGG_FIRSTROW, c) for c in group_cols] + [
+        AggFunc(abi.AGG_SUM, 2, abi.TYPE_DOUBLE, arg_col2=3, arg_expr=abi.ARGEXPR_MUL_CSUB, arg_const=1.0),
+        AggFunc(abi.AGG_AVG, 2, abi.TYPE_DOUBLE, arg_col2=3, arg_expr=abi.ARGEXPR_MUL), AggFunc(abi.AGG_COUNT, -1)]
+    plan = AggPlan([INT_NN, INT_NN, DBL, DBL], group_cols, funcs, expected_groups=100)
+    k = len(group_cols)
+    assert_agg_equal(run_orc_agg(plan, chunks), run_gpu_agg(plan, chunks), {k, k + 1})
+    # overflow: 1e308 * (3 - (-1e308))  ->  ErrOverflow on both sides
+    big = [Chunk([Column(np.zeros(4, dtype=np.int64)), Column(np.zeros(4, dtype=np.int64)), Column(np.array([1.0, 1e308, 2.0, 3.0])), Column(np.array([0.5, -1e308, 0.1, 0.2]))])]
+    oplan = AggPlan([INT_NN, INT_NN, DBL_NN, DBL_NN], group_cols, [AggFunc(abi.AGG_SUM, 2, abi.TYPE_DOUBLE, arg_col2=3, arg_expr=abi.ARGEXPR_MUL_CSUB, arg_const=3.0)])
+    with pytest.raises(RuntimeError):
+        run_orc_agg(oplan, big)
+    with pytest.raises(abi.TgError) as ei:
+        run_gpu_agg(oplan, big)
+    assert ei.value.code == abi.TG_ERR_OVERFLOW
+
+
 def test_agg_multi_push_same_table():
     # several device batches into one handle (fetchChildData loop, agg_hash_executor.go:449): later batches find the groups
     # of earlier ones; the table grows between batches

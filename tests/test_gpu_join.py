@@ -240,6 +240,8 @@ def test_partial_match_and_stats():
                                  dict(TG_PROBE_PARTITION="1", TG_PROBE_PARTS="7", TG_PROBE_SEG_VEC="0"),
                                  dict(TG_PROBE_PARTITION="1", TG_PROBE_PARTS="5", TG_PROBE_SEG_LEAN="0"), dict(TG_PROBE_PARTITION="1", TG_PROBE_PARTS="6", TG_PROBE_SEG_LEAN="2"),
                                  dict(TG_PROBE_PARTITION="1", TG_PROBE_PARTS="4", TG_PROBE_SEG_LEAN="1", TG_PROBE_CARVEOUT="0"),
+                                 dict(TG_PROBE_PARTITION="1", TG_PROBE_PARTS="5", TG_PROBE_SUBSEG="0"), dict(TG_PROBE_PARTITION="1", TG_PROBE_PARTS="2", TG_PROBE_SUBSEG="1"),
+                                 dict(TG_PROBE_PARTITION="1", TG_PROBE_PARTS="9", TG_PROBE_SUBSEG="0", TG_PROBE_SEG_LEAN="0"),
                                  dict(TG_PROBE_PARTITION="2", TG_PROBE_PARTS="5", TG_PROBE_TMA="1"), dict(TG_PROBE_PARTITION="2", TG_PROBE_PARTS="3", TG_SCATTER_BULK="0"),
                                  dict(TG_PROBE_TMA="1", TG_PROBE_PARTITION="0"), dict(TG_PROBE_PARTITION="0"), dict(TG_PROBE_VARIANT="0")])
 def test_fused_probe_variants_forced(env, monkeypatch):
@@ -440,7 +442,8 @@ def test_probe_device_segments_matches_dense_probe(monkeypatch):
     pk, pv = np.concatenate(pk_all), np.concatenate(pv_all)
     t = lambda a: torch.from_numpy(a).to(dev)
     for env in (dict(TG_PROBE_PARTITION="0"), dict(TG_PROBE_PARTITION="1", TG_PROBE_PARTS="6", TG_PROBE_PART_MIN_MB="0", TG_PROBE_PART_MIN_ROWS="0"),
-                dict(TG_PROBE_PARTITION="1", TG_PROBE_PARTS="6", TG_PROBE_PART_MIN_MB="0", TG_PROBE_PART_MIN_ROWS="0", TG_PROBE_SEG_LEAN="0")):
+                dict(TG_PROBE_PARTITION="1", TG_PROBE_PARTS="6", TG_PROBE_PART_MIN_MB="0", TG_PROBE_PART_MIN_ROWS="0", TG_PROBE_SEG_LEAN="0"),
+                dict(TG_PROBE_PARTITION="1", TG_PROBE_PARTS="6", TG_PROBE_PART_MIN_MB="0", TG_PROBE_PART_MIN_ROWS="0", TG_PROBE_SUBSEG="0")):
         for k_, v_ in env.items():
             monkeypatch.setenv(k_, v_)
         plan = JoinPlan(abi.JOIN_INNER, [INT_NN, INT_NN], [INT_NN, INT_NN], [0], [0], device=0)

@@ -30,8 +30,28 @@ struct AggFuncDev {
   int32_t s0, s1;       // state array indices (-1 = unused): s0 value (sum / min / max / count), s1 non-NULL count
   int32_t final_mode;   // TG_AGGMODE_FINAL: inputs are partial results
   int32_t arg_col2;
+  int32_t arg_expr;     // TG_ARGEXPR_*
+  int32_t pad;
+  double arg_const;
 };
-struct AggSpec { int32_t n; int32_t pad; AggFuncDev f[TG_MAX_AGG]; };
+struct AggSpec { int32_t n; int32_t pad; unsigned long long* err; AggFuncDev f[TG_MAX_AGG]; };
+
+// argument of SUM / AVG as a double: a plain column or the fused scalar expression; false = NULL.  A non-finite
+// intermediate on a non-NULL row raises *spec.err (types.ErrOverflow: builtin_arithmetic_vec.go:51-58, :312-318)
+__device__ __forceinline__ bool agg_arg_real(const AggSpec& spec, const AggFuncDev& f, const DevCols& cols, int64_t row, double& v) {
+  const uint8_t* nb = cols.nulls[f.arg_col];
+  if (nb && !bit_not_null(nb, row)) return false;
+  const double a = __longlong_as_double((long long)__ldcs(reinterpret_cast<const unsigned long long*>(cols.data[f.arg_col]) + row));
+  if (f.arg_expr == TG_ARGEXPR_COL) { v = a; return true; }
+  const uint8_t* nb2 = cols.nulls[f.arg_col2];
+  if (nb2 && !bit_not_null(nb2, row)) return false;
+  const double b = __longlong_as_double((long long)__ldcs(reinterpret_cast<const unsigned long long*>(cols.data[f.arg_col2]) + row));
+  const double t = f.arg_expr == TG_ARGEXPR_MUL_CSUB ? __dsub_rn(f.arg_const, b) : b;
+  const double r = __dmul_rn(a, t);     // separate roundings, like the two builtins (no fused multiply-add)
+  if (!isfinite(t) || !isfinite(r)) atomicExch(spec.err, 1ull);
+  v = r;
+  return true;
+}
 #define TG_MAX_GROUP_COLS 4
 struct AggTable {
   long long* keys;                       // single GROUP BY column: the key itself (kEmptyKey = unoccupied)
@@ -90,10 +110,13 @@ __device__ __forceinline__ void agg_apply(const AggTable& t, const AggSpec& spec
         if (f.final_mode) atomicAdd(&t.state[f.s0][s], reinterpret_cast<const unsigned long long*>(cols.data[f.arg_col])[row]);
         else atomicAdd(&t.state[f.s0][s], 1ull);
         break;
-      case TG_AGG_SUM:
-        atomicAdd(reinterpret_cast<double*>(&t.state[f.s0][s]), reinterpret_cast<const double*>(cols.data[f.arg_col])[row]);
+      case TG_AGG_SUM: {
+        double v;
+        if (!agg_arg_real(spec, f, cols, row, v)) break;
+        atomicAdd(reinterpret_cast<double*>(&t.state[f.s0][s]), v);
         if (f.s1 >= 0) atomicAdd(&t.state[f.s1][s], 1ull);
         break;
+      }
       case TG_AGG_AVG:
         if (f.final_mode) {   // args: count column, sum column (func_avg.go:405)
           const uint8_t* nb2 = cols.nulls[f.arg_col2];
@@ -101,7 +124,9 @@ __device__ __forceinline__ void agg_apply(const AggTable& t, const AggSpec& spec
           atomicAdd(reinterpret_cast<double*>(&t.state[f.s0][s]), reinterpret_cast<const double*>(cols.data[f.arg_col2])[row]);
           atomicAdd(&t.state[f.s1][s], reinterpret_cast<const unsigned long long*>(cols.data[f.arg_col])[row]);
         } else {
-          atomicAdd(reinterpret_cast<double*>(&t.state[f.s0][s]), reinterpret_cast<const double*>(cols.data[f.arg_col])[row]);
+          double v;
+          if (!agg_arg_real(spec, f, cols, row, v)) break;
+          atomicAdd(reinterpret_cast<double*>(&t.state[f.s0][s]), v);
           if (f.s1 >= 0) atomicAdd(&t.state[f.s1][s], 1ull);
         }
         break;
@@ -192,6 +217,12 @@ k_agg_update_nogroup(DevCols cols, int64_t n, AggTable t, AggSpec spec) {
         if (nb2 && !bit_not_null(nb2, i)) continue;
         fs += reinterpret_cast<const double*>(cols.data[f.arg_col2])[i];
         cnt += reinterpret_cast<const unsigned long long*>(cols.data[f.arg_col])[i];
+        continue;
+      }
+      if ((f.name == TG_AGG_SUM || f.name == TG_AGG_AVG) && f.arg_expr) {
+        double v;
+        if (!agg_arg_real(spec, f, cols, i, v)) continue;
+        cnt++; fs += v;
         continue;
       }
       cnt++;
@@ -647,11 +678,20 @@ static int agg_setup(AggImpl* a, const tg_agg_desc* d) {
   for (int k = 0; k < d->n_funcs; k++) {
     const tg_agg_func& f = d->funcs[k];
     AggFuncDev& o = a->spec.f[k];
-    o = AggFuncDev{f.name, f.arg_col, 0, 0, -1, -1, 0, f.arg_col2};
+    o = AggFuncDev{f.name, f.arg_col, 0, 0, -1, -1, 0, f.arg_col2, f.arg_expr, 0, f.arg_const};
+    if (f.arg_expr != TG_ARGEXPR_COL) {
+      if (f.arg_expr != TG_ARGEXPR_MUL && f.arg_expr != TG_ARGEXPR_MUL_CSUB) return fail(TG_ERR_INVALID, "unknown aggregate argument expression");
+      if ((f.name != TG_AGG_SUM && f.name != TG_AGG_AVG) || f.mode != TG_AGGMODE_COMPLETE)
+        return fail(TG_ERR_UNSUPPORTED, "argument expressions are fused for SUM / AVG in Complete mode only");
+      if (f.arg_col < 0 || f.arg_col2 < 0 || f.arg_col2 >= d->n_cols || a->types[f.arg_col] != TG_TYPE_DOUBLE || a->types[f.arg_col2] != TG_TYPE_DOUBLE)
+        return fail(TG_ERR_UNSUPPORTED, "argument expressions take two DOUBLE columns");
+      a->needed[f.arg_col2] = 1;
+    }
     if (f.mode != TG_AGGMODE_COMPLETE && f.mode != TG_AGGMODE_FINAL) return fail(TG_ERR_UNSUPPORTED, "only Complete and Final aggregate modes are offloaded");
     o.final_mode = f.mode == TG_AGGMODE_FINAL;
     if (f.arg_col >= a->ncols || f.arg_col2 >= a->ncols) return fail(TG_ERR_INVALID, "aggregate argument column out of range");
     bool arg_nullable = f.arg_col >= 0 && !(a->flags[f.arg_col] & TG_FLAG_NOT_NULL);
+    if (f.arg_expr != TG_ARGEXPR_COL && f.arg_col2 >= 0 && f.arg_col2 < d->n_cols && !(a->flags[f.arg_col2] & TG_FLAG_NOT_NULL)) arg_nullable = true;
     if (f.arg_col >= 0) { if (a->elem[f.arg_col] != 8) return fail(TG_ERR_UNSUPPORTED, "aggregate arguments must be 8-byte columns"); a->needed[f.arg_col] = 1; }
     int atype = f.arg_col >= 0 ? a->types[f.arg_col] : TG_TYPE_LONGLONG;
     o.is_real = atype == TG_TYPE_DOUBLE;
@@ -932,11 +972,12 @@ static int local_partial_pass(AggImpl* a, const GroupKey& gk, const DevCols& col
 }
 
 // aggregate n device-resident rows
-static int update_device(AggImpl* a, const DevCols& cols, int64_t n) {
+static int update_device_impl(AggImpl* a, const DevCols& cols, int64_t n) {
   if (n == 0) return TG_OK;
   a->stats.input_rows += n;
   TG_TRY(a->scalars.ensure(a->device, 64));
   unsigned long long* sc = a->scalars.as<unsigned long long>();
+  a->spec.err = sc + 7;    // raised by a fused argument expression that left the DOUBLE range (types.ErrOverflow)
   if (a->nslots == 0) {
     unsigned long long want = 1024;
     if (a->group_col >= 0) {
@@ -1036,6 +1077,19 @@ static int update_device(AggImpl* a, const DevCols& cols, int64_t n) {
   TG_CUDA(cudaStreamSynchronize(a->stream));
   TG_CUDA(cudaGetLastError());
   float ms = 0; cudaEventElapsedTime(&ms, a->ev0, a->ev1); a->stats.update_ms += ms;
+  return TG_OK;
+}
+
+// aggregate n device-resident rows; a fused argument expression that overflowed fails the call (types.ErrOverflow)
+static int update_device(AggImpl* a, const DevCols& cols, int64_t n) {
+  TG_TRY(update_device_impl(a, cols, n));
+  bool has_expr = false;
+  for (int k = 0; k < a->spec.n; k++) has_expr |= a->spec.f[k].arg_expr != TG_ARGEXPR_COL;
+  if (!has_expr || n == 0) return TG_OK;
+  unsigned long long e = 0;
+  TG_CUDA(cudaMemcpyAsync(&e, a->scalars.as<unsigned long long>() + 7, 8, cudaMemcpyDeviceToHost, a->stream));
+  TG_CUDA(cudaStreamSynchronize(a->stream));
+  if (e) return fail(TG_ERR_OVERFLOW, "ErrOverflow: DOUBLE value is out of range in an aggregate argument expression");
   return TG_OK;
 }
 

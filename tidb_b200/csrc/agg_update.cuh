@@ -81,7 +81,9 @@ __device__ __forceinline__ void agg_apply2(const AggTable& t, const LocalTable& 
           cnt = arg_raw(cols, f.arg_col, row);
           vcol = f.arg_col2;
         }
-        double v = __longlong_as_double((long long)arg_raw(cols, vcol, row));
+        double v;
+        if (f.arg_expr) { if (!agg_arg_real(spec, f, cols, row, v)) break; }
+        else v = __longlong_as_double((long long)arg_raw(cols, vcol, row));
         if (SH) sred_add_f64(lt_state(lt, f.s0, (uint32_t)s), v); else atomicAdd(reinterpret_cast<double*>(&t.state[f.s0][s]), v);
         if (f.s1 >= 0) {
           if (!SH) atomicAdd(&t.state[f.s1][s], cnt);

@@ -651,7 +651,7 @@ static bool fast_path_ok(const JoinImpl* j, const DevCols& pview) {
 }
 
 // ---- fast-path launch tuning (env overrides are for A/B sweeps on the GPU box; defaults are the measured best) ----
-struct ProbeTuning { int variant; int R; int evict_last; int ctas_per_sm; int partition; int parts; int part_min_mb; int part_min_rows; int seg_vec; int seg_lean; int carveout; int tma; int stages; int tma_ctas; int cta_agg; };
+struct ProbeTuning { int variant; int R; int evict_last; int ctas_per_sm; int partition; int subseg; int parts; int part_min_mb; int part_min_rows; int seg_vec; int seg_lean; int carveout; int tma; int stages; int tma_ctas; int cta_agg; };
 static ProbeTuning probe_tuning() {
   ProbeTuning t;
   t.variant = env_int("TG_PROBE_VARIANT", 1);      // 0: CTA-tile kernel (shared-memory offsets), 1: warp-autonomous kernel
@@ -659,6 +659,7 @@ static ProbeTuning probe_tuning() {
   t.evict_last = env_int("TG_PROBE_EVICT_LAST", 0);
   t.ctas_per_sm = env_int("TG_PROBE_CTAS_PER_SM", 0);   // 0 = exactly the resident CTA count (occupancy query)
   t.partition = env_int("TG_PROBE_PARTITION", 1);   // regroup big probes into L2-sized partitions first (0 = never, 2 = counted/dense variant)
+  t.subseg = env_int("TG_PROBE_SUBSEG", 1);         // CTA-private sub-segments in the L2 partition pass (no global cursor atomics)
   t.parts = env_int("TG_PROBE_PARTS", 0);           // 0 = auto: table slices of <= 32 MB
   t.part_min_mb = env_int("TG_PROBE_PART_MIN_MB", 64);
   t.part_min_rows = env_int("TG_PROBE_PART_MIN_ROWS", 1 << 22);
@@ -823,24 +824,36 @@ static int probe_device(JoinImpl* j, const DevCols& pview, int64_t n, ResultBatc
           int P = tune.parts > 0 ? tune.parts : (int)((table_bytes + (32u << 20) - 1) / (32u << 20));
           if (P > TG_MAX_PARTS) P = TG_MAX_PARTS;
           const int64_t n_main = n / PTILE * PTILE;
-          const int64_t C = ((int64_t)((double)n_main / P * 1.05) + 16384 + 127) / 128 * 128;
-          if (P >= 2 && (int64_t)P * C / 128 < (1ll << 31)) {
-            const int nc = 1 + fo.n_pcols;
+          const int nc = 1 + fo.n_pcols;
+          // Segment layout.  Default (TG_PROBE_SUBSEG=1): every scatter CTA owns a private sub-segment of each partition —
+          // G = grid, sub-segment (p, b) = rows [(p*G + b) * C, ...) — so tiles are placed with a shared-memory cursor and
+          // the scatter needs no global atomics (0.575 -> see profiles/r2_*); the probe sweeps P*G segments, partition-major.
+          // TG_PROBE_SUBSEG=0: one segment per partition filled through global cursors (round 1).
+          const int G = tune.subseg ? scatter_bulk_grid_nc(j->device, n_main, nc) : 1;
+          const int64_t nsegs = (int64_t)P * G;
+          const int64_t C = tune.subseg ? ((int64_t)((double)n_main / nsegs * 1.06) + PTILE / P + 256 + 127) / 128 * 128   // + one tile's share: CTAs differ by a tile
+                                        : ((int64_t)((double)n_main / P * 1.05) + 16384 + 127) / 128 * 128;
+          if (P >= 2 && G >= 1 && nsegs * C / 128 < (1ll << 31)) {
             for (int c = 0; c < nc; c++) {
               if (!j->part_cols[c]) j->part_cols[c].reset(new DevBuf());
-              TG_TRY(j->part_cols[c]->ensure(j->device, (size_t)P * C * 8 + 64));
+              TG_TRY(j->part_cols[c]->ensure(j->device, (size_t)nsegs * C * 8 + 64));
             }
-            TG_TRY(j->part_scratch.ensure(j->device, (size_t)TG_MAX_PARTS * 8 * 2 + 64));
+            TG_TRY(j->part_scratch.ensure(j->device, (size_t)(nsegs + 2 * TG_MAX_PARTS) * 8 + 64));
             unsigned long long* cursors = j->part_scratch.as<unsigned long long>();     // fill count per segment
-            long long* bases = reinterpret_cast<long long*>(cursors + TG_MAX_PARTS);     // first row of each segment
-            unsigned long long* flag = cursors + 2 * TG_MAX_PARTS;                       // overflow
-            k_segment_bases<<<1, 32, 0, j->stream>>>(cursors, bases, flag, P, C);
+            long long* bases = reinterpret_cast<long long*>(cursors + nsegs);            // first row of each segment (one per partition)
+            unsigned long long* flag = cursors + nsegs + TG_MAX_PARTS;                   // overflow
             PartDst d{};
             d.nparts = P; d.ncols = nc;
             d.src[0] = pkey;
             for (int c = 0; c < fo.n_pcols; c++) d.src[1 + c] = fo.psrc[c];
             for (int c = 0; c < nc; c++) for (int q = 0; q < P; q++) d.dst[q][c] = j->part_cols[c]->p;
-            d.dst_base = bases; d.capacity = C; d.overflow = flag;
+            if (tune.subseg) {
+              TG_CUDA(cudaMemsetAsync(flag, 0, 8, j->stream));
+              d.dst_base = nullptr; d.base_const = 0; d.capacity = C; d.overflow = flag; d.sub_cap = C; d.sub_grid = (uint32_t)G;
+            } else {
+              k_segment_bases<<<1, 32, 0, j->stream>>>(cursors, bases, flag, P, C);
+              d.dst_base = bases; d.capacity = C; d.overflow = flag;
+            }
             if (in_seg) { d.in_cnt = in_seg->cnt; d.in_cap = in_seg->cap; d.in_tiles_per_seg = (uint32_t)(in_seg->cap / PTILE); }
             TG_TRY(launch_partition_scatter<true>(j->device, j->stream, reinterpret_cast<const long long*>(pkey), nullptr, n_main, d, cursors,
                                                   &j->stats.kernel_launches));
@@ -848,8 +861,8 @@ static int probe_device(JoinImpl* j, const DevCols& pview, int64_t n, ResultBatc
             for (int c = 0; c < fo.n_pcols; c++) pf.psrc[c] = j->part_cols[1 + c]->as<unsigned long long>();
             // the 128-bit stores of the segment kernel need 16-byte aligned output columns: results appended behind an odd
             // number of rows fall back to the 8-byte kernel
-            if (tune.seg_vec && (rb.rows & 1) == 0) TG_TRY(launch_probe_seg(j, j->part_cols[0]->as<int64_t>(), (int64_t)P * C, pf, cur, tune, SegSpec{cursors, (uint32_t)(C / 128), 0, C, flag}));
-            else TG_TRY(launch_probe_warp(j, j->part_cols[0]->as<int64_t>(), (int64_t)P * C, pf, cur, tune, SegSpec{cursors, (uint32_t)(C / 128), 0, C, flag}));
+            if (tune.seg_vec && (rb.rows & 1) == 0) TG_TRY(launch_probe_seg(j, j->part_cols[0]->as<int64_t>(), nsegs * C, pf, cur, tune, SegSpec{cursors, (uint32_t)(C / 128), 0, C, flag}));
+            else TG_TRY(launch_probe_warp(j, j->part_cols[0]->as<int64_t>(), nsegs * C, pf, cur, tune, SegSpec{cursors, (uint32_t)(C / 128), 0, C, flag}));
             // gated fallback: probes the ORIGINAL input only after an overflow; the < 1024-row tail the scatter left behind
             // (dense input only) rides on the same launch — it is probed whatever the flag says
             if (in_seg) TG_TRY(launch_probe_warp(j, pkey, n_main, fo, cur, tune, SegSpec{in_seg->cnt, in_seg->tiles_per_seg, 1, in_seg->cap, flag, 0}));

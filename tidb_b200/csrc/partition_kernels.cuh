@@ -30,7 +30,12 @@ struct PartDst {
   // in_cap a multiple of the scatter tile; nullptr = dense input
   const unsigned long long* in_cnt;
   long long in_cap;
-  uint32_t in_tiles_per_seg, pad;
+  uint32_t in_tiles_per_seg, sub_grid;   // sub_grid: the grid the sub-segment layout was sized for (checked at launch)
+  // sub_cap > 0 (k_partition_scatter_bulk only): CTA-PRIVATE sub-segments.  Destination p is split into gridDim.x
+  // sub-segments of sub_cap rows, sub-segment (p, b) at rows [(p * gridDim.x + b) * sub_cap, ...) belongs to CTA b alone,
+  // so a tile is placed with a shared-memory cursor — no global atomic (and its ~1 us round trip between two CTA
+  // barriers) per (tile, destination).  At the end CTA b stores its fill counts to cursors[p * gridDim.x + b].
+  long long sub_cap;
 };
 
 // HIGH = false: destination GPU, low 32 hash bits (disjoint from the slot bits).
@@ -274,10 +279,11 @@ k_partition_scatter_bulk(int64_t ntiles, PartDst d, unsigned long long* __restri
   unsigned long long* stage = ring + (size_t)STAGES * NC * TILE;                   // [NC][SROWS]
   uint64_t* full = reinterpret_cast<uint64_t*>(stage + (size_t)NC * SROWS);
   __shared__ uint32_t s_cnt[TG_MAX_PARTS], s_off[TG_MAX_PARTS], s_len[TG_MAX_PARTS];
-  __shared__ unsigned long long s_gbase[TG_MAX_PARTS];
+  __shared__ unsigned long long s_gbase[TG_MAX_PARTS], s_cur[TG_MAX_PARTS];
   const int tid = threadIdx.x, lane = tid & 31;
   const uint32_t P = (uint32_t)d.nparts;
   const unsigned long long pol = l2_policy_evict_first();
+  if (tid < TG_MAX_PARTS) s_cur[tid] = 0;
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
     mbar_fence_init();
@@ -322,12 +328,20 @@ k_partition_scatter_bulk(int64_t ntiles, PartDst d, unsigned long long* __restri
       uint32_t c = tid < (int)P ? s_cnt[tid] : 0, len = c;
       unsigned long long g = 0;
       if (tid < (int)P) {
-        unsigned long long old = c ? atomicAdd(&cursors[tid], (unsigned long long)c) : 0ull;
-        if (d.capacity > 0) {
-          unsigned long long avail = old < (unsigned long long)d.capacity ? (unsigned long long)d.capacity - old : 0ull;
+        if (d.sub_cap > 0) {   // CTA-private sub-segment: the cursor lives in shared memory
+          const unsigned long long old = s_cur[tid];
+          s_cur[tid] = old + c;
+          const unsigned long long avail = old < (unsigned long long)d.sub_cap ? (unsigned long long)d.sub_cap - old : 0ull;
           if ((unsigned long long)c > avail) { len = (uint32_t)avail; *d.overflow = 1ull; }
+          g = ((unsigned long long)tid * gridDim.x + blockIdx.x) * (unsigned long long)d.sub_cap + old;
+        } else {
+          unsigned long long old = c ? atomicAdd(&cursors[tid], (unsigned long long)c) : 0ull;
+          if (d.capacity > 0) {
+            unsigned long long avail = old < (unsigned long long)d.capacity ? (unsigned long long)d.capacity - old : 0ull;
+            if ((unsigned long long)c > avail) { len = (uint32_t)avail; *d.overflow = 1ull; }
+          }
+          g = old + (unsigned long long)(d.dst_base ? d.dst_base[tid] : d.base_const);
         }
-        g = old + (unsigned long long)(d.dst_base ? d.dst_base[tid] : d.base_const);
       }
       uint32_t w = tid < (int)P ? (((uint32_t)(g & 1) + c + 1) & ~1u) : 0, incl = w;
       for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
@@ -359,6 +373,10 @@ k_partition_scatter_bulk(int64_t ntiles, PartDst d, unsigned long long* __restri
     }
   }
   if (tid < (int)P * NC) bulk_wait_read_all();
+  if (d.sub_cap > 0 && tid < (int)P) {   // fill counts of this CTA's sub-segments (s_cur was last written by this very thread)
+    const unsigned long long c = s_cur[tid];
+    cursors[(size_t)tid * gridDim.x + blockIdx.x] = c < (unsigned long long)d.sub_cap ? c : (unsigned long long)d.sub_cap;
+  }
 }
 
 // histogram of destinations: 128-bit loads, 4 in flight per thread, counts packed 8 x 8 bit in two 64-bit registers
@@ -443,6 +461,18 @@ inline int scatter_bulk_enabled() {
   return v;
 }
 
+// grid the bulk scatter will use for n rows of NC columns (the CTA-private sub-segment layout depends on it)
+template <int NC>
+inline int scatter_bulk_grid(int device, int64_t n) {
+  constexpr int TILE = PT_BLOCK * 4;
+  size_t smem = (size_t)2 * NC * TILE * 8 + (size_t)NC * (TILE + 2 * TG_MAX_PARTS) * 8 + 2 * 8 + 16;
+  int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(220 * 1024) / (smem + 1024)));
+  return (int)std::min<int64_t>(n / TILE, (int64_t)device_sm_count(device) * per_sm);
+}
+inline int scatter_bulk_grid_nc(int device, int64_t n, int nc) {
+  switch (nc) { case 1: return scatter_bulk_grid<1>(device, n); case 2: return scatter_bulk_grid<2>(device, n); case 3: return scatter_bulk_grid<3>(device, n); default: return scatter_bulk_grid<4>(device, n); }
+}
+
 template <bool HIGH, int NC>
 inline int launch_scatter_nc(int device, cudaStream_t st, int64_t n, PartDst& d, unsigned long long* cursors, int64_t* launches, int ctas_per_sm = 0) {
   int nsm = device_sm_count(device);
@@ -461,6 +491,7 @@ inline int launch_scatter_nc(int device, cudaStream_t st, int64_t n, PartDst& d,
       if (!HIGH && cap_env > 0 && per_sm > cap_env) per_sm = cap_env;
       if (ctas_per_sm > 0 && per_sm > ctas_per_sm) per_sm = ctas_per_sm;
       int grid = (int)std::min<int64_t>(ntiles, (int64_t)nsm * per_sm);
+      if (d.sub_cap > 0 && (uint32_t)grid != d.sub_grid) return fail(TG_ERR_CUDA, "internal: sub-segment layout sized for another grid");
       k_partition_scatter_bulk<HIGH, NC, ITEMS><<<grid, PT_BLOCK, smem, st>>>(ntiles, d, cursors);
       if (launches) (*launches)++;
     }

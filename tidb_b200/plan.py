@@ -161,6 +161,8 @@ class AggFunc:
     arg_flag: int = 0
     mode: int = abi.AGGMODE_COMPLETE
     arg_col2: int = -1
+    arg_expr: int = 0          # abi.ARGEXPR_*: the argument as arg_col * arg_col2 / arg_col * (arg_const - arg_col2)
+    arg_const: float = 0.0
 
 
 @dataclass
@@ -183,6 +185,7 @@ class AggPlan:
         for i, f in enumerate(self.funcs):
             fa[i].name, fa[i].mode, fa[i].arg_col = f.name, f.mode, f.arg_col
             fa[i].arg_type, fa[i].arg_flag, fa[i].arg_col2 = f.arg_type, f.arg_flag, f.arg_col2
+            fa[i].arg_expr, fa[i].arg_const = f.arg_expr, f.arg_const
         keep.append(fa)
         d.funcs = fa
         d.n_funcs = len(self.funcs)
