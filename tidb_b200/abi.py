@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libtidbgpu.so")
+LIB_PATH = os.environ.get("TIDBGPU_LIB") or os.path.join(_HERE, "csrc", "libtidbgpu.so")   # TIDBGPU_LIB: A/B runs against another build of the same ABI
 
 # ---- status codes (tg_status) -------------------------------------------------------------------
 TG_OK, TG_ERR_INVALID, TG_ERR_UNSUPPORTED, TG_ERR_CUDA, TG_ERR_OOM = 0, 1, 2, 3, 4

@@ -659,7 +659,7 @@ static ProbeTuning probe_tuning() {
   t.evict_last = env_int("TG_PROBE_EVICT_LAST", 0);
   t.ctas_per_sm = env_int("TG_PROBE_CTAS_PER_SM", 0);   // 0 = exactly the resident CTA count (occupancy query)
   t.partition = env_int("TG_PROBE_PARTITION", 1);   // regroup big probes into L2-sized partitions first (0 = never, 2 = counted/dense variant)
-  t.subseg = env_int("TG_PROBE_SUBSEG", 1);         // CTA-private sub-segments in the L2 partition pass (no global cursor atomics)
+  t.subseg = env_int("TG_PROBE_SUBSEG", 0);         // 1 = CTA-private sub-segments in the L2 partition pass (no global cursor atomics): MEASURED SLOWER (scatter 0.62 vs 0.575 ms: 7104 write streams; probe 2.3 vs 1.36 ms: the interleaved empty tails let warps drift across partitions) - kept for the record, off
   t.parts = env_int("TG_PROBE_PARTS", 0);           // 0 = auto: table slices of <= 32 MB
   t.part_min_mb = env_int("TG_PROBE_PART_MIN_MB", 64);
   t.part_min_rows = env_int("TG_PROBE_PART_MIN_ROWS", 1 << 22);
@@ -825,10 +825,9 @@ static int probe_device(JoinImpl* j, const DevCols& pview, int64_t n, ResultBatc
           if (P > TG_MAX_PARTS) P = TG_MAX_PARTS;
           const int64_t n_main = n / PTILE * PTILE;
           const int nc = 1 + fo.n_pcols;
-          // Segment layout.  Default (TG_PROBE_SUBSEG=1): every scatter CTA owns a private sub-segment of each partition —
-          // G = grid, sub-segment (p, b) = rows [(p*G + b) * C, ...) — so tiles are placed with a shared-memory cursor and
-          // the scatter needs no global atomics (0.575 -> see profiles/r2_*); the probe sweeps P*G segments, partition-major.
-          // TG_PROBE_SUBSEG=0: one segment per partition filled through global cursors (round 1).
+          // Segment layout.  Default: one segment per partition filled through global cursors.  TG_PROBE_SUBSEG=1 (experiment,
+          // measured slower, profiles/r2_subseg.md): every scatter CTA owns a private sub-segment of each partition —
+          // G = grid, sub-segment (p, b) = rows [(p*G + b) * C, ...) — placed with a shared-memory cursor, no global atomics.
           const int G = tune.subseg ? scatter_bulk_grid_nc(j->device, n_main, nc) : 1;
           const int64_t nsegs = (int64_t)P * G;
           const int64_t C = tune.subseg ? ((int64_t)((double)n_main / nsegs * 1.06) + PTILE / P + 256 + 127) / 128 * 128   // + one tile's share: CTAs differ by a tile
@@ -838,10 +837,11 @@ static int probe_device(JoinImpl* j, const DevCols& pview, int64_t n, ResultBatc
               if (!j->part_cols[c]) j->part_cols[c].reset(new DevBuf());
               TG_TRY(j->part_cols[c]->ensure(j->device, (size_t)nsegs * C * 8 + 64));
             }
-            TG_TRY(j->part_scratch.ensure(j->device, (size_t)(nsegs + 2 * TG_MAX_PARTS) * 8 + 64));
+            const int64_t ncur = std::max<int64_t>(nsegs, TG_MAX_PARTS);                 // k_segment_bases zeroes TG_MAX_PARTS cursors
+            TG_TRY(j->part_scratch.ensure(j->device, (size_t)(ncur + 2 * TG_MAX_PARTS) * 8 + 64));
             unsigned long long* cursors = j->part_scratch.as<unsigned long long>();     // fill count per segment
-            long long* bases = reinterpret_cast<long long*>(cursors + nsegs);            // first row of each segment (one per partition)
-            unsigned long long* flag = cursors + nsegs + TG_MAX_PARTS;                   // overflow
+            long long* bases = reinterpret_cast<long long*>(cursors + ncur);             // first row of each segment (one per partition)
+            unsigned long long* flag = cursors + ncur + TG_MAX_PARTS;                    // overflow
             PartDst d{};
             d.nparts = P; d.ncols = nc;
             d.src[0] = pkey;

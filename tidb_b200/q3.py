@@ -8,10 +8,9 @@ Plan shape follows the reference's TiFlash MPP plan for Q3 (pkg/planner/core/cas
           Selection(c_mktsegment = S) on customer                  (build side)
 
 Everything runs through the C-ABI operators: the three Selections are fused into the joins as build / probe
-filters (tg_filter_item), the projection l_extendedprice * (1 - l_discount) is two VecEval kernels, and the
-aggregation is tg_agg.  o_orderdate and o_shippriority are functionally dependent on the order key, so the
-aggregate groups by l_orderkey and carries them as MAX() — the multi-column GROUP BY itself is not offloaded yet
-(tg_agg_supported declines it).
+filters (tg_filter_item), and the
+aggregation is tg_agg with all three GROUP BY columns (tag-claimed multi-word slots) and the projection
+l_extendedprice * (1 - l_discount) fused into its update kernel (tg_agg_func.arg_expr), followed by tg_topn.
 """
 from __future__ import annotations
 
@@ -61,49 +60,77 @@ def _view(ptr: int, n: int, dev, dt="<i8"):
     return torch.as_tensor(a, device=dev)
 
 
-def run(d: Q3Data, dev, stream) -> Dict[str, torch.Tensor]:
-    """-> {orderkey, revenue, o_date, o_prio} (unordered), all device tensors"""
+def _col_struct(ptr: int, n: int, nulls: int = 0):
+    c = abi.TgColumn(); c.length = n; c.data = ptr or None; c.elem_len = 8; c.null_bitmap = nulls or None; c.offsets = None
+    return c
+
+
+def run(d: Q3Data, dev, stream, topn: int = 10, timings: Dict[str, float] = None, keep_groups: bool = True) -> Dict[str, torch.Tensor]:
+    """The whole query on the device.  -> {orderkey, revenue, o_date, o_prio} of every group (unordered, device tensors) and,
+    under "top", the TopN rows (host numpy arrays, ORDER BY revenue DESC, o_orderdate LIMIT topn).
+    Operators: J1 = orders JOIN customer (Selections fused as build/probe filters), J2 = lineitem JOIN J1 (J1's device-resident
+    output is the build side, borrowed, no copy), HashAgg GROUP BY (l_orderkey, o_orderdate, o_shippriority) with
+    SUM(l_extendedprice * (1 - l_discount)) evaluated INSIDE the update kernel (tg_agg_func.arg_expr: no projected column,
+    the constant is a scalar), TopN (tg_topn)."""
+    import numpy as np
     lib = abi.load_lib()
     st = stream.cuda_stream
     di = dev.index or 0
-    # J1: orders (probe, filter o_date < D) ⋈ customer (build, filter c_seg = S); keep o_orderkey, o_date, o_prio
+    marks = []
+
+    def mark(name):
+        if timings is not None:
+            e = torch.cuda.Event(enable_timing=True); e.record(stream); marks.append((name, e))
+    mark("start")
+    # J1: orders (probe, filter o_date < D) JOIN customer (build, filter c_seg = S); keep o_orderkey, o_date, o_prio
     j1 = DeviceJoin(JoinPlan(abi.JOIN_INNER, [INT] * 4, [INT] * 2, [1], [0], build_is_right=True, lused=[0, 2, 3], rused=[],
                              build_filter=[FilterItem(abi.CMP_EQ, 1, const_i64=SEGMENT)], probe_filter=[FilterItem(abi.CMP_LT, 2, const_i64=DATE)],
                              device=di, stream=st))
     j1.build([d.c_custkey, d.c_seg])
+    mark("J1 build (customer, c_mktsegment filter fused)")
     n1, c1, _ = j1.probe([d.o_orderkey, d.o_custkey, d.o_date, d.o_prio])
-    ok, od, op = (_view(p, n1, dev).clone() for p in c1)
-    j1.close()
-    # J2: lineitem (probe, filter l_ship > D) ⋈ J1 (build on o_orderkey); keep l_orderkey, l_price, l_disc, o_date, o_prio
+    mark("J1 probe (orders, o_orderdate filter fused)")
+    # J2: lineitem (probe, filter l_ship > D) JOIN J1 (build on o_orderkey); keep l_orderkey, l_price, l_disc, o_date, o_prio
     j2 = DeviceJoin(JoinPlan(abi.JOIN_INNER, [INT, DBL, DBL, INT], [INT] * 3, [0], [0], build_is_right=True, lused=[0, 1, 2], rused=[1, 2],
                              probe_filter=[FilterItem(abi.CMP_GT, 3, const_i64=DATE)], device=di, stream=st))
-    j2.build([ok, od, op])
+    j2.build([_view(p, n1, dev) for p in c1])     # borrowed until build_finish: J1's result buffers are read in place
+    mark("J2 build (J1 output, in place)")
+    j1.close()
     n2, c2, _ = j2.probe([d.l_orderkey, d.l_price, d.l_disc, d.l_ship])
+    mark("J2 probe (lineitem, l_shipdate filter fused)")
     lk = _view(c2[0], n2, dev); price = _view(c2[1], n2, dev, "<f8"); disc = _view(c2[2], n2, dev, "<f8")
     jd = _view(c2[3], n2, dev); jp = _view(c2[4], n2, dev)
-    # projection: l_extendedprice * (1 - l_discount)   (builtinArithmeticMinusRealSig / MultiplyRealSig)
-    one_minus = torch.empty(n2, dtype=torch.float64, device=dev); rev = torch.empty(n2, dtype=torch.float64, device=dev)
-    nb = torch.empty((n2 + 7) // 8 + 8, dtype=torch.uint8, device=dev)
-
-    def col(t):
-        c = abi.TgColumn(); c.length = t.numel(); c.data = t.data_ptr() if t.numel() else None; c.elem_len = 8; c.null_bitmap = None
-        return c
-    ones = torch.ones(n2, dtype=torch.float64, device=dev)
-    c_ones, c_disc, c_price = col(ones), col(disc), col(price)
-    abi.check(lib.tg_vec_arith_real(di, 1, abi.ARITH_MINUS, C.byref(c_ones), C.byref(c_disc), C.c_double(0), C.c_void_p(one_minus.data_ptr()),
-                                    C.c_void_p(nb.data_ptr()), C.c_void_p(st)))
-    c_om = col(one_minus)
-    abi.check(lib.tg_vec_arith_real(di, 1, abi.ARITH_MUL, C.byref(c_price), C.byref(c_om), C.c_double(0), C.c_void_p(rev.data_ptr()),
-                                    C.c_void_p(nb.data_ptr()), C.c_void_p(st)))
-    # aggregate
-    agg = DeviceAgg(AggPlan([INT, DBL, INT, INT], [0], [AggFunc(abi.AGG_FIRSTROW, 0), AggFunc(abi.AGG_SUM, 1, abi.TYPE_DOUBLE),
-                                                        AggFunc(abi.AGG_MAX, 2), AggFunc(abi.AGG_MAX, 3)],
+    # HashAgg: GROUP BY l_orderkey, o_orderdate, o_shippriority; SUM(l_extendedprice * (1 - l_discount)) fused
+    agg = DeviceAgg(AggPlan([INT, DBL, DBL, INT, INT], [0, 3, 4],
+                            [AggFunc(abi.AGG_FIRSTROW, 0), AggFunc(abi.AGG_SUM, 1, abi.TYPE_DOUBLE, arg_col2=2, arg_expr=abi.ARGEXPR_MUL_CSUB, arg_const=1.0),
+                             AggFunc(abi.AGG_FIRSTROW, 3), AggFunc(abi.AGG_FIRSTROW, 4)],
                             device=di, stream=st, expected_groups=max(n1, 1)))
-    agg.push([lk, rev, jd, jp])
-    ng, ca, _ = agg.finish()
-    out = {"orderkey": _view(ca[0], ng, dev).clone(), "revenue": _view(ca[1], ng, dev, "<f8").clone(),
-           "o_date": _view(ca[2], ng, dev).clone(), "o_prio": _view(ca[3], ng, dev).clone()}
+    agg.push([lk, price, disc, jd, jp])
+    ng, ca, na = agg.finish()
+    mark("HashAgg (3 GROUP BY columns, projection fused)")
+    out = {"groups": ng}
+    if keep_groups:   # copies of the whole aggregate result (verification); the query's own result is the TopN below
+        out.update({"orderkey": _view(ca[0], ng, dev).clone(), "revenue": _view(ca[1], ng, dev, "<f8").clone(),
+                    "o_date": _view(ca[2], ng, dev).clone(), "o_prio": _view(ca[3], ng, dev).clone()})
+    # TopN: ORDER BY revenue DESC, o_orderdate LIMIT topn  (tpch_suite_out.json:102)
+    if topn > 0:
+        cols = (abi.TgColumn * 4)(*[_col_struct(ca[k], ng, na[k]) for k in range(4)])
+        ck = abi.TgChunk(); ck.ncols = 4; ck.cols = C.cast(cols, C.POINTER(abi.TgColumn)); ck.sel = None; ck.nsel = 0
+        tps = (C.c_int32 * 4)(abi.TYPE_LONGLONG, abi.TYPE_DOUBLE, abi.TYPE_LONGLONG, abi.TYPE_LONGLONG)
+        fls = (C.c_uint32 * 4)(0, 0, 0, 0)
+        items = (abi.TgSortItem * 2)(abi.TgSortItem(1, 1), abi.TgSortItem(2, 0))
+        from .chunk import MutChunk
+        oc = MutChunk([8, 8, 8, 8], max(topn, 8), [np.int64, np.float64, np.int64, np.int64])
+        got = C.c_int64(0)
+        abi.check(lib.tg_topn(di, 1, C.byref(ck), tps, fls, items, 2, C.c_int64(0), C.c_int64(topn), C.byref(oc.struct), C.byref(got), C.c_void_p(st)))
+        out["top"] = [v.copy() for v, _ in oc.columns(got.value)]
+        mark("TopN")
     agg.close(); j2.close()
+    if timings is not None:
+        stream.synchronize()
+        for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
+            timings[name] = timings.get(name, 0.0) + a.elapsed_time(b)
+        timings["rows"] = {"j1_out": n1, "j2_out": n2, "groups": ng}
     return out
 
 

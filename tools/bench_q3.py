@@ -23,11 +23,14 @@ with torch.cuda.stream(stream):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(a.steps):
-        q3.run(d, dev, stream)
+        q3.run(d, dev, stream, keep_groups=False)
     e1.record(stream)
+    stream.synchronize()
+    t = {}
+    q3.run(d, dev, stream, keep_groups=False, timings=t)
 stream.synchronize()
 ms = e0.elapsed_time(e1) / a.steps
 peak, src = peaks()
-rec = dict(op="Q3-shape", sf=a.sf, rows=dict(customer=nc, orders=no, lineitem=nl), groups=int(got["orderkey"].numel()), ms=ms,
+rec = dict(op="Q3-shape", sf=a.sf, rows=dict(customer=nc, orders=no, lineitem=nl), groups=int(got["orderkey"].numel()), ms=ms, phases_ms={k: round(v, 3) for k, v in t.items() if k != "rows"}, operator_rows=t.get("rows"),
            scanned_gb=d.scanned_bytes() / 1e9, gbs=d.scanned_bytes() / ms / 1e6, frac=d.scanned_bytes() / ms / 1e6 / peak, verified=bool(a.verify))
 print(json.dumps(rec)); os.makedirs(os.path.dirname(a.out), exist_ok=True); open(a.out, "a").write(json.dumps(rec) + "\n")
