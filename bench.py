@@ -498,11 +498,42 @@ def run_gpu(args):
                 "nvlink": {"payload_gbs_per_direction_per_gpu": nvl, "reference_gbs": 770.0, "frac": nvl / 770.0,
                            "note": "16 B per exchanged row; reference = measured peer-copy bandwidth per direction (B200_PROFILING.md)"}}
 
+    # ---- side line (N = 1): the 50 % match variant of the same workload (SURVEY 8d input 2) ---------------------------
+    side50 = None
+    if world == 1 and not args.skip_side:
+        with torch.cuda.stream(stream):
+            g2 = torch.Generator(device=dev); g2.manual_seed(4343)
+            pk2 = torch.randint(0, 2 * nb, (npb,), device=dev, generator=g2, dtype=torch.int64) * ODD      # uniform over twice the key range
+            rows2, cols2, _ = join.probe([pk2, pv], sync=True)
+            o_pk, o_pv, o_bk, o_bv = [dview(p, rows2) for p in cols2]
+            assert bool((o_pk == o_bk).all()) and bool((o_bv * ODD == o_bk * 7).all())
+            assert bool((pk2[o_pv] == o_pk).all()), "output rows must carry their own probe key"
+            # bit-exact row count: a probe key matches iff its id (key * ODD^-1 mod 2^64) is below nb; ids were drawn directly
+            g2.manual_seed(4343)
+            ids2 = torch.randint(0, 2 * nb, (npb,), device=dev, generator=g2, dtype=torch.int64)
+            assert rows2 == int((ids2 < nb).sum().item()), "50 % match: output row count differs from the number of matching probe keys"
+            del ids2
+            for _ in range(3):
+                join.probe([pk2, pv], sync=False)
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(stream)
+            for _ in range(args.steps):
+                join.probe([pk2, pv], sync=False)
+            s1.record(stream)
+        stream.synchronize()
+        ms2 = s0.elapsed_time(s1) / args.steps
+        b2 = 16 * npb + 16 * rows2 + 32 * rows2
+        side50 = {"workload": "same join, probe keys uniform over twice the build key range (50 % match)", "ms_per_step": ms2, "value": npb / (ms2 * 1e-3),
+                  "unit": "rows/s", "output_rows": rows2, "algorithmic_bytes": b2, "achieved_gbs": b2 / (ms2 * 1e-3) / 1e9, "frac": b2 / (ms2 * 1e-3) / 1e9 / hbm_peak}
+        del pk2
+
     # ---- e2e: host buffers through tg_join_probe_push / tg_join_next (N = 1 path; per rank at N > 1) ---------
     e2e = None
     if not args.skip_e2e:
         if world == 1:
             e2e = run_e2e(args, lib, abi, torch, dev, local, rank, world, bk, bv, pk, pv, barrier)
+            # side figure: the parent operator does not read build.k (it equals probe.k) -> RUsed = [build.v], 3 output columns
+            e2e["pruned_3_columns"] = run_e2e(args, lib, abi, torch, dev, local, rank, world, bk, bv, pk, pv, barrier, rused=[1])
         else:
             e2e = (run_e2e_mail(args, torch, dist, dev, stream, xstream, rank, world, pk, pv, xmail, join, barrier, dview) if xmail is not None else
                    run_e2e_multi(args, torch, dist, dev, stream, xstream, rank, world, pk, pv, xch_p, bounds, join, barrier))
@@ -544,6 +575,8 @@ def run_gpu(args):
         }
         if roof:
             line["roofline"] = roof
+        if side50:
+            line["side_match_50"] = side50
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
@@ -558,8 +591,10 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def run_e2e(args, lib, abi, torch, dev, local, rank, world, bk, bv, pk, pv, barrier):
-    """The probe through the host-facing C-ABI: pinned host columns in, pinned host columns out."""
+def run_e2e(args, lib, abi, torch, dev, local, rank, world, bk, bv, pk, pv, barrier, rused=None):
+    """The probe through the host-facing C-ABI: pinned host columns in, pinned host columns out.
+    rused = RUsed of the plan (None = all build columns, the reference harness; [1] = the parent does not read the build
+    key, which equals the probe key: column pruning, builder.go:1868-1871)."""
     from tidb_b200.plan import JoinPlan
     nb, npb = bk.numel(), pk.numel()
     chunk_rows = args.e2e_chunk_rows
@@ -579,8 +614,10 @@ def run_e2e(args, lib, abi, torch, dev, local, rank, world, bk, bv, pk, pv, barr
         np_view(p, npb)[:] = t.cpu().numpy()
     for p, t in zip(hb, (bk, bv)):
         np_view(p, nb)[:] = t.cpu().numpy()
-    out = [pinned(chunk_rows * 8) for _ in range(4)]
+    n_out = 2 + (2 if rused is None else len(rused))
+    out = [pinned(chunk_rows * 8) for _ in range(n_out)]
     plan = make_plan(local, 0)
+    plan.rused = rused
     desc, keep = plan.to_struct()
     h = C.c_void_p()
     abi.check(lib.tg_join_open(C.byref(desc), C.byref(h)))
@@ -596,10 +633,10 @@ def run_e2e(args, lib, abi, torch, dev, local, rank, world, bk, bv, pk, pv, barr
         ck = host_chunk(hb, lo, min(chunk_rows, nb - lo))
         abi.check(lib.tg_join_build_push(h, C.byref(ck)))
     abi.check(lib.tg_join_build_finish(h))
-    mc = (abi.TgMutColumn * 4)()
-    for i in range(4):
+    mc = (abi.TgMutColumn * n_out)()
+    for i in range(n_out):
         mc[i].data = out[i].value; mc[i].null_bitmap = None; mc[i].elem_len = 8
-    mch = abi.TgMutChunk(); mch.ncols = 4; mch.cols = C.cast(mc, C.POINTER(abi.TgMutColumn)); mch.capacity_rows = chunk_rows
+    mch = abi.TgMutChunk(); mch.ncols = n_out; mch.cols = C.cast(mc, C.POINTER(abi.TgMutColumn)); mch.capacity_rows = chunk_rows
 
     def one_pass():
         """a fresh probe of the whole probe side.  Two host threads, like the reference's probe fetcher goroutine and
@@ -652,7 +689,8 @@ def run_e2e(args, lib, abi, torch, dev, local, rank, world, bk, bv, pk, pv, barr
         import torch.distributed as dist
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     sec_step = float(tt.item()) / steps
-    return {"value": npb * world / sec_step, "unit": "rows/s", "h2d_bytes_per_step": 16 * npb, "d2h_bytes_per_step": 32 * npb,
+    return {"value": npb * world / sec_step, "unit": "rows/s", "h2d_bytes_per_step": 16 * npb, "d2h_bytes_per_step": 8 * n_out * npb,
+            "output_columns": n_out, "pcie_d2h_gbs": 8 * n_out * npb / sec_step / 1e9, "pcie_h2d_gbs": 16 * npb / sec_step / 1e9,
             "ms_per_step": sec_step * 1e3, "steps": steps, "chunk_rows": chunk_rows,
             "path": "thread A: tg_join_probe_push(host pinned 4M-row chunks) -> kernels; thread B: tg_join_next_wait -> D2H into host pinned buffers",
             "timing": "host wall clock around the passes, device synchronised on both sides (host work is part of the path)"}
@@ -745,6 +783,9 @@ def run_e2e_mail(args, torch, dist, dev, stream, xstream, rank, world, pk, pv, x
         return total
 
     steps = max(2, args.steps // 2)
+    with torch.cuda.stream(stream):
+        xm.discard_outstanding(stream)      # the device-resident loop keeps one step in flight
+    xm._primed = False
     rows = one_pass(2)
     tot = torch.tensor([rows], dtype=torch.int64, device=dev); dist.all_reduce(tot)
     assert int(tot.item()) == npb * world
@@ -784,6 +825,7 @@ def main():
     ap.add_argument("--dma", type=int, default=1, help="N>1, --exchange cf: regroup locally, let copy engines move the regions over NVLink")
     ap.add_argument("--xchunks", type=int, default=1, help="N>1: pieces the probe side is exchanged in (overlap with the probe kernel)")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-side", action="store_true", help="skip the 50 %% match side line (N = 1)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--ncu-traffic-bytes", type=float, default=None, help="dram bytes per launch from the committed ncu capture")
     args = ap.parse_args()

@@ -623,6 +623,13 @@ class MailboxExchange:
         self.abi.check(self.lib.tg_mail_signal(self.device, C.byref(self.targets[(self.KIND_ACK, s_)]), None, C.c_int64(epoch), C.c_void_p(probe_stream.cuda_stream)))
         self.launches += 1
 
+    def discard_outstanding(self, probe_stream):
+        """consume (without probing) every step that was sent but not received yet, e.g. the step a pipelined loop keeps in
+        flight when it stops; afterwards sends and receives are level again"""
+        while self.recv_steps < self.sent_steps:
+            _c, _n, _cap, s_, ep = self.recv(probe_stream)
+            self.release(probe_stream, s_, ep)
+
     def check(self):
         """host check (synchronises): a region overflow or a mailbox timeout anywhere fails the run on every rank"""
         self.torch.cuda.synchronize(self.dev)
