@@ -213,6 +213,9 @@ def run_reference(args):
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------
 def run_gpu(args):
+    # the exchange keeps up to 16 copy streams + compute + NCCL busy: more hardware work queues than the default 8, or streams
+    # that share a queue serialise behind each other (must be set before the CUDA context exists)
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     import torch
     import torch.distributed as dist
     from tidb_b200 import abi
@@ -309,7 +312,7 @@ def run_gpu(args):
     xmail = None
     mail_choice = None
     mail_timings = {}
-    MAIL_CANDIDATES = {"mail": dict(dma=False, ctas_per_sm=args.scatter_ctas), "mail-dma": dict(dma=True, ctas_per_sm=args.scatter_ctas)}
+    MAIL_CANDIDATES = {"mail": dict(dma=False, ctas_per_sm=args.scatter_ctas), "mail-dma": dict(dma=True, ctas_per_sm=args.scatter_ctas, copy_streams=args.copy_streams)}
 
     def mail_step(xm, sync: bool):
         """ALL SM kernels of a rank on ONE stream, in the order regroup(k+1), probe(k): the shared-memory-heavy scatter never
@@ -820,6 +823,7 @@ def main():
                          "move the regions; auto = time mail / mail (2 scatter CTAs per SM) / mail-dma untimed and keep the fastest; cf = round-1 count-free exchange "
                          "(NCCL all-gather per step); p2p = counted peer stores; nccl = local scatter + all_to_all")
     ap.add_argument("--slack", type=float, default=1.03, help="N>1, mailbox exchange: receive-region capacity = expected share x slack + 8192 rows (uniform keys: 3 %% is > 100 sigma)")
+    ap.add_argument("--copy-streams", type=int, default=0, help="N>1, mail-dma: streams the peer copies are spread over (0 = one per copy, at most 16)")
     ap.add_argument("--scatter-ctas", type=int, default=0, help="N>1, --exchange mail: cap on the exchange kernel's CTAs per SM (0 = as many as fit)")
     ap.add_argument("--overlap", type=int, default=2, help="N>1, --exchange cf: 1: run the exchange of step k+1 on a second stream under the probe of step k; 2: additionally a transfer stream, so regroup / NVLink copy / probe work on three consecutive steps")
     ap.add_argument("--dma", type=int, default=1, help="N>1, --exchange cf: regroup locally, let copy engines move the regions over NVLink")

@@ -1,0 +1,48 @@
+"""Worker of tests/test_gpu_multigpu.py::test_q3_two_ranks_vs_oracle (one process per GPU): the distributed Q3-shape plan
+(tidb_b200/q3.py:Q3Distributed) on per-rank shards; every rank dumps its shard's columns, rank 0 also the final TopN."""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", required=True)
+    ap.add_argument("--cust", type=int, default=20_000)
+    ap.add_argument("--orders", type=int, default=200_000)
+    ap.add_argument("--line", type=int, default=800_000)
+    a = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    from tidb_b200 import q3
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        d = q3.gen(dev, a.cust, a.orders, a.line, rank=rank, world=world)
+    stream.synchronize()
+    qd = q3.Q3Distributed(rank, world, dev, stream, d.o_orderkey.numel(), d.l_orderkey.numel())
+    t = {}
+    res = qd.run(d, topn=10, timings=t)
+    res2 = qd.run(d, topn=10)                     # a second execution reuses the exchange buffers
+    assert [x.tolist() for x in res["top"]] == [x.tolist() for x in res2["top"]] and res["groups"] == res2["groups"]
+    out = {k: v.cpu().numpy() for k, v in d.__dict__.items()}
+    out["groups"] = np.array([res["groups"]])
+    for c in range(4):
+        out[f"top{c}"] = np.asarray(res["top"][c])
+    np.savez(os.path.join(a.out, f"q3_rank{rank}.npz"), **out)
+    qd.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -119,6 +119,34 @@ def test_gpu_other_condition_gate():
     assert lib.tg_join_supported(C.byref(d)) == abi.TG_ERR_UNSUPPORTED
 
 
+@pytest.mark.parametrize("build_is_right", [True, False])
+@pytest.mark.parametrize("uq", ["1", "0"])
+def test_gpu_unique_key_single_pass_probe(build_is_right, uq, monkeypatch):
+    # k_probe_inner_uq: inner join, unique build keys, two NOT NULL build payload columns (row store), probe filters, a probe
+    # key column with NULLs that is not output, the sentinel-valued key; TG_PROBE_UQ=0 sends the same plan down the general
+    # count -> scan -> write path, both against the oracle
+    monkeypatch.setenv("TG_PROBE_UQ", uq)
+    rng = np.random.default_rng(77 + int(build_is_right))
+    nb, npr = 40_000, 300_000
+    bk = rng.permutation(nb * 3)[:nb].astype(np.int64) * 2654435761 - (1 << 41)
+    bk[3] = -(1 << 63)
+    build = Chunk([Column(bk), Column(np.arange(nb, dtype=np.int64) * 3), Column(rng.integers(0, 9, nb).astype(np.int64))])
+    pick = rng.integers(0, nb * 2, npr)
+    pk = np.where(pick < nb, bk[np.minimum(pick, nb - 1)], pick.astype(np.int64) * 11 + 5)
+    pkn = rng.random(npr) < 0.05
+    f = rng.integers(0, 100, npr).astype(np.int64)
+    probe = Chunk([Column(np.arange(npr, dtype=np.int64)), Column(pk, pkn), Column(f), Column(rng.random(npr))])
+    ptypes, btypes = [INT_NN, INT, INT_NN, FieldType(abi.TYPE_DOUBLE, abi.FLAG_NOT_NULL)], [INT_NN, INT_NN, INT_NN]
+    pf = [FilterItem(abi.CMP_LT, 2, const_i64=60), FilterItem(abi.CMP_GT, 3, is_real=True, const_f64=0.25)]
+    if build_is_right:
+        plan = JoinPlan(abi.JOIN_INNER, ptypes, btypes, [1], [0], build_is_right=True, lused=[0, 3], rused=[1, 2, 0], probe_filter=pf)
+        l, r = probe.split(1 << 15), build.split(1 << 13)
+    else:
+        plan = JoinPlan(abi.JOIN_INNER, btypes, ptypes, [0], [1], build_is_right=False, lused=[2, 1], rused=[0, 2], probe_filter=pf)
+        l, r = build.split(1 << 13), probe.split(1 << 15)
+    assert_rows_equal(run_oracle(plan, l, r), run_gpu(plan, l, r, required_rows=1 << 16))
+
+
 def test_gpu_double_keys_and_mixed_sign():
     rng = np.random.default_rng(5)
     ltypes, rtypes, l, r = make_case(rng, 1500, 2000, 0.1, True, False, key_dtype=np.float64)

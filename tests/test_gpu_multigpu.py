@@ -58,3 +58,33 @@ def test_mailbox_exchange_two_ranks_vs_oracle(dma):
     for k in range(world):
         assert int(res[k]["overflow_detected"][0]) == 1, "a receive-region overflow must be reported on every rank"
         assert int(res[k]["timeout_detected"][0]) == 1, "a silent sender must end the wait with an error, not a hang"
+
+
+def test_q3_two_ranks_vs_oracle():
+    # the distributed Q3-shape plan (broadcast customer, repartition filtered orders and lineitem by order key over NVLink,
+    # shard-local J2 + HashAgg + TopN, global TopN) on 2 ranks against the oracle operators on the concatenated shards
+    lib = abi.load_lib()
+    if lib.tg_device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import topn as OT
+    from test_gpu_q3 import oracle_q3
+    world = 2
+    with tempfile.TemporaryDirectory() as td:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+               "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "mgpu_q3_worker.py"), "--out", td]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        if r.returncode != 0 and os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+            open(os.path.join(ROOT, "gpurun_out", "mgpu_q3_worker.log"), "w").write(r.stdout + "\n==== stderr ====\n" + r.stderr)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-6000:]
+        res = [dict(np.load(os.path.join(td, f"q3_rank{k}.npz"))) for k in range(world)]
+    cols = ["c_custkey", "c_seg", "o_orderkey", "o_custkey", "o_date", "o_prio", "l_orderkey", "l_price", "l_disc", "l_ship"]
+    h = {c: np.concatenate([res[k][c] for k in range(world)]) for c in cols}
+    n1, n2, ng, (ok, rev, od, op) = oracle_q3(h)
+    assert int(res[0]["groups"][0]) == ng
+    exp_top = OT.topn_rows(list(zip(ok.tolist(), rev.tolist(), od.tolist(), op.tolist())), ["int", "real", "int", "int"], [(1, True), (2, False)], 0, 10)
+    top = [res[0][f"top{c}"] for c in range(4)]
+    assert len(top[0]) == len(exp_top) == 10
+    for i, e in enumerate(exp_top):
+        assert (int(top[0][i]), int(top[2][i]), int(top[3][i])) == (e[0], e[2], e[3])
+        assert top[1][i] == pytest.approx(e[1], rel=1e-6)

@@ -63,7 +63,12 @@ struct AggTable {
   // column (NULL stored as 0) plus, when a column is nullable, a word with the columns' NULL bits
   unsigned long long* tags;
   long long* keyw[TG_MAX_GROUP_COLS + 1];
-  int32_t nkw, pad;
+  int32_t nkw;
+  // element stride of every array above, in 8-byte words: 1 = structure of arrays (single-key tables: hot groups live in
+  // L2 and same-sector atomics would serialise, profiles/r2_agg_lab.md); multi-key tables are ARRAY OF RECORDS
+  // [tag | key words | rows | states], padded to 32 bytes: their groups are mostly cold (Q3: 2.4 rows per group, a 1.4 GB
+  // table), and a row should touch one or two DRAM sectors instead of one per array
+  uint32_t stride;
 };
 struct GroupKey { const void* data; const uint8_t* nulls; int32_t kind; int32_t pad; };
 struct GroupKeys { int32_t n, nkw; const void* data[TG_MAX_GROUP_COLS]; const uint8_t* nulls[TG_MAX_GROUP_COLS]; int32_t kind[TG_MAX_GROUP_COLS]; };
@@ -83,23 +88,24 @@ __global__ void k_agg_init(AggTable t, AggSpec spec, unsigned long long n_total)
   unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
   unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   for (; i < n_total; i += stride) {
-    if (t.nkw) t.tags[i] = 0; else t.keys[i] = kEmptyKey;
-    t.rows[i] = 0;
+    if (t.nkw) { t.tags[(size_t)i * t.stride] = 0; for (int j = 0; j < t.nkw; j++) t.keyw[j][(size_t)i * t.stride] = 0; }
+    else t.keys[i] = kEmptyKey;
+    t.rows[(size_t)i * t.stride] = 0;
     for (int k = 0; k < spec.n; k++) {
       const AggFuncDev& f = spec.f[k];
       if (f.s0 >= 0) {
         unsigned long long init = 0;
         if (f.name == TG_AGG_MIN) init = ~0ull;          // ordered domain: larger than everything
-        t.state[f.s0][i] = init;
+        t.state[f.s0][(size_t)i * t.stride] = init;
       }
-      if (f.s1 >= 0) t.state[f.s1][i] = 0;
+      if (f.s1 >= 0) t.state[f.s1][(size_t)i * t.stride] = 0;
     }
   }
 }
 
 __device__ __forceinline__ void agg_apply(const AggTable& t, const AggSpec& spec, const DevCols& cols, int64_t row,
                                           unsigned long long s) {
-  atomicAdd(&t.rows[s], 1ull);
+  atomicAdd(&t.rows[(size_t)s * t.stride], 1ull);
   for (int k = 0; k < spec.n; k++) {
     const AggFuncDev& f = spec.f[k];
     if (f.arg_col < 0 || f.s0 < 0) continue;   // COUNT(*) and NOT NULL COUNT(x) read rows[]; FIRSTROW reads the key
@@ -107,27 +113,27 @@ __device__ __forceinline__ void agg_apply(const AggTable& t, const AggSpec& spec
     if (nb && !bit_not_null(nb, row)) continue;
     switch (f.name) {
       case TG_AGG_COUNT:
-        if (f.final_mode) atomicAdd(&t.state[f.s0][s], reinterpret_cast<const unsigned long long*>(cols.data[f.arg_col])[row]);
-        else atomicAdd(&t.state[f.s0][s], 1ull);
+        if (f.final_mode) atomicAdd(&t.state[f.s0][(size_t)s * t.stride], reinterpret_cast<const unsigned long long*>(cols.data[f.arg_col])[row]);
+        else atomicAdd(&t.state[f.s0][(size_t)s * t.stride], 1ull);
         break;
       case TG_AGG_SUM: {
         double v;
         if (!agg_arg_real(spec, f, cols, row, v)) break;
-        atomicAdd(reinterpret_cast<double*>(&t.state[f.s0][s]), v);
-        if (f.s1 >= 0) atomicAdd(&t.state[f.s1][s], 1ull);
+        atomicAdd(reinterpret_cast<double*>(&t.state[f.s0][(size_t)s * t.stride]), v);
+        if (f.s1 >= 0) atomicAdd(&t.state[f.s1][(size_t)s * t.stride], 1ull);
         break;
       }
       case TG_AGG_AVG:
         if (f.final_mode) {   // args: count column, sum column (func_avg.go:405)
           const uint8_t* nb2 = cols.nulls[f.arg_col2];
           if (nb2 && !bit_not_null(nb2, row)) break;
-          atomicAdd(reinterpret_cast<double*>(&t.state[f.s0][s]), reinterpret_cast<const double*>(cols.data[f.arg_col2])[row]);
-          atomicAdd(&t.state[f.s1][s], reinterpret_cast<const unsigned long long*>(cols.data[f.arg_col])[row]);
+          atomicAdd(reinterpret_cast<double*>(&t.state[f.s0][(size_t)s * t.stride]), reinterpret_cast<const double*>(cols.data[f.arg_col2])[row]);
+          atomicAdd(&t.state[f.s1][(size_t)s * t.stride], reinterpret_cast<const unsigned long long*>(cols.data[f.arg_col])[row]);
         } else {
           double v;
           if (!agg_arg_real(spec, f, cols, row, v)) break;
-          atomicAdd(reinterpret_cast<double*>(&t.state[f.s0][s]), v);
-          if (f.s1 >= 0) atomicAdd(&t.state[f.s1][s], 1ull);
+          atomicAdd(reinterpret_cast<double*>(&t.state[f.s0][(size_t)s * t.stride]), v);
+          if (f.s1 >= 0) atomicAdd(&t.state[f.s1][(size_t)s * t.stride], 1ull);
         }
         break;
       case TG_AGG_MIN: case TG_AGG_MAX: {
@@ -135,8 +141,8 @@ __device__ __forceinline__ void agg_apply(const AggTable& t, const AggSpec& spec
         if (f.is_real) v = f64_to_ordered(reinterpret_cast<const double*>(cols.data[f.arg_col])[row]);
         else if (f.is_unsigned) v = reinterpret_cast<const unsigned long long*>(cols.data[f.arg_col])[row];
         else v = i64_to_ordered(reinterpret_cast<const long long*>(cols.data[f.arg_col])[row]);
-        if (f.name == TG_AGG_MIN) atomicMin(&t.state[f.s0][s], v); else atomicMax(&t.state[f.s0][s], v);
-        if (f.s1 >= 0) atomicAdd(&t.state[f.s1][s], 1ull);
+        if (f.name == TG_AGG_MIN) atomicMin(&t.state[f.s0][(size_t)s * t.stride], v); else atomicMax(&t.state[f.s0][(size_t)s * t.stride], v);
+        if (f.s1 >= 0) atomicAdd(&t.state[f.s1][(size_t)s * t.stride], 1ull);
         break;
       }
       default: break;
@@ -279,6 +285,7 @@ k_agg_update_local(GroupKey gk, DevCols cols, int64_t row_lo, int64_t row_hi, Ag
   const int LS = local_slots, NT = local_slots + 2;
   const unsigned int max_local_fill = (unsigned int)(local_slots / 2);
   AggTable lt;
+  lt.stride = 1; lt.nkw = 0; lt.tags = nullptr;
   lt.nslots = (unsigned long long)LS;
   lt.keys = reinterpret_cast<long long*>(smem_raw);
   lt.rows = reinterpret_cast<unsigned long long*>(smem_raw) + NT;
@@ -414,7 +421,7 @@ __global__ void k_agg_count(AggTable t, unsigned long long* count) {
   unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
   unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   unsigned long long c = 0;
-  for (; i < n_total; i += stride) c += i < t.nslots ? (t.nkw ? t.tags[i] != 0 : t.keys[i] != kEmptyKey) : (t.rows[i] != 0);
+  for (; i < n_total; i += stride) c += i < t.nslots ? (t.nkw ? t.tags[(size_t)i * t.stride] != 0 : t.keys[i] != kEmptyKey) : (t.rows[(size_t)i * t.stride] != 0);
   for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
 }
@@ -432,30 +439,30 @@ k_agg_finalize(AggTable t, AggSpec spec, int gk_kind, AggOut out, unsigned long 
   for (; base < n_total; base += stride) {
     unsigned long long i = base + threadIdx.x;
     bool occ = false;
-    if (i < t.nslots) occ = t.nkw ? t.tags[i] != 0 : t.keys[i] != kEmptyKey;
-    else if (i < n_total) occ = t.rows[i] != 0;
+    if (i < t.nslots) occ = t.nkw ? t.tags[(size_t)i * t.stride] != 0 : t.keys[i] != kEmptyKey;
+    else if (i < n_total) occ = t.rows[(size_t)i * t.stride] != 0;
     unsigned b = __ballot_sync(0xffffffffu, occ);
     unsigned long long wbase = 0;
     if (lane == 0 && b) wbase = atomicAdd(cursor, (unsigned long long)__popc(b));
     wbase = __shfl_sync(0xffffffffu, wbase, 0);
     if (!occ) continue;
     unsigned long long o = wbase + __popc(b & ((1u << lane) - 1));
-    unsigned long long rows = t.rows[i];
+    unsigned long long rows = t.rows[(size_t)i * t.stride];
     for (int k = 0; k < spec.n; k++) {
       const AggFuncDev& f = spec.f[k];
-      unsigned long long nn = f.s1 >= 0 ? t.state[f.s1][i] : rows;   // non-NULL inputs seen
+      unsigned long long nn = f.s1 >= 0 ? t.state[f.s1][(size_t)i * t.stride] : rows;   // non-NULL inputs seen
       bool valid = true;
       unsigned long long v = 0;
       switch (f.name) {
-        case TG_AGG_COUNT: v = (f.arg_col < 0 || f.s0 < 0) ? rows : t.state[f.s0][i]; break;
-        case TG_AGG_SUM: valid = nn != 0; v = t.state[f.s0][i]; break;   // NULL when no non-NULL input (func_sum.go:80)
+        case TG_AGG_COUNT: v = (f.arg_col < 0 || f.s0 < 0) ? rows : t.state[f.s0][(size_t)i * t.stride]; break;
+        case TG_AGG_SUM: valid = nn != 0; v = t.state[f.s0][(size_t)i * t.stride]; break;   // NULL when no non-NULL input (func_sum.go:80)
         case TG_AGG_AVG:
           valid = nn != 0;
-          if (valid) v = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)t.state[f.s0][i]) / (double)nn);   // func_avg.go:332
+          if (valid) v = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)t.state[f.s0][(size_t)i * t.stride]) / (double)nn);   // func_avg.go:332
           break;
         case TG_AGG_MIN: case TG_AGG_MAX: {
           valid = nn != 0;
-          unsigned long long u = t.state[f.s0][i];
+          unsigned long long u = t.state[f.s0][(size_t)i * t.stride];
           if (f.is_real) v = (unsigned long long)__double_as_longlong(ordered_to_f64(u));
           else if (f.is_unsigned) v = u;
           else v = u ^ 0x8000000000000000ull;
@@ -464,8 +471,8 @@ k_agg_finalize(AggTable t, AggSpec spec, int gk_kind, AggOut out, unsigned long 
         default:   // FIRSTROW(group column): the group key itself (firstRow4Int func_first_row.go:140)
           if (t.nkw) {   // f.arg_col2 = index of the column among the GROUP BY items | word with the NULL bits << 8 (0 = none)
             const int g = f.arg_col2 & 0xff, nullword = (f.arg_col2 >> 8) & 0xff;
-            if (nullword && ((unsigned long long)t.keyw[nullword][i] >> g) & 1ull) valid = false;
-            else v = (unsigned long long)t.keyw[g][i];
+            if (nullword && ((unsigned long long)t.keyw[nullword][(size_t)i * t.stride] >> g) & 1ull) valid = false;
+            else v = (unsigned long long)t.keyw[g][(size_t)i * t.stride];
           }
           else if (i == t.nslots) valid = false;                       // NULL group
           else if (i == t.nslots + 1) v = (unsigned long long)kEmptyKey;
@@ -516,20 +523,26 @@ __device__ __forceinline__ unsigned long long mk_find_or_insert(const AggTable& 
   const unsigned long long ready = h | 3ull, busy = (h & ~3ull) | 1ull;
   uint32_t s = slot32(h, (uint32_t)t.nslots), steps = 0;
   for (;;) {
-    unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&t.tags[s]);
+    // tag and the first three key words sit in the record's first 32 bytes: ONE L2-coherent 256-bit load (records are 32-byte aligned)
+    unsigned long long cur, k0, k1, k2;
+    asm volatile("ld.global.cg.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(cur), "=l"(k0), "=l"(k1), "=l"(k2) : "l"(&t.tags[(size_t)s * t.stride]) : "memory");
     if (cur == 0) {
-      cur = atomicCAS(&t.tags[s], 0ull, busy);
+      cur = atomicCAS(&t.tags[(size_t)s * t.stride], 0ull, busy);
       if (cur == 0) {
-        for (int j = 0; j < t.nkw; j++) t.keyw[j][s] = k.w[j];
+        for (int j = 0; j < t.nkw; j++) t.keyw[j][(size_t)s * t.stride] = k.w[j];
         __threadfence();
-        *reinterpret_cast<volatile unsigned long long*>(&t.tags[s]) = ready;   // publish
+        *reinterpret_cast<volatile unsigned long long*>(&t.tags[(size_t)s * t.stride]) = ready;   // publish
         return s;
       }
     }
     if ((cur | 2ull) == ready) {
-      while (cur != ready) cur = *reinterpret_cast<volatile unsigned long long*>(&t.tags[s]);   // the claimer is still writing the key words
-      bool eq = true;
-      for (int j = 0; j < t.nkw; j++) eq &= *reinterpret_cast<volatile long long*>(&t.keyw[j][s]) == k.w[j];
+      bool eq = cur == ready && (unsigned long long)k.w[0] == k0 && (t.nkw < 2 || (unsigned long long)k.w[1] == k1) && (t.nkw < 3 || (unsigned long long)k.w[2] == k2);
+      if (eq && t.nkw > 3) eq = *reinterpret_cast<volatile long long*>(&t.keyw[3][(size_t)s * t.stride]) == k.w[3];
+      if (!eq) {   // still being written, or the vector load raced with the writer, or a different key with the same hash: settle it with ordered loads
+        while (cur != ready) cur = *reinterpret_cast<volatile unsigned long long*>(&t.tags[(size_t)s * t.stride]);
+        eq = true;
+        for (int j = 0; j < t.nkw; j++) eq &= *reinterpret_cast<volatile long long*>(&t.keyw[j][(size_t)s * t.stride]) == k.w[j];
+      }
       if (eq) return s;
     }
     if (++steps > max_probe) return ~0ull;
@@ -560,16 +573,16 @@ __global__ void k_agg_rehash_mk(AggTable oldt, AggTable newt, int nstates) {
   unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   for (; i < oldt.nslots; i += stride) {
-    const unsigned long long tag = oldt.tags[i];
+    const unsigned long long tag = oldt.tags[(size_t)i * oldt.stride];
     if (tag == 0) continue;
     uint32_t s = slot32(tag, (uint32_t)newt.nslots);
     for (;;) {
-      if (atomicCAS(&newt.tags[s], 0ull, tag) == 0ull) break;
+      if (atomicCAS(&newt.tags[(size_t)s * newt.stride], 0ull, tag) == 0ull) break;
       if (++s == (uint32_t)newt.nslots) s = 0;
     }
-    for (int j = 0; j < oldt.nkw; j++) newt.keyw[j][s] = oldt.keyw[j][i];
-    newt.rows[s] = oldt.rows[i];
-    for (int a = 0; a < nstates; a++) newt.state[a][s] = oldt.state[a][i];
+    for (int j = 0; j < oldt.nkw; j++) newt.keyw[j][(size_t)s * newt.stride] = oldt.keyw[j][(size_t)i * oldt.stride];
+    newt.rows[(size_t)s * newt.stride] = oldt.rows[(size_t)i * oldt.stride];
+    for (int a = 0; a < nstates; a++) newt.state[a][(size_t)s * newt.stride] = oldt.state[a][(size_t)i * oldt.stride];
   }
 }
 
@@ -743,20 +756,30 @@ static int agg_setup(AggImpl* a, const tg_agg_desc* d) {
   return TG_OK;
 }
 
+static int table_record_words(const AggImpl* a) { return a->nkw ? ((1 + a->nkw + 1 + a->nstates + 3) / 4) * 4 : (2 + a->nstates); }
 static void layout_table(AggImpl* a, uint8_t* mem, unsigned long long nslots, AggTable& t) {
   size_t n = (size_t)nslots + 2;
   t.nslots = nslots;
   t.nkw = a->nkw;
+  if (a->nkw) {   // array of records: [tag | nkw key words | rows | states], padded to a multiple of 32 bytes
+    unsigned long long* w = reinterpret_cast<unsigned long long*>(mem);
+    t.stride = (uint32_t)table_record_words(a);
+    t.tags = w; t.keys = reinterpret_cast<long long*>(w);
+    for (int j = 0; j < a->nkw; j++) t.keyw[j] = reinterpret_cast<long long*>(w + 1 + j);
+    t.rows = w + 1 + a->nkw;
+    for (int s = 0; s < a->nstates; s++) t.state[s] = w + 2 + a->nkw + s;
+    return;
+  }
+  t.stride = 1;
   t.keys = reinterpret_cast<long long*>(mem);
-  t.tags = reinterpret_cast<unsigned long long*>(mem);          // multi-key tables: the tag array takes the place of keys[]
+  t.tags = reinterpret_cast<unsigned long long*>(mem);
   t.rows = reinterpret_cast<unsigned long long*>(mem + n * 8);
   for (int s = 0; s < a->nstates; s++) t.state[s] = reinterpret_cast<unsigned long long*>(mem + n * 8 * (2 + s));
-  for (int j = 0; j < a->nkw; j++) t.keyw[j] = reinterpret_cast<long long*>(mem + n * 8 * (2 + a->nstates + j));
 }
 
 static int alloc_table(AggImpl* a, unsigned long long nslots, DevBuf& mem, AggTable& t) {
   size_t n = (size_t)nslots + 2;
-  TG_TRY(mem.ensure(a->device, n * 8 * (2 + a->nstates + a->nkw)));
+  TG_TRY(mem.ensure(a->device, n * 8 * (size_t)table_record_words(a) + 64));
   layout_table(a, mem.as<uint8_t>(), nslots, t);
   k_agg_init<<<agrid(a, (int64_t)n), 256, 0, a->stream>>>(t, a->spec, n);
   a->stats.kernel_launches++;

@@ -650,6 +650,19 @@ static bool fast_path_ok(const JoinImpl* j, const DevCols& pview) {
   return true;
 }
 
+// single-pass unique-key probe (k_probe_inner_uq): inner join, every build key unique, no OtherCondition, 8-byte output
+// columns that cannot be NULL (probe used columns without a bitmap in this batch, build columns without NULLs)
+static bool uq_path_ok(const JoinImpl* j, const DevCols& pview) {
+  static int en = -1;
+  if (en < 0) en = env_int("TG_PROBE_UQ", 1);
+  if (!en || j->probe_kind != PK_INNER || j->need_scan || !j->other.empty() || j->stats.max_dup > 1) return false;
+  if (j->tv.mode != TABLE_U1 && j->tv.mode != TABLE_G) return false;
+  for (int c : j->probe.used) if (j->probe.elem[c] != 8 || pview.nulls[c]) return false;
+  for (int c : j->build.used) if (j->build.elem[c] != 8 || j->bcols.has_nulls[c]) return false;
+  for (int e : j->out_elem) if (e != 8) return false;
+  return true;
+}
+
 // ---- fast-path launch tuning (env overrides are for A/B sweeps on the GPU box; defaults are the measured best) ----
 struct ProbeTuning { int variant; int R; int evict_last; int ctas_per_sm; int partition; int subseg; int parts; int part_min_mb; int part_min_rows; int seg_vec; int seg_lean; int carveout; int tma; int stages; int tma_ctas; int cta_agg; };
 static ProbeTuning probe_tuning() {
@@ -929,6 +942,29 @@ static int probe_device(JoinImpl* j, const DevCols& pview, int64_t n, ResultBatc
       rb.rows += (int64_t)got;
       j->stats.output_rows += (int64_t)got;
     }
+    return TG_OK;
+  }
+  // single-pass path: inner join on unique build keys with filters / several payload columns (k_probe_inner_uq)
+  if (uq_path_ok(j, pview) && !in_seg) {
+    TG_TRY(ensure_result(j, rb, rb.rows + n, rb.rows > 0, rb.rows));
+    OutCols oc{};
+    fill_outspec_probe(j, oc);
+    for (int c = 0; c < j->n_out; c++) { oc.data[c] = rb.cols[c]->as<uint8_t>() + (size_t)rb.rows * 8; oc.valid[c] = nullptr; if (rb.bitmaps[c]->p) rb.bitmaps[c]->release(); }
+    unsigned long long* cur = j->out_cursor.as<unsigned long long>();
+    TG_CUDA(cudaMemsetAsync(cur, 0, 8, j->stream));
+    if (n > 0) {
+      int64_t tiles = (n + 256 * UQ_R - 1) / (256 * UQ_R);
+      int grid = (int)std::min<int64_t>(tiles, (int64_t)j->nsm * 8);
+      k_probe_inner_uq<<<grid, 256, 0, j->stream>>>(ks, pview, p.filter, n, j->tv, oc, cur);
+      j->stats.kernel_launches++;
+    }
+    // the output row count decides rb.rows (and the next append position): always needed on the host
+    unsigned long long got = 0;
+    TG_CUDA(cudaMemcpyAsync(&got, cur, 8, cudaMemcpyDeviceToHost, j->stream));
+    TG_CUDA(cudaStreamSynchronize(j->stream));
+    TG_CUDA(cudaGetLastError());
+    rb.rows += (int64_t)got;
+    j->stats.output_rows += (int64_t)got;
     return TG_OK;
   }
   // general path, in sub-batches

@@ -1019,6 +1019,75 @@ k_probe_write(int64_t n, const unsigned long long* __restrict__ off, const uint3
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// probe — single pass for inner joins on UNIQUE build keys (any number of NOT NULL build payload columns, probe
+// filters, NULL-able keys): SetChunkForProbe's filter + innerJoinProbe.Probe (base_join_probe.go:179, inner_join_probe.go:27)
+// fused.  The general path costs three passes (count, scan, write) and two table gathers per matching row; with at most
+// one match per probe row the output position is a warp ballot + one cursor atomic per warp row-group, so one pass does
+// it: R rows per thread, all first-slot gathers of a tile in flight before the first compare.  Output order is arrival
+// order (unspecified in the reference too).  Q3-shape: lineitem (600 M rows, l_shipdate filter) against the filtered
+// orders runs here instead of count -> scan -> write.
+// ---------------------------------------------------------------------------------------------
+#define UQ_R 4
+__global__ void __launch_bounds__(256)
+k_probe_inner_uq(KeySpec key, DevCols pcols, DevFilter filt, int64_t n, TableView t, OutCols out, unsigned long long* __restrict__ out_cursor) {
+  const int lane = threadIdx.x & 31;
+  const int64_t tile = 256 * UQ_R;
+  for (int64_t base = (int64_t)blockIdx.x * tile; base < n; base += (int64_t)gridDim.x * tile) {
+    int64_t k[UQ_R];
+    unsigned long long sl[UQ_R];
+    Slot v[UQ_R];
+    bool valid[UQ_R];
+#pragma unroll
+    for (int r = 0; r < UQ_R; r++) {
+      const int64_t i = base + (int64_t)r * 256 + threadIdx.x;
+      valid[r] = i < n;
+      k[r] = 0;
+      if (valid[r] && filt.n) valid[r] = eval_filter(filt, pcols, i);
+      if (valid[r]) valid[r] = load_key(key, i, k[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < UQ_R; r++) {
+      sl[r] = t.nslots; v[r].key = kEmptyKey; v[r].meta = 0;
+      if (valid[r]) {
+        if (k[r] != kEmptyKey) sl[r] = home_slot(hash64((uint64_t)k[r]), t.nslots, t.pair_home);
+        v[r] = load_slot(t.slots + sl[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < UQ_R; r++) {
+      const int64_t i = base + (int64_t)r * 256 + threadIdx.x;
+      bool m = false;
+      if (valid[r]) {
+        if (k[r] == kEmptyKey) m = v[r].key != 0;                       // the side slot is occupied iff a build row carried this key
+        else {
+          while (v[r].key != k[r] && v[r].key != kEmptyKey) { if (++sl[r] == t.nslots) sl[r] = 0; v[r] = load_slot(t.slots + sl[r]); }
+          m = v[r].key == k[r];
+        }
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, m);
+      if (!bal) continue;
+      unsigned long long wbase = 0;
+      if (lane == 0) wbase = atomicAdd(out_cursor, (unsigned long long)__popc(bal));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (!m) continue;
+      const unsigned long long o = wbase + __popc(bal & ((1u << lane) - 1));
+      const unsigned long long* brow = t.mode == TABLE_G ? t.rows + (v[r].meta >> 28) * t.row_words : nullptr;
+      for (int c = 0; c < out.n; c++) {
+        const OutSpec sp = out.spec[c];
+        unsigned long long val;
+        switch (sp.src) {
+          case SRC_PROBE_COL: val = reinterpret_cast<const unsigned long long*>(pcols.data[sp.idx])[i]; break;
+          case SRC_BUILD_KEY: val = (unsigned long long)k[r]; break;
+          case SRC_BUILD_META: val = v[r].meta; break;
+          default: val = brow[sp.idx]; break;   // SRC_BUILD_WORD
+        }
+        reinterpret_cast<unsigned long long*>(out.data[c])[o] = val;
+      }
+    }
+  }
+}
+
 // ScanRowTable (outer_join_probe.go:117, semi_join_probe.go:72): rows of the BUILD side that are
 // (un)matched, taken from the device-resident build columns; probe-side output columns become NULL.
 //   mode 0: emit build rows whose key was never matched (outer join, anti semi) — invalid-key rows included

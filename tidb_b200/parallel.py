@@ -460,7 +460,7 @@ class MailboxExchange:
     SLOTS = 16   # TG_MAIL_MAX_PEERS
 
     def __init__(self, rank: int, world: int, device: int, xstream, ncols: int, rows_per_step: int, slack: float = 1.06,
-                 dma: bool = False, ctas_per_sm: int = 0, timeout_ms: int = 10000):
+                 dma: bool = False, ctas_per_sm: int = 0, timeout_ms: int = 10000, copy_streams: int = 0):
         import torch
         import torch.distributed as dist
         from . import abi
@@ -526,7 +526,11 @@ class MailboxExchange:
                 # pointer so that this lands in staging region p; own rows go straight into the own receive set
                 flat = [self.recv_ptrs[s_][c] if p == rank else row[c] + (p - rank) * self.cap * 8 for p in range(world) for c in range(ncols)]
                 self.stage_arr.append((C.c_void_p * len(flat))(*flat))
-            self.copy_streams = [torch.cuda.Stream(device=self.dev) for _ in range(min(4, world - 1))]
+            # one stream drives one copy engine at a time: the (world-1) x ncols region copies are spread over several streams
+            # (default: one per copy, at most 16).  Measured at 8 GPUs with 4 streams: 430 GB/s per direction, the transfer
+            # (not the SMs) bounded the step (profiles/r2_trace_8gpu_first.txt)
+            ncs = copy_streams if copy_streams > 0 else min(16, (world - 1) * ncols)
+            self.copy_streams = [torch.cuda.Stream(device=self.dev) for _ in range(max(1, ncs))]
             self.dstream = torch.cuda.Stream(device=self.dev)
         torch.cuda.synchronize(self.dev)
         dist.barrier()    # every mailbox is zeroed and mapped before anybody signals
@@ -592,10 +596,11 @@ class MailboxExchange:
             ready = torch.cuda.Event(); ready.record(D)
         for cs in self.copy_streams:
             cs.wait_event(ready)
+        q = 0
         for i in range(1, self.world):
             p = (self.rank + i) % self.world      # ring order spreads the peers' NVLink ingress
-            cs = self.copy_streams[(i - 1) % len(self.copy_streams)]
             for c in range(len(cols)):
+                cs = self.copy_streams[q % len(self.copy_streams)]; q += 1
                 abi.check(lib.tg_memcpy_d2d_async(self.device, C.c_void_p(self.peer_recv[s_][p][c] + self.rank * self.cap * 8),
                                                   C.c_void_p(self.staging[s_][c] + p * self.cap * 8), C.c_size_t(self.cap * 8), C.c_void_p(cs.cuda_stream)))
         with torch.cuda.stream(D):
