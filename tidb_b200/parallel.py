@@ -460,7 +460,7 @@ class MailboxExchange:
     SLOTS = 16   # TG_MAIL_MAX_PEERS
 
     def __init__(self, rank: int, world: int, device: int, xstream, ncols: int, rows_per_step: int, slack: float = 1.06,
-                 dma: bool = False, ctas_per_sm: int = 0, timeout_ms: int = 10000, copy_streams: int = 0):
+                 dma: bool = False, ctas_per_sm: int = 0, timeout_ms: int = 10000, copy_streams: int = 0, direct_peers: int = 0):
         import torch
         import torch.distributed as dist
         from . import abi
@@ -469,6 +469,11 @@ class MailboxExchange:
         self.rank, self.world, self.device, self.stream, self.ncols = rank, world, device, xstream, ncols
         self.dev = torch.device("cuda", device)
         self.dma = bool(dma) and world > 1
+        # dma + direct_peers = K: HYBRID transfer.  The regroup kernel stores the rows of the K next ranks (ring order) straight
+        # into those peers over NVLink (SM bulk stores, ~580 GB/s while the kernel runs) and stages the rest for the copy engines
+        # (~400 GB/s per direction under load at 8 GPUs, profiles/r2_trace_8gpu_cs14.txt): the two paths add up, the copy
+        # engines' share shrinks until it hides behind the probe again
+        self.direct = set(((rank + i) % world) for i in range(1, min(int(direct_peers), world - 1) + 1)) if self.dma else set()
         self.ctas_per_sm = int(ctas_per_sm)
         self.timeout_ms = int(timeout_ms)
         self.cap = region_capacity(rows_per_step, world, slack)
@@ -524,7 +529,8 @@ class MailboxExchange:
                 self.staging.append(row)
                 # the kernel writes destination p at rows [rank*cap, ...) of the pointer it is given: bias the staging
                 # pointer so that this lands in staging region p; own rows go straight into the own receive set
-                flat = [self.recv_ptrs[s_][c] if p == rank else row[c] + (p - rank) * self.cap * 8 for p in range(world) for c in range(ncols)]
+                flat = [self.recv_ptrs[s_][c] if p == rank else (self.peer_recv[s_][p][c] if p in self.direct else row[c] + (p - rank) * self.cap * 8)
+                        for p in range(world) for c in range(ncols)]
                 self.stage_arr.append((C.c_void_p * len(flat))(*flat))
             # one stream drives one copy engine at a time: the (world-1) x ncols region copies are spread over several streams
             # (default: one per copy, at most 16).  Measured at 8 GPUs with 4 streams: 430 GB/s per direction, the transfer
@@ -581,9 +587,10 @@ class MailboxExchange:
         with torch.cuda.stream(cs_):
             if self.staged_free[s_] is not None:
                 cs_.wait_event(self.staged_free[s_])      # the copies of step k-2 have left staging set s_
-            if k >= self.sets and cs_ is self.stream:
+            if k >= self.sets and (cs_ is self.stream or self.direct):
                 # own rows go straight into the own receive set: the own probe of step k-2 must be done.  (On the probe's own
                 # stream that is stream order; on a separate exchange stream it is the ACK mailbox, which includes this rank.)
+                # Hybrid transfer: the kernel also stores into the direct peers, whose probes of step k-2 must be done.
                 abi.check(lib.tg_mail_wait(self.device, C.c_void_p(self._mail(self.KIND_ACK, s_)), self.world, C.c_int64(epoch - self.sets), None, err, C.c_int64(self.timeout_ms), X))
             abi.check(lib.tg_partition_exchange_cf_ex(self.device, C.c_void_p(key.data_ptr()), C.c_int64(key.numel()), self.world, len(cols), src_p,
                                                       self.stage_arr[s_], C.c_int64(self.rank * self.cap), C.c_int64(self.cap),
@@ -599,6 +606,8 @@ class MailboxExchange:
         q = 0
         for i in range(1, self.world):
             p = (self.rank + i) % self.world      # ring order spreads the peers' NVLink ingress
+            if p in self.direct:
+                continue                          # already stored by the regroup kernel
             for c in range(len(cols)):
                 cs = self.copy_streams[q % len(self.copy_streams)]; q += 1
                 abi.check(lib.tg_memcpy_d2d_async(self.device, C.c_void_p(self.peer_recv[s_][p][c] + self.rank * self.cap * 8),
