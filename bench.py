@@ -267,7 +267,7 @@ def run_gpu(args):
             # NVLink scatter of piece c+1 overlaps the probe kernel of piece c
             xch_p = ([KeyExchange(rank, world, local, xstream, 2, int(npb / xchunks * 1.03) + 8192, args.exchange) for _ in range(2 if xchunks > 1 else 1)]
                      if args.exchange in ("p2p", "nccl") else [])
-        if args.exchange in ("mail", "mail-dma", "mail-hybrid", "auto"):
+        if args.exchange in ("mail", "mail-dma", "mail-hybrid", "mail-smcopy", "auto"):
             pass   # created below (after the build side's exchange), possibly several candidates
         elif args.exchange == "cf":
             from tidb_b200.parallel import SegmentExchange
@@ -313,6 +313,7 @@ def run_gpu(args):
     mail_choice = None
     mail_timings = {}
     MAIL_CANDIDATES = {"mail": dict(dma=False, ctas_per_sm=args.scatter_ctas), "mail-dma": dict(dma=True, ctas_per_sm=args.scatter_ctas, copy_streams=args.copy_streams, direct_peers=args.direct_peers),
+                       "mail-smcopy": dict(dma=True, ctas_per_sm=args.scatter_ctas, sm_copy=True, sm_copy_ctas=args.sm_copy_ctas),
                        "mail-hybrid": dict(dma=True, ctas_per_sm=args.scatter_ctas, copy_streams=args.copy_streams, direct_peers=max(1, (world - 1) // 3))}
 
     def mail_step(xm, sync: bool):
@@ -342,9 +343,9 @@ def run_gpu(args):
         if xm.last_transfer is not None:
             stream.wait_event(xm.last_transfer)
 
-    if world > 1 and args.exchange in ("mail", "mail-dma", "mail-hybrid", "auto"):
+    if world > 1 and args.exchange in ("mail", "mail-dma", "mail-hybrid", "mail-smcopy", "auto"):
         from tidb_b200.parallel import MailboxExchange
-        names = ["mail", "mail-dma", "mail-hybrid"] if args.exchange == "auto" else [args.exchange]
+        names = ["mail-dma", "mail-hybrid", "mail"] if args.exchange == "auto" else [args.exchange]   # mail-smcopy measured slower (4.75 vs 3.45 ms at N = 2): explicit only
         timings = {}
         for nm in names:
             xm = MailboxExchange(rank, world, local, xstream, 2, npb, slack=args.slack, **MAIL_CANDIDATES[nm])
@@ -819,11 +820,12 @@ def main():
     ap.add_argument("--cpu-sample-rows", type=int, default=8_000_000)
     ap.add_argument("--ref-sample-rows", type=int, default=8_000_000)
     ap.add_argument("--e2e-chunk-rows", type=int, default=4 << 20)
-    ap.add_argument("--exchange", default="mail", choices=["mail", "mail-dma", "mail-hybrid", "auto", "cf", "p2p", "nccl"],
+    ap.add_argument("--exchange", default="mail", choices=["mail", "mail-dma", "mail-hybrid", "mail-smcopy", "auto", "cf", "p2p", "nccl"],
                     help="N>1 probe-side exchange: mail = count-free peer bulk stores + device mailboxes (no NCCL / host in a step); mail-dma = same, copy engines "
                          "move the regions; auto = time mail / mail (2 scatter CTAs per SM) / mail-dma untimed and keep the fastest; cf = round-1 count-free exchange "
                          "(NCCL all-gather per step); p2p = counted peer stores; nccl = local scatter + all_to_all")
     ap.add_argument("--slack", type=float, default=1.03, help="N>1, mailbox exchange: receive-region capacity = expected share x slack + 8192 rows (uniform keys: 3 %% is > 100 sigma)")
+    ap.add_argument("--sm-copy-ctas", type=int, default=0, help="N>1, mail-smcopy: 128-thread CTAs of the region copy kernel (0 = one per SM)")
     ap.add_argument("--direct-peers", type=int, default=0, help="N>1, mail-dma: peers (ring order) whose rows the regroup kernel stores directly over NVLink; the rest go through the copy engines (mail-hybrid = (N-1)//3)")
     ap.add_argument("--copy-streams", type=int, default=0, help="N>1, mail-dma: streams the peer copies are spread over (0 = one per copy, at most 16)")
     ap.add_argument("--scatter-ctas", type=int, default=0, help="N>1, --exchange mail: cap on the exchange kernel's CTAs per SM (0 = as many as fit)")

@@ -441,6 +441,15 @@ int tg_partition_exchange_cf_ex(int device, const int64_t* key_dev, int64_t rows
                                 int64_t region_cap, int64_t* sent_rows_dev, uint64_t* overflow_dev, int32_t ctas_per_sm,
                                 void* stream);
 
+/* Transfer stage of the count-free exchange on the SMs instead of the copy engines: region r = the first
+ * min(counts_dev[count_index[r]], cap_rows) rows (8 bytes each) of src_dev[r] -> dst_peer[r] (a peer address mapped with
+ * tg_ipc_open).  128-bit loads / stores, no shared memory, <= 32 registers: the kernel fits NEXT TO the persistent probe
+ * kernel on every SM and copies only the filled part of each region (the copy engines move whole regions: the host
+ * never learns the fill).  ctas = 0: one 128-thread CTA per SM.                                                        */
+#define TG_COPY_MAX_REGIONS 64
+int tg_peer_copy_regions(int device, int32_t n_regions, const void* const* src_dev, void* const* dst_peer,
+                         const int32_t* count_index, const int64_t* counts_dev, int64_t cap_rows, int32_t ctas, void* stream);
+
 /* Cross-GPU mailboxes — the synchronisation of the count-free exchange without NCCL and without the host: one 8-byte
  * word per (sender) in a device buffer of the RECEIVER that every sender has mapped with tg_ipc_open.
  *   tg_mail_signal: after everything already enqueued on `stream` (the scatter kernel whose peer stores it publishes),

@@ -33,7 +33,9 @@ def main():
     t = {}
     res = qd.run(d, topn=10, timings=t)
     res2 = qd.run(d, topn=10)                     # a second execution reuses the exchange buffers
-    assert [x.tolist() for x in res["top"]] == [x.tolist() for x in res2["top"]] and res["groups"] == res2["groups"]
+    # same rows (the SUMs may differ in the last bits: the order of the atomic additions is not fixed)
+    assert res["groups"] == res2["groups"] and all(np.array_equal(res["top"][c], res2["top"][c]) for c in (0, 2, 3))
+    assert np.allclose(res["top"][1], res2["top"][1], rtol=1e-9, atol=0)
     out = {k: v.cpu().numpy() for k, v in d.__dict__.items()}
     out["groups"] = np.array([res["groups"]])
     for c in range(4):

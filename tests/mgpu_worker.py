@@ -32,7 +32,7 @@ def main():
     ap.add_argument("--build-rows", type=int, default=60_000)
     ap.add_argument("--probe-rows", type=int, default=300_000)
     ap.add_argument("--steps", type=int, default=4)
-    ap.add_argument("--dma", type=int, default=0, help="0: SM stores, 1: copy engines, 2: hybrid (copy engines + 1 direct peer)")
+    ap.add_argument("--dma", type=int, default=0, help="0: SM stores, 1: copy engines, 2: hybrid (copy engines + 1 direct peer), 3: SM region copy kernel")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -63,7 +63,7 @@ def main():
         lbk, lbv = xb.exchange(dbk, [dbk, dbv])
         join = DeviceJoin(plan)
         join.build([lbk, lbv])
-    xm = MailboxExchange(rank, world, local, xstream, 2, a.probe_rows, dma=bool(a.dma), direct_peers=1 if a.dma == 2 else 0)
+    xm = MailboxExchange(rank, world, local, xstream, 2, a.probe_rows, dma=bool(a.dma), direct_peers=1 if a.dma == 2 else 0, sm_copy=a.dma == 3)
     inputs = []
     for s in range(a.steps):
         _, _, pk, pv = gen(rank, world, a.build_rows, a.probe_rows, s)

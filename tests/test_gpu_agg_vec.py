@@ -214,6 +214,17 @@ def test_agg_fused_argument_expression(group_cols):
     assert ei.value.code == abi.TG_ERR_OVERFLOW
 
 
+def test_agg_next_small_required_rows():
+    # HashAggExec.Next with RequiredRows = 3 on a result that carries NULL bitmaps (SUM over all-NULL groups is NULL)
+    rng = np.random.default_rng(8)
+    n = 5000
+    g = rng.integers(0, 37, n).astype(np.int64)
+    x = rng.random(n); xn = (g % 5 == 0) | (rng.random(n) < 0.1)
+    chunks = Chunk([Column(g), Column(x, xn)]).split(512)
+    plan = AggPlan([INT_NN, DBL], [0], [AggFunc(abi.AGG_FIRSTROW, 0), AggFunc(abi.AGG_SUM, 1, abi.TYPE_DOUBLE), AggFunc(abi.AGG_COUNT, 1, abi.TYPE_DOUBLE)])
+    assert_agg_equal(run_orc_agg(plan, chunks), run_gpu_agg(plan, chunks, required_rows=3), {1})
+
+
 def test_agg_multi_push_same_table():
     # several device batches into one handle (fetchChildData loop, agg_hash_executor.go:449): later batches find the groups
     # of earlier ones; the table grows between batches

@@ -147,6 +147,22 @@ def test_gpu_unique_key_single_pass_probe(build_is_right, uq, monkeypatch):
     assert_rows_equal(run_oracle(plan, l, r), run_gpu(plan, l, r, required_rows=1 << 16))
 
 
+@pytest.mark.parametrize("required_rows", [1, 3, 13])
+def test_next_serves_any_required_rows_with_null_bitmaps(required_rows):
+    # exec.Executor: Next fills at most RequiredRows rows and RequiredRows may be 1 (LIMIT 1, MaxOneRow): a left outer join whose
+    # output carries NULL bitmaps must be drainable one row at a time (the library re-aligns its bit-packed bitmaps on the host)
+    rng = np.random.default_rng(5 + required_rows)
+    ltypes, rtypes, l, r = make_case(rng, 120, 150, 0.2, True, False)
+    plan = JoinPlan(abi.JOIN_LEFT_OUTER, ltypes, rtypes, [1], [0], build_is_right=True, lused=[0, 1, 2], rused=[2, 0])
+    e = HashJoinExec(plan, MockDataSource(plan.left_types, l), MockDataSource(plan.right_types, r))
+    chunks = drain(e, required_rows)
+    assert all(0 < c.num_rows() <= required_rows for c in chunks)
+    rows = []
+    for c in chunks:
+        rows.extend(columns_to_rows([(col_.data, col_.nulls()) for col_ in c.columns]))
+    assert_rows_equal(run_oracle(plan, l, r), rows)
+
+
 def test_gpu_double_keys_and_mixed_sign():
     rng = np.random.default_rng(5)
     ltypes, rtypes, l, r = make_case(rng, 1500, 2000, 0.1, True, False, key_dtype=np.float64)

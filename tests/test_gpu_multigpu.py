@@ -27,7 +27,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("dma", [0, 1, 2])
+@pytest.mark.parametrize("dma", [0, 1, 2, 3])
 def test_mailbox_exchange_two_ranks_vs_oracle(dma):
     lib = abi.load_lib()
     if lib.tg_device_count() < 2:

@@ -134,7 +134,7 @@ EXPORTED_SYMBOLS = [
     "tg_vec_compare_int", "tg_vec_compare_real", "tg_vec_arith_int", "tg_vec_arith_real",
     "tg_vec_filter", "tg_topn",
     "tg_partition_by_key", "tg_partition_of_key", "tg_partition_exchange", "tg_partition_exchange_cf", "tg_partition_exchange_cf_ex", "tg_partition_count",
-    "tg_mail_signal", "tg_mail_wait",
+    "tg_mail_signal", "tg_mail_wait", "tg_peer_copy_regions",
     "tg_ipc_export", "tg_ipc_open", "tg_ipc_close",
 ]
 

@@ -1332,21 +1332,35 @@ int tg_agg_next(tg_agg* h, tg_mut_chunk* out, int64_t max_rows, int64_t* nrows) 
   int64_t lo = a->consumed;
   int64_t want = std::min<int64_t>(std::min<int64_t>(max_rows, out->capacity_rows), a->out_rows - lo);
   if (want <= 0) return TG_OK;
-  if (want < a->out_rows - lo) want -= want % 8;
-  if (want <= 0) return fail(TG_ERR_CAPACITY, "tg_agg_next needs max_rows >= 8");
+  // any RequiredRows >= 1 is served: bitmaps that start inside a byte are fetched whole and shifted on the host
+  const int shift = (int)(lo & 7);
+  std::vector<std::vector<uint8_t>> shifted;
   for (int k = 0; k < a->spec.n; k++) {
     TG_CUDA(cudaMemcpyAsync(out->cols[k].data, a->out_cols[k]->as<uint8_t>() + (size_t)lo * 8, (size_t)want * 8, cudaMemcpyDeviceToHost, a->stream));
     a->stats.d2h_bytes += want * 8;
     size_t nb = (size_t)((want + 7) / 8);
     if (a->out_bitmaps[k]->p) {
       if (!out->cols[k].null_bitmap) return fail(TG_ERR_INVALID, "output column can be NULL but the caller passed no null bitmap");
-      TG_CUDA(cudaMemcpyAsync(out->cols[k].null_bitmap, a->out_bitmaps[k]->as<uint8_t>() + lo / 8, nb, cudaMemcpyDeviceToHost, a->stream));
+      if (shift == 0) TG_CUDA(cudaMemcpyAsync(out->cols[k].null_bitmap, a->out_bitmaps[k]->as<uint8_t>() + lo / 8, nb, cudaMemcpyDeviceToHost, a->stream));
+      else {
+        shifted.emplace_back((size_t)((shift + want + 7) / 8) + 1, (uint8_t)0);
+        TG_CUDA(cudaMemcpyAsync(shifted.back().data(), a->out_bitmaps[k]->as<uint8_t>() + lo / 8, shifted.back().size() - 1, cudaMemcpyDeviceToHost, a->stream));
+      }
     } else if (out->cols[k].null_bitmap) {
       std::memset(out->cols[k].null_bitmap, 0xff, nb);
       if (want & 7) out->cols[k].null_bitmap[nb - 1] = (uint8_t)((1u << (want & 7)) - 1);
     }
   }
   TG_CUDA(cudaStreamSynchronize(a->stream));
+  if (shift) {
+    size_t q = 0;
+    for (int k = 0; k < a->spec.n; k++) {
+      if (!a->out_bitmaps[k]->p) continue;
+      const std::vector<uint8_t>& src = shifted[q++];
+      size_t nb = (size_t)((want + 7) / 8);
+      for (size_t b = 0; b < nb; b++) out->cols[k].null_bitmap[b] = (uint8_t)((src[b] >> shift) | (src[b + 1] << (8 - shift)));
+    }
+  }
   if (want & 7) for (int k = 0; k < a->spec.n; k++) if (a->out_bitmaps[k]->p) out->cols[k].null_bitmap[want >> 3] &= (uint8_t)((1u << (want & 7)) - 1);
   a->consumed += want;
   *nrows = want;

@@ -1241,13 +1241,9 @@ static int join_next_impl(tg_join* h, tg_mut_chunk* out, int64_t max_rows, int64
   ResultBatch& rb = *j->results.front();
   int64_t want = std::min<int64_t>(std::min<int64_t>(max_rows, out->capacity_rows), rb.rows - rb.consumed);
   if (want <= 0) return TG_OK;
-  // bitmaps are bit-packed: serve whole bytes so that the caller's bitmap starts at bit 0
+  // any RequiredRows >= 1 is served (LIMIT 1, MaxOneRow): the result's bit-packed NULL bitmaps are re-aligned on the host
+  // when the read cursor is not on a byte boundary (see below)
   int64_t lo = rb.consumed;
-  bool has_bm = false;
-  for (int c = 0; c < j->n_out; c++) if (rb.bitmaps[c]->p) has_bm = true;
-  if (has_bm && (lo % 8)) return fail(TG_ERR_STATE, "internal: unaligned bitmap cursor");
-  if (has_bm && want < rb.rows - lo) want -= want % 8;   // keep the cursor byte aligned
-  if (want <= 0) return fail(TG_ERR_CAPACITY, "tg_join_next needs max_rows >= 8 when the result carries NULL bitmaps");
   // row bytes of all columns, for the small-request window
   size_t row_bytes = 0;
   for (int c = 0; c < j->n_out; c++) row_bytes += j->out_elem[c];
@@ -1280,11 +1276,17 @@ static int join_next_impl(tg_join* h, tg_mut_chunk* out, int64_t max_rows, int64
       offb += (size_t)wn * el;
     }
   }
+  const int shift = (int)(lo & 7);
+  std::vector<std::vector<uint8_t>> shifted;    // bitmaps that start inside a byte: fetched whole, shifted below
   for (int c = 0; c < j->n_out; c++) {
     size_t nb = (size_t)((want + 7) / 8);
     if (rb.bitmaps[c]->p) {
       if (!out->cols[c].null_bitmap) return fail(TG_ERR_INVALID, "output column can be NULL but the caller passed no null bitmap");
-      TG_CUDA(cudaMemcpyAsync(out->cols[c].null_bitmap, rb.bitmaps[c]->as<uint8_t>() + lo / 8, nb, cudaMemcpyDeviceToHost, cstream));
+      if (shift == 0) TG_CUDA(cudaMemcpyAsync(out->cols[c].null_bitmap, rb.bitmaps[c]->as<uint8_t>() + lo / 8, nb, cudaMemcpyDeviceToHost, cstream));
+      else {
+        shifted.emplace_back((size_t)((shift + want + 7) / 8) + 1, (uint8_t)0);
+        TG_CUDA(cudaMemcpyAsync(shifted.back().data(), rb.bitmaps[c]->as<uint8_t>() + lo / 8, shifted.back().size() - 1, cudaMemcpyDeviceToHost, cstream));
+      }
       j->d2h_bytes += nb;
     } else if (out->cols[c].null_bitmap) {
       std::memset(out->cols[c].null_bitmap, 0xff, nb);
@@ -1292,6 +1294,15 @@ static int join_next_impl(tg_join* h, tg_mut_chunk* out, int64_t max_rows, int64
     }
   }
   TG_CUDA(cudaStreamSynchronize(cstream));
+  if (shift) {
+    size_t q = 0;
+    for (int c = 0; c < j->n_out; c++) {
+      if (!rb.bitmaps[c]->p) continue;
+      const std::vector<uint8_t>& src = shifted[q++];
+      size_t nb = (size_t)((want + 7) / 8);
+      for (size_t b = 0; b < nb; b++) out->cols[c].null_bitmap[b] = (uint8_t)((src[b] >> shift) | (src[b + 1] << (8 - shift)));
+    }
+  }
   // mask the tail bits of copied bitmaps (Column.nullBitmap keeps unused bits zero)
   if (want & 7) for (int c = 0; c < j->n_out; c++) if (rb.bitmaps[c]->p) out->cols[c].null_bitmap[(want >> 3)] &= (uint8_t)((1u << (want & 7)) - 1);
   rb.consumed += want;

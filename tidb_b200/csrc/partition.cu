@@ -155,6 +155,55 @@ int tg_partition_exchange_cf_ex(int device, const int64_t* key_dev, int64_t rows
   return exchange_cf_impl(device, key_dev, rows, nparts, ncols, src_cols_dev, recv_cols_peer, region_base, region_cap, sent_rows_dev, overflow_dev, ctas_per_sm, stream);
 }
 
+// ---- SM-driven region copy over NVLink (the transfer stage of the count-free exchange without copy engines) --------------
+// Copies the FILLED part of up to 64 staged regions to their peers with 128-bit loads / stores: no shared memory and at most
+// 32 registers per thread, 128 threads per CTA — exactly the 4096 registers an SM has left next to three resident CTAs of
+// the persistent probe kernel (3 x 256 x 80), so the copy runs UNDER the probe of the previous step without touching the
+// probe's L1 carve-out.  CTA b starts with region b % n, so the CTAs spread over the peers instead of convoying.
+struct CopyJob {
+  const ulonglong2* src[TG_COPY_MAX_REGIONS];
+  ulonglong2* dst[TG_COPY_MAX_REGIONS];
+  int32_t cnt_idx[TG_COPY_MAX_REGIONS];
+  int32_t n, pad;
+  long long cap_rows;
+  const unsigned long long* counts;
+};
+static __global__ void __launch_bounds__(128, 16) k_peer_copy(CopyJob j) {   // 16 CTAs per SM = at most 32 registers per thread
+  for (int q = 0; q < j.n; q++) {
+    const int r = (q + (int)blockIdx.x) % j.n;
+    unsigned long long rows = j.counts[j.cnt_idx[r]];
+    if (rows > (unsigned long long)j.cap_rows) rows = (unsigned long long)j.cap_rows;
+    const long long n16 = (long long)((rows + 1) >> 1);            // 16-byte units; regions hold an even number of rows
+    const ulonglong2* __restrict__ src = j.src[r];
+    ulonglong2* __restrict__ dst = j.dst[r];
+    for (long long i = (long long)blockIdx.x * 512 + threadIdx.x; i < n16; i += (long long)gridDim.x * 512) {
+      ulonglong2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) if (i + u * 128 < n16) v[u] = __ldcs(src + i + u * 128);
+#pragma unroll
+      for (int u = 0; u < 4; u++) if (i + u * 128 < n16) __stcs(dst + i + u * 128, v[u]);
+    }
+  }
+}
+
+int tg_peer_copy_regions(int device, int32_t n_regions, const void* const* src_dev, void* const* dst_peer, const int32_t* count_index,
+                         const int64_t* counts_dev, int64_t cap_rows, int32_t ctas, void* stream) {
+  if (n_regions < 1 || n_regions > TG_COPY_MAX_REGIONS) return fail(TG_ERR_INVALID, "1..64 regions per call");
+  if (!src_dev || !dst_peer || !count_index || !counts_dev || cap_rows <= 0 || (cap_rows & 1)) return fail(TG_ERR_INVALID, "pointers required; cap_rows must be even");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(TG_ERR_CUDA, "cudaSetDevice failed (no usable CUDA device)");
+  CopyJob j{};
+  j.n = n_regions; j.cap_rows = cap_rows; j.counts = reinterpret_cast<const unsigned long long*>(counts_dev);
+  for (int r = 0; r < n_regions; r++) {
+    if (!ptr_aligned16(src_dev[r]) || !ptr_aligned16(dst_peer[r])) return fail(TG_ERR_UNSUPPORTED, "regions must be 16-byte aligned");
+    j.src[r] = reinterpret_cast<const ulonglong2*>(src_dev[r]); j.dst[r] = reinterpret_cast<ulonglong2*>(dst_peer[r]); j.cnt_idx[r] = count_index[r];
+  }
+  int grid = ctas > 0 ? ctas : device_sm_count(device);
+  k_peer_copy<<<grid, 128, 0, (cudaStream_t)stream>>>(j);
+  TG_CUDA(cudaGetLastError());
+  return TG_OK;
+}
+
 // ---- cross-GPU mailboxes: the exchange's only synchronisation, peer stores + spinning loads, no NCCL, no host ------
 // One 8-byte word per (kind, buffer set, sender): epoch << 40 | value.  A single 64-bit store is atomic, so the word needs
 // no second flag.  The signal kernel runs AFTER the kernel whose peer stores it publishes (stream order: kernel

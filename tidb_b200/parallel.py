@@ -460,7 +460,8 @@ class MailboxExchange:
     SLOTS = 16   # TG_MAIL_MAX_PEERS
 
     def __init__(self, rank: int, world: int, device: int, xstream, ncols: int, rows_per_step: int, slack: float = 1.06,
-                 dma: bool = False, ctas_per_sm: int = 0, timeout_ms: int = 10000, copy_streams: int = 0, direct_peers: int = 0):
+                 dma: bool = False, ctas_per_sm: int = 0, timeout_ms: int = 10000, copy_streams: int = 0, direct_peers: int = 0,
+                 sm_copy: bool = False, sm_copy_ctas: int = 0):
         import torch
         import torch.distributed as dist
         from . import abi
@@ -474,6 +475,10 @@ class MailboxExchange:
         # (~400 GB/s per direction under load at 8 GPUs, profiles/r2_trace_8gpu_cs14.txt): the two paths add up, the copy
         # engines' share shrinks until it hides behind the probe again
         self.direct = set(((rank + i) % world) for i in range(1, min(int(direct_peers), world - 1) + 1)) if self.dma else set()
+        # dma + sm_copy: the staged regions are moved by tg_peer_copy_regions (an SM kernel small enough to sit next to the
+        # persistent probe kernel: 128 threads x 32 registers, no shared memory) instead of the copy engines; it copies the
+        # FILL of every region, read on the device
+        self.sm_copy, self.sm_copy_ctas = bool(sm_copy) and self.dma, int(sm_copy_ctas)
         self.ctas_per_sm = int(ctas_per_sm)
         self.timeout_ms = int(timeout_ms)
         self.cap = region_capacity(rows_per_step, world, slack)
@@ -601,6 +606,25 @@ class MailboxExchange:
             if k >= self.sets:   # the peers have finished probing the step that used the receive set the copies overwrite
                 abi.check(lib.tg_mail_wait(self.device, C.c_void_p(self._mail(self.KIND_ACK, s_)), self.world, C.c_int64(epoch - self.sets), None, err, C.c_int64(self.timeout_ms), C.c_void_p(D.cuda_stream)))
             ready = torch.cuda.Event(); ready.record(D)
+        if self.sm_copy:
+            with torch.cuda.stream(D):
+                srcs, dsts, idx = [], [], []
+                for i in range(1, self.world):
+                    p = (self.rank + i) % self.world
+                    if p in self.direct:
+                        continue
+                    for c in range(len(cols)):
+                        srcs.append(self.staging[s_][c] + p * self.cap * 8); dsts.append(self.peer_recv[s_][p][c] + self.rank * self.cap * 8); idx.append(p)
+                if srcs:
+                    abi.check(lib.tg_peer_copy_regions(self.device, len(srcs), (C.c_void_p * len(srcs))(*srcs), (C.c_void_p * len(dsts))(*dsts),
+                                                       (C.c_int32 * len(idx))(*idx), C.c_void_p(self.sent[s_].data_ptr()), C.c_int64(self.cap),
+                                                       C.c_int32(self.sm_copy_ctas), C.c_void_p(D.cuda_stream)))
+                abi.check(lib.tg_mail_signal(self.device, C.byref(self.targets[(self.KIND_COUNT, s_)]), C.c_void_p(self.sent[s_].data_ptr()), C.c_int64(epoch), C.c_void_p(D.cuda_stream)))
+                done = torch.cuda.Event(); done.record(D)
+                self.staged_free[s_] = done
+                self.last_transfer = done
+            self.launches += 5 if k >= self.sets else 4
+            return
         for cs in self.copy_streams:
             cs.wait_event(ready)
         q = 0
