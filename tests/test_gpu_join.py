@@ -286,10 +286,10 @@ def test_partial_match_and_stats():
                                  dict(TG_PROBE_PARTITION="1", TG_PROBE_PARTS="4", TG_PROBE_SEG_LEAN="1", TG_PROBE_CARVEOUT="0"),
                                  dict(TG_PROBE_PARTITION="1", TG_PROBE_PARTS="5", TG_PROBE_SUBSEG="0"), dict(TG_PROBE_PARTITION="1", TG_PROBE_PARTS="2", TG_PROBE_SUBSEG="1"),
                                  dict(TG_PROBE_PARTITION="1", TG_PROBE_PARTS="9", TG_PROBE_SUBSEG="0", TG_PROBE_SEG_LEAN="0"),
-                                 dict(TG_PROBE_PARTITION="2", TG_PROBE_PARTS="5", TG_PROBE_TMA="1"), dict(TG_PROBE_PARTITION="2", TG_PROBE_PARTS="3", TG_SCATTER_BULK="0"),
-                                 dict(TG_PROBE_TMA="1", TG_PROBE_PARTITION="0"), dict(TG_PROBE_PARTITION="0"), dict(TG_PROBE_VARIANT="0")])
+                                 dict(TG_PROBE_PARTITION="2", TG_PROBE_PARTS="5"), dict(TG_PROBE_PARTITION="2", TG_PROBE_PARTS="3", TG_SCATTER_BULK="0"),
+                                 dict(TG_PROBE_PARTITION="0"), dict(TG_PROBE_VARIANT="0")])
 def test_fused_probe_variants_forced(env, monkeypatch):
-    # every launch variant of the fused fast path (TMA-fed ring, L2 partition pass, warp kernel, CTA-tile kernel) must
+    # every launch variant of the fused fast path (L2 partition pass in both layouts, segment kernels, warp kernel, CTA-tile kernel) must
     # give the same multiset; odd sizes exercise the tail tiles; PART_MIN_MB=0 forces the partition pass on a small table
     for k, v in dict(env, TG_PROBE_PART_MIN_MB="0", TG_PROBE_PART_MIN_ROWS="0").items():
         monkeypatch.setenv(k, v)

@@ -442,9 +442,22 @@ k_agg_finalize(AggTable t, AggSpec spec, int gk_kind, AggOut out, unsigned long 
     if (i < t.nslots) occ = t.nkw ? t.tags[(size_t)i * t.stride] != 0 : t.keys[i] != kEmptyKey;
     else if (i < n_total) occ = t.rows[(size_t)i * t.stride] != 0;
     unsigned b = __ballot_sync(0xffffffffu, occ);
-    unsigned long long wbase = 0;
-    if (lane == 0 && b) wbase = atomicAdd(cursor, (unsigned long long)__popc(b));
-    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    // one cursor atomic per CTA iteration (256 slots), not per warp: a 29 M-slot table (Q3) would otherwise put 0.9 M atomics on
+    // one address
+    __shared__ uint32_t s_wcnt[8];
+    __shared__ unsigned long long s_cbase;
+    const int warp = threadIdx.x >> 5;
+    if (lane == 0) s_wcnt[warp] = __popc(b);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t tot = 0;
+      for (int w = 0; w < 8; w++) tot += s_wcnt[w];
+      s_cbase = tot ? atomicAdd(cursor, (unsigned long long)tot) : 0ull;
+    }
+    __syncthreads();
+    unsigned long long wbase = s_cbase;
+    for (int w = 0; w < warp; w++) wbase += s_wcnt[w];
+    __syncthreads();   // s_wcnt / s_cbase are rewritten by the next iteration
     if (!occ) continue;
     unsigned long long o = wbase + __popc(b & ((1u << lane) - 1));
     unsigned long long rows = t.rows[(size_t)i * t.stride];

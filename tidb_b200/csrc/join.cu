@@ -309,7 +309,7 @@ static int setup(JoinImpl* j, const tg_join_desc* d) {
   j->n_out = (int)j->out_elem.size();
   if (j->n_out > TG_MAX_OUT) return fail(TG_ERR_UNSUPPORTED, "too many output columns");
   j->device = d->device;
-  j->load_factor = (d->load_factor > 0.05 && d->load_factor <= 0.95) ? d->load_factor : 0.4;   // measured best (profiles/r1_sweep_probe.jsonl)
+  j->load_factor = (d->load_factor > 0.05 && d->load_factor <= 0.95) ? d->load_factor : 0.35;   // measured best with the lean segment probe (profiles/r2_sweep_probe_lf_parts.jsonl: 1.93 vs 1.96 ms at 0.4, 2.12 at 0.5)
   return TG_OK;
 }
 
@@ -679,7 +679,7 @@ static ProbeTuning probe_tuning() {
   t.seg_vec = env_int("TG_PROBE_SEG_VEC", 1);            // 128-bit loads/stores in the segment probe
   t.seg_lean = env_int("TG_PROBE_SEG_LEAN", 1);          // 1 = lean full-tile path (default: 1.954 vs 2.089 ms per step, profiles/r2_sweep_probe.jsonl), 0 = round-1 kernel, 2 = + register prefetch (2.01 ms)
   t.carveout = env_int("TG_PROBE_CARVEOUT", -1);         // EXPERIMENTAL: preferred shared-memory carve-out (%) of the segment probe kernels, -1 = driver default
-  t.tma = env_int("TG_PROBE_TMA", 0);               // TMA-fed kernels (cp.async.bulk ring) for the streamed inputs
+  t.tma = 0;                                        // (the TMA-fed probe kernels were removed in round 2)
   t.stages = env_int("TG_PROBE_STAGES", 4);
   t.tma_ctas = env_int("TG_PROBE_TMA_CTAS", 3);
   t.cta_agg = env_int("TG_PROBE_CTA_AGG", 1);        // one output-cursor atomic per CTA tile (TMA kernel)
@@ -768,35 +768,12 @@ struct LaunchSeg {
     return TG_OK;
   }
 };
-template <int NPC, int NKD, int NMD>
-struct LaunchTma {
-  static int run(JoinImpl* j, const int64_t* pkey, int64_t ntiles, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t) {
-    int grid = (int)std::min<int64_t>(ntiles, (int64_t)j->nsm * t.tma_ctas);
-    if (t.stages >= 4) {
-      size_t smem = (size_t)4 * (1 + NPC) * TG_PROBE_TILE * 8 + 4 * 8 + 16;
-      TG_CUDA(cudaFuncSetAttribute(k_probe_inner_u1_tma<NPC, NKD, NMD, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_probe_inner_u1_tma<NPC, NKD, NMD, 4, false><<<grid, 256, smem, j->stream>>>(pkey, ntiles, j->tv, fo, cur);
-    } else if (t.cta_agg) {
-      size_t smem = (size_t)2 * (1 + NPC) * TG_PROBE_TILE * 8 + 2 * 8 + 16;
-      TG_CUDA(cudaFuncSetAttribute(k_probe_inner_u1_tma<NPC, NKD, NMD, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_probe_inner_u1_tma<NPC, NKD, NMD, 2, true><<<grid, 256, smem, j->stream>>>(pkey, ntiles, j->tv, fo, cur);
-    } else {
-      size_t smem = (size_t)2 * (1 + NPC) * TG_PROBE_TILE * 8 + 2 * 8 + 16;
-      TG_CUDA(cudaFuncSetAttribute(k_probe_inner_u1_tma<NPC, NKD, NMD, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_probe_inner_u1_tma<NPC, NKD, NMD, 2, false><<<grid, 256, smem, j->stream>>>(pkey, ntiles, j->tv, fo, cur);
-    }
-    return TG_OK;
-  }
-};
 static int launch_probe_warp(JoinImpl* j, const int64_t* pkey, int64_t n, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t,
                              const SegSpec& seg = SegSpec{nullptr, 0, 0, 0, nullptr}) {
   return dispatch_shape<LaunchWarp>(fo, j, pkey, n, fo, cur, t, seg);
 }
 static int launch_probe_seg(JoinImpl* j, const int64_t* pkey, int64_t n, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t, const SegSpec& seg) {
   return dispatch_shape<LaunchSeg>(fo, j, pkey, n, fo, cur, t, seg);
-}
-static int launch_probe_tma(JoinImpl* j, const int64_t* pkey, int64_t ntiles, const FastOut& fo, unsigned long long* cur, const ProbeTuning& t) {
-  return dispatch_shape<LaunchTma>(fo, j, pkey, ntiles, fo, cur, t);
 }
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -914,11 +891,7 @@ static int probe_device(JoinImpl* j, const DevCols& pview, int64_t n, ResultBatc
             for (int c = 0; c < fo.n_pcols; c++) fo.psrc[c] = j->part_cols[1 + c]->as<unsigned long long>();
           }
         }
-        bool tma_ok = !partitioned && tune.tma && !in_seg && aligned16(pkey);
-        for (int c = 0; c < fo.n_pcols; c++) tma_ok = tma_ok && aligned16(fo.psrc[c]);
-        int64_t full_tiles = tma_ok ? n / TG_PROBE_TILE : 0;
-        if (full_tiles > 0) TG_TRY(launch_probe_tma(j, pkey, full_tiles, fo, cur, tune));
-        int64_t done = partitioned ? n : full_tiles * TG_PROBE_TILE;
+        int64_t done = partitioned ? n : 0;
         if (done < n) {
           FastOut tail = fo;
           for (int c = 0; c < fo.n_pcols; c++) tail.psrc[c] = fo.psrc[c] + done;
@@ -926,7 +899,6 @@ static int probe_device(JoinImpl* j, const DevCols& pview, int64_t n, ResultBatc
           else TG_TRY(launch_probe_warp(j, pkey + done, n - done, tail, cur, tune));
           j->stats.kernel_launches++;
         }
-        if (full_tiles > 0) j->stats.kernel_launches++;
       } else {
         constexpr int R = 4;
         int64_t tiles = (n + 256 * R - 1) / (256 * R);

@@ -752,70 +752,9 @@ k_probe_inner_u1_seg_lean(const int64_t* __restrict__ pkey, int64_t n, TableView
   }
 }
 
-// TMA-fed: the streamed inputs (probe key + payload columns) arrive in shared memory through a STAGES-deep ring of
-// 1024-row tiles filled by cp.async.bulk (one elected thread, mbarrier completion).  Full tiles only; the tail
-// (< 1024 rows) is finished by k_probe_inner_u1_w on the same output cursor.
-#define TG_PROBE_TILE 1024
-template <int NPC, int NKD, int NMD, int STAGES, bool CTA_AGG>
-__global__ void __launch_bounds__(256)
-k_probe_inner_u1_tma(const int64_t* __restrict__ pkey, int64_t ntiles, TableView t, FastOut out,
-                     unsigned long long* __restrict__ out_cursor) {
-  constexpr int T = TG_PROBE_TILE, R = T / 256, COLS = 1 + NPC;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned long long* ring = reinterpret_cast<unsigned long long*>(smem_raw);          // [STAGES][COLS][T]
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * COLS * T * 8);
-  const int tid = threadIdx.x, lane = tid & 31;
-  const unsigned long long pol_stream = l2_policy_evict_first();
-  if (tid == 0) {
-    for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  auto issue = [&](int64_t it) {
-    int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
-    if (tile >= ntiles) return;
-    int s = (int)(it % STAGES);
-    unsigned long long* st = ring + (size_t)s * COLS * T;
-    mbar_arrive_expect_tx(&full[s], (uint32_t)(COLS * T * 8));
-    bulk_g2s(st, pkey + tile * T, T * 8, &full[s], pol_stream);
-#pragma unroll
-    for (int c = 0; c < NPC; c++) bulk_g2s(st + (size_t)(1 + c) * T, out.psrc[c] + tile * T, T * 8, &full[s], pol_stream);
-  };
-  if (tid == 0) for (int it = 0; it < STAGES; it++) issue(it);
-  for (int64_t it = 0;; it++) {
-    const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
-    if (tile >= ntiles) break;
-    const int s = (int)(it % STAGES);
-    mbar_wait(&full[s], (uint32_t)((it / STAGES) & 1));
-    const unsigned long long* st = ring + (size_t)s * COLS * T;
-    int64_t k[R];
-    unsigned long long pv[R][NPC > 0 ? NPC : 1];
-    unsigned long long sl[R];
-    bool in[R];
-    unsigned long long dep = 0;
-#pragma unroll
-    for (int j = 0; j < R; j++) {
-      in[j] = true;
-      k[j] = (int64_t)st[j * 256 + tid];
-#pragma unroll
-      for (int c = 0; c < NPC; c++) pv[j][c] = st[(size_t)(1 + c) * T + j * 256 + tid];
-    }
-    // The shared-memory loads above must have RETURNED before the CTA barrier: BAR.SYNC does not wait for outstanding
-    // LDS, and on a busy LSU (other warps' uncoalesced gathers queue for microseconds) the refill issued right after
-    // the barrier can land first.  Consuming every loaded value (hash of the keys, XOR of the payloads) before the
-    // barrier makes the scoreboard wait for them.
-#pragma unroll
-    for (int j = 0; j < R; j++) {
-      sl[j] = (k[j] == kEmptyKey) ? t.nslots : home_slot(hash64((uint64_t)k[j]), t.nslots, t.pair_home);
-#pragma unroll
-      for (int c = 0; c < NPC; c++) dep ^= pv[j][c];
-    }
-    if (NPC > 0 && dep == 0x9E3779B97F4A7C15ull && sl[0] == ~0ull) out_cursor[1] = dep;   // never true; keeps `dep` alive
-    __syncthreads();                 // the whole CTA has drained stage s into registers
-    if (tid == 0) issue(it + STAGES);
-    probe_rows_u1<R, NPC, NKD, NMD, CTA_AGG>(k, pv, sl, in, t, out, out_cursor, lane);
-  }
-}
+// (The TMA-fed variant of this kernel — keys/payloads through a cp.async.bulk ring — was removed in round 2: measured no
+// faster in round 1 (the segment probe is bound by L1 gather issue, and every KB of shared memory it holds costs L1), it
+// added 96 instantiations to the library.  tools/scratch/probe_lab.cu keeps the experiment; profiles/r1_probe_lab.md the numbers.)
 
 // OtherCondition on ONE candidate pair (probe row i, build row `brow` of the row store): true iff every CNF item is
 // non-NULL true (expression.VectorizedFilter over the joined chunk, inner_join_probe.go:72-79)

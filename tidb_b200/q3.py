@@ -118,6 +118,9 @@ def run(d: Q3Data, dev, stream, topn: int = 10, timings: Dict[str, float] = None
     agg.push([lk, price, disc, jd, jp])
     ng, ca, na = agg.finish()
     mark("HashAgg (3 GROUP BY columns, projection fused)")
+    if timings is not None:
+        ast_ = agg.stats()
+        timings["agg_kernels_ms"] = {"update": round(ast_.update_ms, 3), "finalize": round(ast_.finalize_ms, 3), "table_slots": int(ast_.table_slots), "launches": int(ast_.kernel_launches)}
     out = {"groups": ng}
     if keep_groups:   # copies of the whole aggregate result (verification); the query's own result is the TopN below
         out.update({"orderkey": _view(ca[0], ng, dev).clone(), "revenue": _view(ca[1], ng, dev, "<f8").clone(),

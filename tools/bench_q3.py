@@ -65,6 +65,6 @@ with torch.cuda.stream(stream):
 stream.synchronize()
 ms = e0.elapsed_time(e1) / a.steps
 rec = dict(op="Q3-shape", sf=a.sf, n_gpus=1, rows=dict(customer=nc, orders=no, lineitem=nl), groups=int(got["orderkey"].numel()), ms=ms,
-           phases_ms={k: round(v, 3) for k, v in t.items() if k != "rows"}, operator_rows=t.get("rows"),
+           phases_ms={k: (round(v, 3) if not isinstance(v, dict) else v) for k, v in t.items() if k != "rows"}, operator_rows=t.get("rows"),
            scanned_gb=d.scanned_bytes() / 1e9, gbs=d.scanned_bytes() / ms / 1e6, frac=d.scanned_bytes() / ms / 1e6 / peak, verified=bool(a.verify))
 print(json.dumps(rec)); os.makedirs(os.path.dirname(a.out), exist_ok=True); open(a.out, "a").write(json.dumps(rec) + "\n")
