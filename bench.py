@@ -15,11 +15,11 @@ N > 1 (weak scaling, per-GPU work fixed) = BASELINE.json configs[4] divided by 8
 125M probe rows (N = 8: the 1B x 100M join) whose keys are uniform over the GLOBAL key set, so a key-hash
 repartition is mandatory: build side repartitioned once (untimed, like the build itself), every timed step =
 regroup the probe columns by destination GPU + move them over NVLink + shard-local probe (L2 partition pass +
-segment probe).  Default (--exchange mail): tidb_b200/parallel.py:MailboxExchange — ONE kernel regroups 1024-row
-tiles and appends them to this rank's region on every peer with bulk stores over NVLink; the only synchronisation
-is device-side mailboxes (peer stores + spinning loads): no NCCL collective, no copy-engine call and no host wait
-inside a step.  The exchange stream runs one step ahead of the probe stream (two receive sets), the way a stream
-of probe batches is processed.  The timed region holds exactly K exchanges and K probes (the pipeline is empty at
+segment probe).  tidb_b200/parallel.py:MailboxExchange: a kernel regroups 1024-row tiles by destination with bulk stores (into a
+local staging copy of the region layout, or straight into a peer), copy engines move the staged regions over NVLink
+under the probe of the previous step, and the only synchronisation is device-side mailboxes (peer stores + spinning
+loads): no NCCL collective and no host wait inside a step.  All SM kernels of a rank run on ONE stream in the order
+regroup(k+1), probe(k) (two receive sets), the way a stream of probe batches is processed.  The timed region holds exactly K exchanges and K probes (the pipeline is empty at
 both events: barrier + synchronize before, the last probe's completion after).  --exchange auto times the
 candidate transports for a few untimed steps and keeps the fastest (reported in config).
 
@@ -314,7 +314,7 @@ def run_gpu(args):
     mail_timings = {}
     MAIL_CANDIDATES = {"mail": dict(dma=False, ctas_per_sm=args.scatter_ctas), "mail-dma": dict(dma=True, ctas_per_sm=args.scatter_ctas, copy_streams=args.copy_streams, direct_peers=args.direct_peers),
                        "mail-smcopy": dict(dma=True, ctas_per_sm=args.scatter_ctas, sm_copy=True, sm_copy_ctas=args.sm_copy_ctas),
-                       "mail-hybrid": dict(dma=True, ctas_per_sm=args.scatter_ctas, copy_streams=args.copy_streams, direct_peers=max(1, (world - 1) // 3))}
+                       "mail-hybrid": dict(dma=True, ctas_per_sm=args.scatter_ctas, copy_streams=args.copy_streams, direct_peers=1)}   # measured at 8 GPUs: 1 direct peer 4.07 ms, 2: 4.21, 3: 4.42, 0 (copy engines only): 4.69
 
     def mail_step(xm, sync: bool):
         """ALL SM kernels of a rank on ONE stream, in the order regroup(k+1), probe(k): the shared-memory-heavy scatter never
@@ -809,21 +809,140 @@ def run_e2e_mail(args, torch, dist, dev, stream, xstream, rank, world, pk, pv, x
             "timing": "host wall clock, max over ranks, device synchronised on both sides"}
 
 
+# ---------------------------------------------------------------------------------------------------------
+# --workload agg: BASELINE configs[2], HashAgg SUM/COUNT GROUP BY int64, 100M rows / 1M groups, 1 GPU
+# ---------------------------------------------------------------------------------------------------------
+def run_agg(args):
+    """Same JSON contract as the join line, metric = aggregated input rows/sec.  A step = one whole aggregation (table
+    init + update + finalize) of the 100M-row batch.  roofline: 16.24 algorithmic bytes per row over the HBM peak,
+    plus the measured L2-operation floor of this access pattern (profiles/r2_agg_lab.md) as `l2_op_floor_ms`."""
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+    import torch
+    from tidb_b200 import abi
+    from tidb_b200.chunk import Chunk, Column
+    from tidb_b200.device import DeviceAgg
+    from tidb_b200.plan import AggFunc, AggPlan, FieldType
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    n, G = args.agg_rows, args.agg_groups
+    hbm_peak, peak_src = peaks()
+    stream = torch.cuda.Stream(device=dev)
+    INT = FieldType(abi.TYPE_LONGLONG, abi.FLAG_NOT_NULL); DBL = FieldType(abi.TYPE_DOUBLE, abi.FLAG_NOT_NULL)
+    with torch.cuda.stream(stream):
+        g = torch.Generator(device=dev); g.manual_seed(44)
+        keys = torch.randint(0, G, (n,), device=dev, generator=g, dtype=torch.int64)
+        x = torch.floor(torch.rand(n, device=dev, generator=g, dtype=torch.float64) * 1e7)
+    stream.synchronize()
+    funcs = [AggFunc(abi.AGG_FIRSTROW, 0), AggFunc(abi.AGG_SUM, 1, abi.TYPE_DOUBLE), AggFunc(abi.AGG_COUNT, 1, abi.TYPE_DOUBLE)]
+    plan = AggPlan([INT, DBL], [0], funcs, stream=stream.cuda_stream, expected_groups=G)
+
+    def view(p, m, dt):
+        class _A:
+            pass
+        o = _A(); o.__cuda_array_interface__ = {"shape": (m,), "typestr": dt, "data": (p, False), "version": 3}
+        return torch.as_tensor(o, device=dev)
+
+    def one(verify=False):
+        agg = DeviceAgg(plan)
+        with torch.cuda.stream(stream):
+            agg.push([keys, x])
+            rows, cols, _ = agg.finish()
+            if verify:   # COUNT bit-exact, SUM within 1e-6 relative against plain reductions of the same columns
+                gk, s_, c_ = view(cols[0], rows, "<i8"), view(cols[1], rows, "<f8"), view(cols[2], rows, "<i8")
+                assert rows == G and torch.equal(torch.sort(gk).values, torch.arange(G, device=dev))
+                assert torch.equal(c_, torch.bincount(keys, minlength=G)[gk])
+                exp = torch.zeros(G, dtype=torch.float64, device=dev).scatter_add_(0, keys, x)
+                assert torch.allclose(s_, exp[gk], rtol=1e-6, atol=0)
+        st = agg.stats()
+        agg.close()
+        return st
+    for _ in range(max(3, args.warmup) - 1):
+        one()
+    one(verify=True)
+    sampler = ClockSampler(0); sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+    for _ in range(args.steps):
+        launches += one().kernel_launches
+    with torch.cuda.stream(stream):
+        e1.record(stream)
+    stream.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    # e2e: host chunks through tg_agg_push / tg_agg_next (pinned host memory in, host result out)
+    e2e = None
+    if not args.skip_e2e:
+        from tidb_b200.executor import HashAggExec, MockDataSource, drain
+        hk = torch.empty(n, dtype=torch.int64, pin_memory=True); hk.copy_(keys)
+        hx = torch.empty(n, dtype=torch.float64, pin_memory=True); hx.copy_(x)
+        chunks = Chunk([Column(hk.numpy()), Column(hx.numpy())]).split(args.e2e_chunk_rows)
+        hplan = AggPlan([INT, DBL], [0], funcs, expected_groups=G)
+        drain(HashAggExec(hplan, MockDataSource(hplan.col_types, chunks)), 1 << 20)
+        t0 = time.perf_counter(); reps = max(1, args.steps // 3)
+        for _ in range(reps):
+            out = drain(HashAggExec(hplan, MockDataSource(hplan.col_types, chunks)), 1 << 20)
+        dt = (time.perf_counter() - t0) / reps
+        assert sum(c.num_rows() for c in out) == G
+        e2e = {"value": n / dt, "unit": "rows/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 24 * G, "ms_per_step": dt * 1e3,
+               "path": "pinned host columns in 4M-row chunks -> tg_agg_push (H2D + update) -> tg_agg_finish -> tg_agg_next (D2H of the 3 result columns)"}
+    # CPU baseline: the oracle's HashAgg restatement on a bounded sample, at the reference's default concurrency (5) and on all threads
+    cpu = None
+    if not args.skip_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+        sample = min(n, args.cpu_sample_rows)
+        hk_s, hx_s = keys[:sample].cpu().numpy(), x[:sample].cpu().numpy()
+        ch = Chunk([Column(hk_s), Column(hx_s)]).split(1024)
+        threads = host_threads()
+        res = {}
+        for conc in sorted({5, threads}):
+            oa = O.OracleAgg(AggPlan([INT, DBL], [0], funcs), conc, conc)
+            t0 = time.perf_counter(); oa.run(ch); dt = time.perf_counter() - t0
+            oa.close()
+            res[conc] = sample / dt
+        cpu = {"value": res[threads], "unit": "rows/s", "cores": threads, "kind": "port",
+               "sample": f"first {sample} rows as 1024-row chunks (groups seen: up to {G}); oracle/agg.cpp restates TiDB's HashAggExec partial/final workers (not the Go binary)",
+               "value_at_reference_default_concurrency_5": res.get(5)}
+    alg = 16 * n + 24 * G
+    line = {"metric": "hash-agg input rows/sec", "value": n / (ms * 1e-3), "unit": "rows/s", "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"HashAggExec SUM/COUNT GROUP BY int64, {n} rows / {G} groups, 1 GPU (BASELINE configs[2])",
+                       "l2": "inputs (1.6 GB) larger than L2; the group table (48 MB) is L2 resident by design"},
+            "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
+            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "k_agg_init + k_agg_update2<false> + k_agg_count + k_agg_finalize (one step)",
+                         "algorithmic_bytes_per_launch": alg,
+                         "l2_op_floor_ms": 1.572 * n / 1e8, "frac_of_l2_op_floor": (1.572 * n / 1e8) / ms,
+                         "note": "the table lives in L2: one key gather + two 64-bit REDs per row cost 1.572 ms per 100 M rows on this chip (tools/scratch/agg_lab.cu, profiles/r2_agg_lab.md)"}}
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="join", choices=["join", "agg"], help="join = the headline (BASELINE configs[1] / configs[4]); agg = BASELINE configs[2] on one GPU")
+    ap.add_argument("--agg-rows", type=int, default=100_000_000)
+    ap.add_argument("--agg-groups", type=int, default=1_000_000)
     ap.add_argument("--build-rows", type=int, default=None, help="per GPU; default 10M at N=1 (configs[1]), 12.5M at N>1 (configs[4] / 8)")
     ap.add_argument("--probe-rows", type=int, default=None, help="per GPU; default 100M at N=1, 125M at N>1")
     ap.add_argument("--cpu-sample-rows", type=int, default=8_000_000)
     ap.add_argument("--ref-sample-rows", type=int, default=8_000_000)
     ap.add_argument("--e2e-chunk-rows", type=int, default=4 << 20)
-    ap.add_argument("--exchange", default="mail", choices=["mail", "mail-dma", "mail-hybrid", "mail-smcopy", "auto", "cf", "p2p", "nccl"],
-                    help="N>1 probe-side exchange: mail = count-free peer bulk stores + device mailboxes (no NCCL / host in a step); mail-dma = same, copy engines "
-                         "move the regions; auto = time mail / mail (2 scatter CTAs per SM) / mail-dma untimed and keep the fastest; cf = round-1 count-free exchange "
-                         "(NCCL all-gather per step); p2p = counted peer stores; nccl = local scatter + all_to_all")
+    ap.add_argument("--exchange", default="auto", choices=["mail", "mail-dma", "mail-hybrid", "mail-smcopy", "auto", "cf", "p2p", "nccl"],
+                    help="N>1 probe-side exchange, all count-free with device mailboxes (no NCCL / host wait in a step): mail = the regroup kernel stores into the peers "
+                         "itself; mail-dma = copy engines move the staged regions; mail-hybrid = copy engines + one direct peer; mail-smcopy = an SM copy kernel next to "
+                         "the probe; auto (default) = time mail-dma / mail-hybrid / mail for a few untimed steps and keep the fastest.  cf = round-1 exchange (NCCL "
+                         "all-gather per step); p2p = counted peer stores; nccl = local scatter + all_to_all")
     ap.add_argument("--slack", type=float, default=1.03, help="N>1, mailbox exchange: receive-region capacity = expected share x slack + 8192 rows (uniform keys: 3 %% is > 100 sigma)")
     ap.add_argument("--sm-copy-ctas", type=int, default=0, help="N>1, mail-smcopy: 128-thread CTAs of the region copy kernel (0 = one per SM)")
     ap.add_argument("--direct-peers", type=int, default=0, help="N>1, mail-dma: peers (ring order) whose rows the regroup kernel stores directly over NVLink; the rest go through the copy engines (mail-hybrid = (N-1)//3)")
@@ -841,6 +960,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "agg":
+        run_agg(args)
     else:
         run_gpu(args)
 
