@@ -479,14 +479,14 @@ def run_gpu(args):
     traffic = args.ncu_traffic_bytes
     if traffic is None:
         try:   # per-launch DRAM bytes of the committed ncu --set full capture of this kernel
-            traffic = float(json.load(open(os.path.join(ROOT, "profiles", "r1_pipeline_traffic.json" if os.environ.get("TG_PROBE_PARTITION", "1") == "1" else "r1_probe_final_traffic.json")))["dram_bytes_per_launch"])
+            traffic = float(json.load(open(os.path.join(ROOT, "profiles", "r2_pipeline_traffic.json" if os.environ.get("TG_PROBE_PARTITION", "1") == "1" else "r1_probe_final_traffic.json")))["dram_bytes_per_launch"])
         except Exception:
             traffic = None
     if world == 1:
         achieved = BYTES_PER_PROBE_ROW * npb / (ms_step * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "kernel": ("k_partition_scatter_bulk<1,2,4> + k_probe_inner_u1_seg<1,2,1> (L2 partition pass + segment probe: one step; frac is over the WHOLE step)"
+                "kernel": ("k_partition_scatter_bulk<1,2,4> + k_probe_inner_u1_seg_lean<1,2,1,0> (L2 partition pass + segment probe: one step; frac is over the WHOLE step)"
                            if os.environ.get("TG_PROBE_PARTITION", "1") == "1" else "k_probe_inner_u1_w<4,1,2,1>"),
                 "algorithmic_bytes_per_launch": BYTES_PER_PROBE_ROW * npb,
                 "read_only_frac": 32 * npb / (ms_step * 1e-3) / 1e9 / hbm_peak}
