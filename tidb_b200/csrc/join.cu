@@ -98,6 +98,7 @@ struct JoinImpl {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int nsm = 148;
   double load_factor = 0.5;
+  bool default_load_factor = true;
 
   int join_type = 0;
   bool build_is_right = true;
@@ -309,6 +310,7 @@ static int setup(JoinImpl* j, const tg_join_desc* d) {
   j->n_out = (int)j->out_elem.size();
   if (j->n_out > TG_MAX_OUT) return fail(TG_ERR_UNSUPPORTED, "too many output columns");
   j->device = d->device;
+  j->default_load_factor = !(d->load_factor > 0.05 && d->load_factor <= 0.95);
   j->load_factor = (d->load_factor > 0.05 && d->load_factor <= 0.95) ? d->load_factor : 0.35;   // measured best with the lean segment probe (profiles/r2_sweep_probe_lf_parts.jsonl: 1.93 vs 1.96 ms at 0.4, 2.12 at 0.5)
   return TG_OK;
 }
@@ -454,6 +456,14 @@ static int build_table(JoinImpl* j) {
   KeySpec ks = j->build_key;
   ks.data = bview.data[b.key_col]; ks.nulls = bview.nulls[b.key_col];
   unsigned long long nslots = (unsigned long long)((double)(n > 0 ? n : 1) / j->load_factor) + 32;
+  // the L2 partition pass handles at most TG_MAX_PARTS slices and wants them <= ~33 MB (45 MB slices: 2.10 vs 1.93 ms,
+  // profiles/r2_sweep_probe_lf_parts.jsonl): with the DEFAULT load factor a table that would need more slices is made denser,
+  // down to load factor 0.5, instead of growing its slices
+  if (j->default_load_factor) {
+    const unsigned long long fit = ((unsigned long long)TG_MAX_PARTS * (33ull << 20)) / sizeof(Slot);
+    const unsigned long long dense = (unsigned long long)((double)(n > 0 ? n : 1) / 0.5) + 32;
+    if (nslots > fit) nslots = std::max(fit, dense);
+  }
   nslots &= ~1ull;   // even: slots are addressed as 32-byte pairs
   const int pair_home = env_int("TG_PAIR_HOME", 1);
   if (nslots + 1 >= 0xFFFFFFFFull) return fail(TG_ERR_UNSUPPORTED, "build side too large for 32-bit slot ids");

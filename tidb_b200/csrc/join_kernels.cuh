@@ -972,22 +972,32 @@ __global__ void __launch_bounds__(256)
 k_probe_inner_uq(KeySpec key, DevCols pcols, DevFilter filt, int64_t n, TableView t, OutCols out, unsigned long long* __restrict__ out_cursor) {
   // ONE output-cursor atomic per 1024-row CTA tile: a per-warp reservation (600 M rows -> 19 M atomics on one address) was
   // measured to serialise in L2 at ~2 ns each (Q3 J2 probe 38.8 ms); per tile it is 0.6 M
-  __shared__ uint32_t s_cnt[UQ_R][8];
-  __shared__ unsigned long long s_base;
+  __shared__ uint32_t s_cnt[2][UQ_R][8];          // double-buffered by tile parity: two CTA barriers per tile, not three
+  __shared__ unsigned long long s_base[2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t tile = 256 * UQ_R;
-  for (int64_t base = (int64_t)blockIdx.x * tile; base < n; base += (int64_t)gridDim.x * tile) {
+  int par = 0;
+  for (int64_t base = (int64_t)blockIdx.x * tile; base < n; base += (int64_t)gridDim.x * tile, par ^= 1) {
     int64_t k[UQ_R];
     unsigned long long sl[UQ_R];
     Slot v[UQ_R];
     bool valid[UQ_R];
+    // the key loads do not depend on the filter: issue them first so that key and filter columns stream in together
+    // (ncu, profiles/r2_q3_kernels.md: the kernel was bound by three dependent DRAM round trips per tile)
 #pragma unroll
     for (int r = 0; r < UQ_R; r++) {
       const int64_t i = base + (int64_t)r * 256 + threadIdx.x;
       valid[r] = i < n;
-      k[r] = 0;
+      k[r] = (valid[r] && key.kind == KEY_I64) ? __ldcs(reinterpret_cast<const int64_t*>(key.data) + i) : 0;
+    }
+#pragma unroll
+    for (int r = 0; r < UQ_R; r++) {
+      const int64_t i = base + (int64_t)r * 256 + threadIdx.x;
       if (valid[r] && filt.n) valid[r] = eval_filter(filt, pcols, i);
-      if (valid[r]) valid[r] = load_key(key, i, k[r]);
+      if (valid[r]) {
+        if (key.kind == KEY_I64) valid[r] = !(key.nulls && !bit_not_null(key.nulls, i)) && !(key.reject_negative && k[r] < 0);
+        else valid[r] = load_key(key, i, k[r]);
+      }
     }
 #pragma unroll
     for (int r = 0; r < UQ_R; r++) {
@@ -1009,21 +1019,21 @@ k_probe_inner_uq(KeySpec key, DevCols pcols, DevFilter filt, int64_t n, TableVie
         }
       }
       bal[r] = __ballot_sync(0xffffffffu, m);
-      if (lane == 0) s_cnt[r][warp] = __popc(bal[r]);
+      if (lane == 0) s_cnt[par][r][warp] = __popc(bal[r]);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
       uint32_t tot = 0;
 #pragma unroll
-      for (int r = 0; r < UQ_R; r++) for (int w = 0; w < 8; w++) tot += s_cnt[r][w];
-      s_base = tot ? atomicAdd(out_cursor, (unsigned long long)tot) : 0ull;
+      for (int r = 0; r < UQ_R; r++) for (int w = 0; w < 8; w++) tot += s_cnt[par][r][w];
+      s_base[par] = tot ? atomicAdd(out_cursor, (unsigned long long)tot) : 0ull;
     }
     __syncthreads();
-    unsigned long long run = s_base;
+    unsigned long long run = s_base[par];
 #pragma unroll
     for (int r = 0; r < UQ_R; r++) {
       unsigned long long wb = run;
-      for (int w = 0; w < 8; w++) { if (w < warp) wb += s_cnt[r][w]; run += s_cnt[r][w]; }
+      for (int w = 0; w < 8; w++) { if (w < warp) wb += s_cnt[par][r][w]; run += s_cnt[par][r][w]; }
       if (!((bal[r] >> lane) & 1u)) continue;
       const int64_t i = base + (int64_t)r * 256 + threadIdx.x;
       const unsigned long long o = wb + __popc(bal[r] & ((1u << lane) - 1));
@@ -1040,7 +1050,7 @@ k_probe_inner_uq(KeySpec key, DevCols pcols, DevFilter filt, int64_t n, TableVie
         reinterpret_cast<unsigned long long*>(out.data[c])[o] = val;
       }
     }
-    __syncthreads();   // s_cnt / s_base are reused by the next tile
+    // no third barrier: the next tile writes the OTHER parity of s_cnt / s_base, and the tile after that is two barriers away
   }
 }
 
