@@ -84,3 +84,28 @@ def test_partition_function_is_stable(lib):
     assert set(cnt) == set(range(8))
     assert max(cnt.values()) < 1.1 * 10000 and min(cnt.values()) > 0.9 * 10000
     assert lib.tg_partition_of_key(12345, 1) == 0
+
+
+def test_round2_gates_without_gpu(lib):
+    # the planner gates answer on a host without a device: multi-column GROUP BY (up to 4), fused aggregate argument
+    # expressions (SUM / AVG over two DOUBLE columns, Complete mode), OtherCondition shapes
+    from tidb_b200.plan import OtherCond
+    DBL_NN = FieldType(abi.TYPE_DOUBLE, abi.FLAG_NOT_NULL)
+    def agg_rc(plan):
+        d, keep = plan.to_struct()
+        return lib.tg_agg_supported(C.byref(d))
+    cols = [INT_NN] * 5 + [DBL_NN, DBL_NN]
+    assert agg_rc(AggPlan(cols, [0, 1, 2, 3], [AggFunc(abi.AGG_FIRSTROW, 2), AggFunc(abi.AGG_COUNT, -1)])) == abi.TG_OK
+    assert agg_rc(AggPlan(cols, [0, 1, 2, 3, 4], [AggFunc(abi.AGG_COUNT, -1)])) == abi.TG_ERR_UNSUPPORTED
+    assert agg_rc(AggPlan(cols, [0], [AggFunc(abi.AGG_FIRSTROW, 1)])) == abi.TG_ERR_UNSUPPORTED           # FIRSTROW of a non-group column
+    ok = AggFunc(abi.AGG_SUM, 5, abi.TYPE_DOUBLE, arg_col2=6, arg_expr=abi.ARGEXPR_MUL_CSUB, arg_const=1.0)
+    assert agg_rc(AggPlan(cols, [0], [ok])) == abi.TG_OK
+    assert agg_rc(AggPlan(cols, [0], [AggFunc(abi.AGG_MAX, 5, abi.TYPE_DOUBLE, arg_col2=6, arg_expr=abi.ARGEXPR_MUL)])) == abi.TG_ERR_UNSUPPORTED
+    assert agg_rc(AggPlan(cols, [0], [AggFunc(abi.AGG_SUM, 5, abi.TYPE_DOUBLE, arg_col2=1, arg_expr=abi.ARGEXPR_MUL)])) == abi.TG_ERR_UNSUPPORTED   # int operand
+    def join_rc(plan):
+        d, keep = plan.to_struct()
+        return lib.tg_join_supported(C.byref(d))
+    oc = [OtherCond(abi.CMP_LT, 0, 1, 1, 1)]
+    assert join_rc(JoinPlan(abi.JOIN_INNER, [INT_NN, INT_NN], [INT_NN, INT_NN], [0], [0], other_cond=oc)) == abi.TG_OK
+    assert join_rc(JoinPlan(abi.JOIN_LEFT_OUTER, [INT_NN, INT_NN], [INT_NN, INT_NN], [0], [0], build_is_right=False, other_cond=oc)) == abi.TG_ERR_UNSUPPORTED
+    assert join_rc(JoinPlan(abi.JOIN_INNER, [INT_NN, INT_NN], [INT_NN, INT_NN], [0], [0], other_cond=[OtherCond(abi.CMP_LT, 0, 5, 1, 1)])) == abi.TG_ERR_INVALID
