@@ -203,7 +203,11 @@ typedef struct tg_join_desc {
   const int32_t* left_types;  const uint32_t* left_flags;
   const int32_t* right_types; const uint32_t* right_flags;
   /* equal-condition keys: column index per side (BuildKeyColIdx / ProbeKeyColIdx after
-   * mapping to left/right, builder.go:1780-1830)                                                */
+   * mapping to left/right, builder.go:1780-1830).  nkeys = 1: int family / float / double key (OneInt64 mode and the
+   * 8-byte fixed keys).  nkeys = 2..4: FixedSerializedKey mode (join_table_meta.go:174-178) for 8-byte integer-family
+   * columns — a row with a NULL in any key column has no key; a pair matches iff every key column is equal by value
+   * (signed vs unsigned compared by value).  Join shapes that need a build-side scan or the NULL-aware match flag are
+   * declined with several keys (TG_ERR_UNSUPPORTED → the planner keeps the CPU executor), like with OtherCondition.  */
   int32_t nkeys;
   int32_t reserved0;
   const int32_t* left_key_idx;

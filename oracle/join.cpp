@@ -379,8 +379,22 @@ static bool serialize_keys(const tg_chunk& chk, const std::vector<FieldType>& tp
           out.buf.insert(out.buf.end(), r, r + 8);
           break;
         }
+        case TypeDate: case TypeDatetime: case TypeTimestamp: {
+          // codec.go:697-707: Time.ToPackedUint (types/time.go:646-657) of the CoreTime bit fields (types/time.go:235-241)
+          const uint64_t v = (uint64_t)col_i64(col, p);
+          const uint64_t year = (v >> 50) & 0x3fff, month = (v >> 46) & 0xf, day = (v >> 41) & 0x1f, hour = (v >> 36) & 0x1f,
+                         minute = (v >> 30) & 0x3f, second = (v >> 24) & 0x3f, micro = (v >> 4) & 0xfffff;
+          uint64_t packed = 0;
+          if (year | month | day | hour | minute | second | micro) {   // IsZero → 0
+            const uint64_t ymd = ((year * 13 + month) << 5) | day, hms = (hour << 12) | (minute << 6) | second;
+            packed = (((ymd << 17) | hms) << 24) | micro;
+          }
+          const uint8_t* r = reinterpret_cast<const uint8_t*>(&packed);
+          out.buf.insert(out.buf.end(), r, r + 8);
+          break;
+        }
         default:
-          set_error("oracle: join key type not restated (var-len / time / decimal keys are out of scope)");
+          set_error("oracle: join key type not restated (var-len / decimal keys are out of scope)");
           return false;
       }
     }

@@ -59,6 +59,11 @@ def _key(row: Row, idx: Sequence[int], types, float_norm=True):
             return None
         if isinstance(v, float) and v == 0:
             v = 0.0
+        if types[i].tp in (abi.TYPE_DATE, abi.TYPE_DATETIME, abi.TYPE_TIMESTAMP):
+            # date-time keys compare by their calendar fields (codec.go:697-707 serializes Time.ToPackedUint); the low 4 bits
+            # of the CoreTime word are type / fsp (types/time.go:243-251)
+            w = int(v) & ((1 << 64) - 1)
+            v = ("time", w >> 50, (w >> 46) & 0xf, (w >> 41) & 0x1f, (w >> 36) & 0x1f, (w >> 30) & 0x3f, (w >> 24) & 0x3f, (w >> 4) & 0xfffff)
         k.append(v)
     return tuple(k)
 

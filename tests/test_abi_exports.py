@@ -43,9 +43,9 @@ def test_join_supported_gate(lib):
     ok = JoinPlan(abi.JOIN_INNER, [INT_NN, INT_NN], [INT_NN, INT_NN], [0], [0])
     d, keep = ok.to_struct()
     assert lib.tg_join_supported(C.byref(d)) == abi.TG_OK
-    multi = JoinPlan(abi.JOIN_INNER, [INT_NN, INT_NN], [INT_NN, INT_NN], [0, 1], [0, 1])
+    multi = JoinPlan(abi.JOIN_INNER, [INT_NN, INT_NN], [INT_NN, INT_NN], [0, 1], [0, 1])   # round 2: FixedSerializedKey mode
     d, keep = multi.to_struct()
-    assert lib.tg_join_supported(C.byref(d)) == abi.TG_ERR_UNSUPPORTED
+    assert lib.tg_join_supported(C.byref(d)) == abi.TG_OK
     strkey = JoinPlan(abi.JOIN_INNER, [FieldType(abi.TYPE_VARSTRING)], [FieldType(abi.TYPE_VARSTRING)], [0], [0])
     d, keep = strkey.to_struct()
     assert lib.tg_join_supported(C.byref(d)) == abi.TG_ERR_UNSUPPORTED
@@ -109,3 +109,42 @@ def test_round2_gates_without_gpu(lib):
     assert join_rc(JoinPlan(abi.JOIN_INNER, [INT_NN, INT_NN], [INT_NN, INT_NN], [0], [0], other_cond=oc)) == abi.TG_OK
     assert join_rc(JoinPlan(abi.JOIN_LEFT_OUTER, [INT_NN, INT_NN], [INT_NN, INT_NN], [0], [0], build_is_right=False, other_cond=oc)) == abi.TG_ERR_UNSUPPORTED
     assert join_rc(JoinPlan(abi.JOIN_INNER, [INT_NN, INT_NN], [INT_NN, INT_NN], [0], [0], other_cond=[OtherCond(abi.CMP_LT, 0, 5, 1, 1)])) == abi.TG_ERR_INVALID
+
+
+def test_multi_column_join_key_gates_without_gpu(lib):
+    # several equal conditions (FixedSerializedKey mode, join_table_meta.go:174-178): 2..4 8-byte integer-family key columns
+    # on the shapes that need no build-side scan and no NULL-aware flag; everything else is declined, never mis-evaluated
+    from tidb_b200.plan import OtherCond
+    DBL = FieldType(abi.TYPE_DOUBLE, 0)
+    I32 = FieldType(abi.TYPE_LONG, 0)
+    def rc(plan):
+        d, keep = plan.to_struct()
+        return lib.tg_join_supported(C.byref(d))
+    four = [INT_NN] * 5
+    assert rc(JoinPlan(abi.JOIN_INNER, four, four, [0, 1], [1, 0])) == abi.TG_OK
+    assert rc(JoinPlan(abi.JOIN_INNER, four, four, [0, 1, 2, 3], [0, 1, 2, 3], build_is_right=False)) == abi.TG_OK
+    assert rc(JoinPlan(abi.JOIN_LEFT_OUTER, four, four, [0, 1], [0, 1], build_is_right=True)) == abi.TG_OK
+    assert rc(JoinPlan(abi.JOIN_ANTI_SEMI, four, four, [0, 1], [0, 1], build_is_right=True, rused=[])) == abi.TG_OK
+    assert rc(JoinPlan(abi.JOIN_INNER, four, four, [0, 1, 2, 3, 4], [0, 1, 2, 3, 4])) == abi.TG_ERR_UNSUPPORTED        # > 4 keys
+    assert rc(JoinPlan(abi.JOIN_LEFT_OUTER, four, four, [0, 1], [0, 1], build_is_right=False)) == abi.TG_ERR_UNSUPPORTED   # build-side scan
+    assert rc(JoinPlan(abi.JOIN_LEFT_OUTER_SEMI, four, four, [0, 1], [0, 1], rused=[])) == abi.TG_ERR_UNSUPPORTED        # NULL-aware flag
+    assert rc(JoinPlan(abi.JOIN_INNER, [INT_NN, DBL], [INT_NN, DBL], [0, 1], [0, 1])) == abi.TG_ERR_UNSUPPORTED          # real key column
+    assert rc(JoinPlan(abi.JOIN_INNER, [INT_NN, I32], [INT_NN, I32], [0, 1], [0, 1])) == abi.TG_OK                       # INT is 8 bytes in a chunk (chunk/codec.go:153)
+    assert rc(JoinPlan(abi.JOIN_INNER, four, four, [0, 9], [0, 1])) == abi.TG_ERR_INVALID
+    # the residual key equalities share the 8 OtherCondition item slots
+    oc = [OtherCond(abi.CMP_LT, 0, 4, 1, 4)] * 5
+    assert rc(JoinPlan(abi.JOIN_INNER, four, four, [0, 1, 2], [0, 1, 2], other_cond=oc)) == abi.TG_OK
+    assert rc(JoinPlan(abi.JOIN_INNER, four, four, [0, 1, 2, 3], [0, 1, 2, 3], other_cond=oc)) == abi.TG_ERR_UNSUPPORTED
+
+
+def test_time_join_key_gates_without_gpu(lib):
+    # DATE / DATETIME / TIMESTAMP join keys (getKeyProp join_table_meta.go:154) are offloaded against each other only
+    DT, D, TS = FieldType(abi.TYPE_DATETIME, 0), FieldType(abi.TYPE_DATE, 0), FieldType(abi.TYPE_TIMESTAMP, 0)
+    def rc(plan):
+        d, keep = plan.to_struct()
+        return lib.tg_join_supported(C.byref(d))
+    assert rc(JoinPlan(abi.JOIN_INNER, [DT], [D], [0], [0])) == abi.TG_OK
+    assert rc(JoinPlan(abi.JOIN_LEFT_OUTER, [TS, INT_NN], [DT], [0], [0], build_is_right=False)) == abi.TG_OK
+    assert rc(JoinPlan(abi.JOIN_INNER, [DT], [INT_NN], [0], [0])) == abi.TG_ERR_UNSUPPORTED
+    assert rc(JoinPlan(abi.JOIN_INNER, [FieldType(abi.TYPE_DOUBLE, 0)], [D], [0], [0])) == abi.TG_ERR_UNSUPPORTED
+    assert rc(JoinPlan(abi.JOIN_INNER, [DT, INT_NN], [D, INT_NN], [0, 1], [0, 1])) == abi.TG_ERR_UNSUPPORTED   # several keys: integer family only

@@ -119,6 +119,106 @@ def test_gpu_other_condition_gate():
     assert lib.tg_join_supported(C.byref(d)) == abi.TG_ERR_UNSUPPORTED
 
 
+@pytest.mark.parametrize("jt,build_is_right", [(abi.JOIN_INNER, True), (abi.JOIN_INNER, False), (abi.JOIN_LEFT_OUTER, True),
+                                               (abi.JOIN_RIGHT_OUTER, False), (abi.JOIN_SEMI, True), (abi.JOIN_ANTI_SEMI, True)])
+@pytest.mark.parametrize("nkeys,unsigned_second,nulls", [(2, False, 0.0), (3, False, 0.08), (2, True, 0.08), (4, False, 0.05)])
+def test_gpu_multi_column_join_keys(jt, build_is_right, nkeys, unsigned_second, nulls):
+    # several equal conditions (FixedSerializedKey mode, join_table_meta.go:174-178, codec.go:822): the device joins on a
+    # synthetic 64-bit candidate key (k_composite_key) and re-checks every key column on each candidate pair; key values come
+    # from a small range so pairs that agree on some but not all key columns are common, NULL in any key column = no key,
+    # signed vs unsigned key columns compare by value
+    from test_oracle_join import make_multikey_case
+    rng = np.random.default_rng(5100 + jt * 13 + nkeys + int(build_is_right))
+    if nkeys == 4:
+        INTU = FieldType(abi.TYPE_LONGLONG, 0)
+        def side(rows):
+            return [Column(rng.integers(-3, 3, rows).astype(np.int64), rng.random(rows) < nulls) for _ in range(4)]
+        ltypes = rtypes = [INTU] * 4
+        l, r = Chunk(side(5000)).split(1024), Chunk(side(4000)).split(700)
+        lk = rk = [0, 1, 2, 3]
+    else:
+        ltypes, rtypes, l, r = make_multikey_case(rng, 4000, 6000, nulls, nkeys, unsigned_second=unsigned_second)
+        lk, rk = list(range(1, 1 + nkeys)), list(range(nkeys))
+    semi = jt >= abi.JOIN_SEMI
+    plan = JoinPlan(jt, ltypes, rtypes, lk, rk, build_is_right=build_is_right, lused=[0, 1, 2, 3], rused=[] if semi else [3, 0, 1])
+    want = run_oracle(plan, l, r)
+    assert len(want) > 0 or jt == abi.JOIN_ANTI_SEMI
+    assert_rows_equal(want, run_gpu(plan, l, r))
+
+
+def test_gpu_multi_column_join_keys_with_other_condition_and_filters():
+    # the residual key equalities and the user's OtherCondition share one item list; build / probe filters still apply first
+    from test_oracle_join import make_multikey_case
+    from tidb_b200.plan import OtherCond
+    rng = np.random.default_rng(6200)
+    ltypes, rtypes, l, r = make_multikey_case(rng, 5000, 8000, 0.05, 2)
+    other = [OtherCond(abi.CMP_LT, 0, 0, 1, 3), OtherCond(abi.CMP_NE, 1, 2, -1, -1, const_i64=0)]
+    for jt in (abi.JOIN_INNER, abi.JOIN_LEFT_OUTER):
+        plan = JoinPlan(jt, ltypes, rtypes, [1, 2], [0, 1], build_is_right=True, lused=[0, 1, 2, 3], rused=[3, 0, 1], other_cond=other,
+                        probe_filter=[FilterItem(abi.CMP_GT, 3, const_i64=-(1 << 39))],
+                        build_filter=[] if jt == abi.JOIN_LEFT_OUTER else [FilterItem(abi.CMP_LT, 2, const_i64=1 << 39)])
+        want = run_oracle(plan, l, r)
+        assert len(want) > 0
+        assert_rows_equal(want, run_gpu(plan, l, r))
+
+
+def test_gpu_multi_column_join_keys_large_device_batches():
+    # 3 M probe rows against 300 K build rows on (a, b): crosses the general path's sub-batches only at 16 M rows, so this
+    # checks the bulk behaviour (hash collisions between distinct key tuples would show up as wrong row counts)
+    rng = np.random.default_rng(6300)
+    nb, npr = 300_000, 3_000_000
+    a, b = rng.integers(0, 1000, nb).astype(np.int64), rng.integers(0, 1000, nb).astype(np.int64)
+    pay = np.arange(nb, dtype=np.int64)
+    pa, pb = rng.integers(0, 1000, npr).astype(np.int64), rng.integers(0, 1000, npr).astype(np.int64)
+    plan = JoinPlan(abi.JOIN_INNER, [INT_NN, INT_NN], [INT_NN, INT_NN, INT_NN], [0, 1], [0, 1], build_is_right=True, lused=[0, 1], rused=[2])
+    got = run_gpu(plan, [Chunk([Column(pa), Column(pb)])], [Chunk([Column(a), Column(b), Column(pay)])], required_rows=1 << 20)
+    # expected count by value: pairs per (a, b) tuple
+    key_b = a * 1000 + b
+    key_p = pa * 1000 + pb
+    cnt_b = np.bincount(key_b, minlength=1_000_000)
+    assert len(got) == int(cnt_b[key_p].sum())
+    g = np.array(got, dtype=np.int64)
+    assert np.array_equal(g[:, 0], a[g[:, 2]]) and np.array_equal(g[:, 1], b[g[:, 2]])   # every output row joins equal tuples
+
+
+@pytest.mark.parametrize("jt,build_is_right", [(abi.JOIN_INNER, True), (abi.JOIN_INNER, False), (abi.JOIN_LEFT_OUTER, True),
+                                               (abi.JOIN_LEFT_OUTER, False), (abi.JOIN_SEMI, True), (abi.JOIN_ANTI_SEMI, False)])
+def test_gpu_time_join_keys(jt, build_is_right):
+    # DATE / DATETIME / TIMESTAMP keys (getKeyProp join_table_meta.go:154, codec.go:697-707): compared by calendar fields, the
+    # type / fsp bits of the CoreTime word ignored — a DATE joins the DATETIME at midnight of the same day
+    from test_oracle_join import make_time_case
+    rng = np.random.default_rng(7400 + jt)
+    ltypes, rtypes, l, r = make_time_case(rng, 3000, 5000, 0.07)
+    semi = jt >= abi.JOIN_SEMI
+    plan = JoinPlan(jt, ltypes, rtypes, [1], [0], build_is_right=build_is_right, lused=[0, 1, 2], rused=[] if semi else [1, 0])
+    want = run_oracle(plan, l, r)
+    assert len(want) > 0
+    assert_rows_equal(want, run_gpu(plan, l, r))
+
+
+def test_gpu_time_join_keys_unique_build_and_gate():
+    # unique DATE build keys: the single-pass / U1 paths read the key through load_key(KEY_TIME) as well; the build key column is
+    # an output column, so it must come back with its own type bits, not the masked compare word
+    from test_oracle_join import DATE_TT, DATETIME0_TT, DATETIME6_TT, core_time
+    days = [(2020 + i // 336, 1 + (i // 28) % 12, 1 + i % 28) for i in range(2000)]
+    bkey = np.array([core_time(y, m, d, fsp_tt=DATE_TT) for (y, m, d) in days], dtype=np.int64)
+    rng = np.random.default_rng(7500)
+    pick = rng.integers(0, 2000, 9000)
+    pkey = np.array([core_time(*days[i], fsp_tt=DATETIME6_TT) if rng.random() < 0.6 else core_time(*days[i], 12, 30, 0, 0, DATETIME6_TT) for i in pick], dtype=np.int64)
+    DT, D = FieldType(abi.TYPE_DATETIME, abi.FLAG_NOT_NULL), FieldType(abi.TYPE_DATE, abi.FLAG_NOT_NULL)
+    left = [Chunk([Column(pkey), Column(np.arange(9000, dtype=np.int64))])]
+    right = [Chunk([Column(bkey), Column(np.arange(2000, dtype=np.int64) * 3)])]
+    for rused in ([1], [0, 1]):
+        plan = JoinPlan(abi.JOIN_INNER, [DT, INT_NN], [D, INT_NN], [0], [0], build_is_right=True, lused=[0, 1], rused=rused)
+        want = run_oracle(plan, left, right)
+        assert 4000 < len(want) < 7000
+        assert_rows_equal(want, run_gpu(plan, left, right))
+    lib = abi.load_lib()
+    mixed = JoinPlan(abi.JOIN_INNER, [DT], [INT_NN], [0], [0])     # date-time vs integer key: the planner casts first
+    d, keep = mixed.to_struct()
+    assert lib.tg_join_supported(C.byref(d)) == abi.TG_ERR_UNSUPPORTED
+
+
 @pytest.mark.parametrize("build_is_right", [True, False])
 @pytest.mark.parametrize("uq", ["1", "0"])
 def test_gpu_unique_key_single_pass_probe(build_is_right, uq, monkeypatch):

@@ -233,3 +233,95 @@ def test_oracle_other_condition_vs_nested_loop(jt, build_is_right):
     other = [OtherCond(abi.CMP_LT, 0, 0, 1, 1), OtherCond(abi.CMP_NE, 1, 2, -1, -1, const_i64=3)]
     plan = JoinPlan(jt, ltypes, rtypes, [1], [0], build_is_right=build_is_right, lused=[0, 1, 2], rused=[] if semi else [2, 0], other_cond=other)
     assert_rows_equal(nested_loop_join(plan, l, r), run_oracle(plan, l, r))
+
+
+def make_multikey_case(rng, n_build, n_probe, null_frac, nkeys=2, key_range=6, unsigned_second=False):
+    """two sides of 4 columns each; the first `nkeys` columns of the right side and columns 1..nkeys of the left side are
+    the equal-condition keys, drawn from a small range so that pairs agreeing on SOME but not ALL key columns are common"""
+    def side(rows, first_key):
+        cols = []
+        for c in range(4):
+            is_key = first_key <= c < first_key + nkeys
+            v = rng.integers(-key_range, key_range, rows).astype(np.int64) if is_key else rng.integers(-1 << 40, 1 << 40, rows).astype(np.int64)
+            nulls = rng.random(rows) < null_frac if null_frac > 0 else None
+            cols.append(Column(v, nulls))
+        return cols
+    right, left = side(n_build, 0), side(n_probe, 1)
+    u = FieldType(abi.TYPE_LONGLONG, abi.FLAG_UNSIGNED)
+    rtypes = [INT] * 4
+    ltypes = [INT] * 4
+    if unsigned_second:
+        ltypes[2] = u      # left key 2 unsigned vs right key 2 signed: equal bits of a negative value must not match
+    return ltypes, rtypes, Chunk(left).split(41), Chunk(right).split(23)
+
+
+@pytest.mark.parametrize("jt,build_is_right", [(abi.JOIN_INNER, True), (abi.JOIN_INNER, False), (abi.JOIN_LEFT_OUTER, True),
+                                               (abi.JOIN_RIGHT_OUTER, False), (abi.JOIN_SEMI, True), (abi.JOIN_ANTI_SEMI, True),
+                                               (abi.JOIN_LEFT_OUTER, False), (abi.JOIN_SEMI, False)])
+@pytest.mark.parametrize("nkeys,unsigned_second", [(2, False), (3, False), (2, True)])
+def test_oracle_multi_column_keys_vs_nested_loop(jt, build_is_right, nkeys, unsigned_second):
+    # several equal conditions: FixedSerializedKey (join_table_meta.go:174-178, codec.go:822 SerializeKeys): a pair matches
+    # iff EVERY key column is non-NULL and equal by value
+    rng = np.random.default_rng(4100 + jt * 11 + nkeys)
+    ltypes, rtypes, l, r = make_multikey_case(rng, 500, 700, 0.08, nkeys, unsigned_second=unsigned_second)
+    semi = jt >= abi.JOIN_SEMI
+    plan = JoinPlan(jt, ltypes, rtypes, list(range(1, 1 + nkeys)), list(range(nkeys)), build_is_right=build_is_right,
+                    lused=[0, 1, 2, 3], rused=[] if semi else [3, 0, 1])
+    want = nested_loop_join(plan, l, r)
+    assert len(want) > 0
+    assert_rows_equal(want, run_oracle(plan, l, r))
+
+
+def core_time(year, month, day, hour=0, minute=0, second=0, micro=0, fsp_tt=0):
+    """types.CoreTime bit fields + the fspTt nibble (types/time.go:235-251): year 14 bits at 50, month 4 at 46, day 5 at 41,
+    hour 5 at 36, minute 6 at 30, second 6 at 24, microsecond 20 at 4; fspTt = 0b1110 for DATE, fsp << 1 | is_timestamp else"""
+    v = (year << 50) | (month << 46) | (day << 41) | (hour << 36) | (minute << 30) | (second << 24) | (micro << 4) | fsp_tt
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+DATE_TT, DATETIME0_TT, DATETIME6_TT, TIMESTAMP0_TT = 0b1110, 0, 6 << 1, 1
+
+
+def make_time_case(rng, n_build, n_probe, null_frac):
+    """left: (payload, DATETIME(6) key, payload), right: (DATE key, payload): days from a small window so that dates repeat;
+    a third of the left keys sit at midnight (they can match a DATE), the rest carry a time of day (they cannot)"""
+    def days(n):
+        d = rng.integers(0, 40, n)
+        return [(2023 + int(x) // 28 // 12, 1 + (int(x) // 28) % 12, 1 + int(x) % 28) for x in d]
+    rk = [core_time(y, m, d, fsp_tt=DATE_TT) for (y, m, d) in days(n_build)]
+    lk = []
+    for (y, m, d) in days(n_probe):
+        if rng.random() < 0.34:
+            lk.append(core_time(y, m, d, fsp_tt=DATETIME6_TT))
+        else:
+            lk.append(core_time(y, m, d, int(rng.integers(0, 24)), int(rng.integers(0, 60)), int(rng.integers(0, 60)), int(rng.integers(0, 1000000)), DATETIME6_TT))
+    nl = lambda n: (rng.random(n) < null_frac) if null_frac > 0 else None
+    left = [Column(rng.integers(-1 << 40, 1 << 40, n_probe).astype(np.int64), nl(n_probe)), Column(np.array(lk, dtype=np.int64), nl(n_probe)),
+            Column(rng.integers(-1 << 40, 1 << 40, n_probe).astype(np.int64), nl(n_probe))]
+    right = [Column(np.array(rk, dtype=np.int64), nl(n_build)), Column(rng.integers(-1 << 40, 1 << 40, n_build).astype(np.int64), nl(n_build))]
+    ltypes = [INT, FieldType(abi.TYPE_DATETIME, 0), INT]
+    rtypes = [FieldType(abi.TYPE_DATE, 0), INT]
+    return ltypes, rtypes, Chunk(left).split(61), Chunk(right).split(47)
+
+
+def test_oracle_time_key_known_pairs():
+    # DATE '2024-02-29' joins DATETIME '2024-02-29 00:00:00' whatever the fsp, and the zero date joins the zero datetime
+    # (Time.ToPackedUint, types/time.go:646-657: IsZero → 0); a time of day or another day never does
+    d = [core_time(2024, 2, 29, fsp_tt=DATE_TT), core_time(0, 0, 0, fsp_tt=DATE_TT), core_time(9999, 12, 31, fsp_tt=DATE_TT)]
+    t = [core_time(2024, 2, 29, fsp_tt=DATETIME0_TT), core_time(2024, 2, 29, fsp_tt=DATETIME6_TT), core_time(2024, 2, 29, 0, 0, 0, 1, DATETIME6_TT),
+         core_time(0, 0, 0, fsp_tt=DATETIME0_TT), core_time(2024, 2, 28, fsp_tt=DATETIME0_TT), core_time(9999, 12, 31, fsp_tt=TIMESTAMP0_TT)]
+    plan = JoinPlan(abi.JOIN_INNER, [FieldType(abi.TYPE_DATETIME, 0)], [FieldType(abi.TYPE_DATE, 0)], [0], [0])
+    got = run_oracle(plan, [Chunk([col(t)])], [Chunk([col(d)])])
+    assert sorted(got) == sorted([(t[0], d[0]), (t[1], d[0]), (t[3], d[1]), (t[5], d[2])])
+
+
+@pytest.mark.parametrize("jt,build_is_right", [(abi.JOIN_INNER, True), (abi.JOIN_INNER, False), (abi.JOIN_LEFT_OUTER, True),
+                                               (abi.JOIN_LEFT_OUTER, False), (abi.JOIN_SEMI, True), (abi.JOIN_ANTI_SEMI, False)])
+def test_oracle_time_keys_vs_nested_loop(jt, build_is_right):
+    rng = np.random.default_rng(7300 + jt)
+    ltypes, rtypes, l, r = make_time_case(rng, 300, 500, 0.07)
+    semi = jt >= abi.JOIN_SEMI
+    plan = JoinPlan(jt, ltypes, rtypes, [1], [0], build_is_right=build_is_right, lused=[0, 1, 2], rused=[] if semi else [1, 0])
+    want = nested_loop_join(plan, l, r)
+    assert len(want) > 0
+    assert_rows_equal(want, run_oracle(plan, l, r))

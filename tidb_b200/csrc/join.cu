@@ -21,7 +21,9 @@ struct Side {
   std::vector<uint32_t> flags;
   std::vector<int> elem;
   std::vector<char> needed;       // staged to the device (key ∪ used ∪ filter columns)
-  int key_col = -1;
+  int key_col = -1;               // the single equal-condition key; -1 when the join has several (key_cols)
+  std::vector<int> key_cols;      // several equal conditions: the key columns in condition order
+  std::vector<int> key_reject;    //   per key column: mixed-signedness pair and this is the signed side (negative = no key)
   std::vector<int> used;          // columns of this side that appear in the output
   DevFilter filter{};
 };
@@ -112,6 +114,8 @@ struct JoinImpl {
   int n_out = 0;
   std::vector<int> out_elem;
   KeySpec build_key{}, probe_key{};   // data pointers filled per launch
+  bool multi_key = false;             // several equal conditions: synthetic 64-bit candidate key + residual equalities (k_composite_key)
+  DevBuf bkey_syn, bkey_syn_nn, pkey_syn, pkey_syn_nn;
   std::vector<tg_other_item> other;   // OtherCondition (sides already mapped: 0 = probe child, 1 = build child)
   std::vector<int> other_build_cols;  // build columns it reads (kept in the row store although they may not be output)
   DevOther dev_other{};               // compiled after the build (row-store word of every build operand)
@@ -174,6 +178,7 @@ static int key_kind_of(int tp) {
   if (is_int_family(tp)) return KEY_I64;
   if (tp == TG_TYPE_DOUBLE) return KEY_F64;
   if (tp == TG_TYPE_FLOAT) return KEY_F32;
+  if (tp == TG_TYPE_DATE || tp == TG_TYPE_DATETIME || tp == TG_TYPE_TIMESTAMP) return KEY_TIME;   // getKeyProp join_table_meta.go:154
   return -1;
 }
 static bool key_unsigned(int tp, uint32_t flag) {
@@ -209,13 +214,34 @@ static int setup(JoinImpl* j, const tg_join_desc* d) {
   Side left, right;
   TG_TRY(fill_side(left, d->n_left_cols, d->left_types, d->left_flags));
   TG_TRY(fill_side(right, d->n_right_cols, d->right_types, d->right_flags));
-  if (d->nkeys != 1) return fail(TG_ERR_UNSUPPORTED, "GPU hash join handles exactly one equal-condition key (OneInt64 / fixed 8-byte key modes)");
-  int lk = d->left_key_idx[0], rk = d->right_key_idx[0];
-  if (lk < 0 || lk >= left.ncols || rk < 0 || rk >= right.ncols) return fail(TG_ERR_INVALID, "key column out of range");
-  left.key_col = lk; right.key_col = rk;
-  int lkind = key_kind_of(left.types[lk]), rkind = key_kind_of(right.types[rk]);
-  if (lkind < 0 || rkind < 0) return fail(TG_ERR_UNSUPPORTED, "join key type is not offloaded (int family / float / double only)");
-  if ((lkind == KEY_I64) != (rkind == KEY_I64)) return fail(TG_ERR_UNSUPPORTED, "integer vs real join keys are cast by the planner before the join");
+  if (d->nkeys < 1 || d->nkeys > TG_MAX_JOIN_KEYS) return fail(TG_ERR_UNSUPPORTED, "GPU hash join handles 1..4 equal-condition keys");
+  if (!d->left_key_idx || !d->right_key_idx) return fail(TG_ERR_INVALID, "key index arrays are NULL");
+  j->multi_key = d->nkeys > 1;
+  std::vector<tg_other_item> residual;   // several keys: `left_key_i = right_key_i`, re-checked on every candidate pair
+  if (!j->multi_key) {
+    int lk = d->left_key_idx[0], rk = d->right_key_idx[0];
+    if (lk < 0 || lk >= left.ncols || rk < 0 || rk >= right.ncols) return fail(TG_ERR_INVALID, "key column out of range");
+    left.key_col = lk; right.key_col = rk;
+    int lkind = key_kind_of(left.types[lk]), rkind = key_kind_of(right.types[rk]);
+    if (lkind < 0 || rkind < 0) return fail(TG_ERR_UNSUPPORTED, "join key type is not offloaded (int family / float / double / date-time only)");
+    if ((lkind == KEY_I64) != (rkind == KEY_I64)) return fail(TG_ERR_UNSUPPORTED, "integer vs real join keys are cast by the planner before the join");
+    if ((lkind == KEY_TIME) != (rkind == KEY_TIME)) return fail(TG_ERR_UNSUPPORTED, "date-time keys only join date-time keys (codec.go:707)");
+  } else {
+    // FixedSerializedKey mode (join_table_meta.go:174-178) restricted to 8-byte integer-family columns
+    for (int q = 0; q < d->nkeys; q++) {
+      int lk = d->left_key_idx[q], rk = d->right_key_idx[q];
+      if (lk < 0 || lk >= left.ncols || rk < 0 || rk >= right.ncols) return fail(TG_ERR_INVALID, "key column out of range");
+      if (!is_int_family(left.types[lk]) || !is_int_family(right.types[rk]) || left.elem[lk] != 8 || right.elem[rk] != 8)
+        return fail(TG_ERR_UNSUPPORTED, "joins on several key columns are offloaded for 8-byte integer-family keys only");
+      const bool lu = key_unsigned(left.types[lk], left.flags[lk]), ru = key_unsigned(right.types[rk], right.flags[rk]);
+      left.key_cols.push_back(lk); right.key_cols.push_back(rk);
+      left.key_reject.push_back(lu != ru && !lu); right.key_reject.push_back(lu != ru && !ru);
+      tg_other_item it{};
+      it.op = TG_CMP_EQ; it.is_real = 0; it.lhs_side = 0; it.lhs_col = lk; it.rhs_side = 1; it.rhs_col = rk;
+      it.lhs_unsigned = lu; it.rhs_unsigned = ru;
+      residual.push_back(it);
+    }
+  }
   auto used_list = [&](int n, const int32_t* v, int ncols, std::vector<int>& out) -> int {
     out.clear();
     if (n < 0) { for (int i = 0; i < ncols; i++) out.push_back(i); return TG_OK; }
@@ -254,13 +280,16 @@ static int setup(JoinImpl* j, const tg_join_desc* d) {
   TG_TRY(check_filter(j->probe, d->probe_filter, d->n_probe_filter, j->probe.filter));
   // OtherCondition (inner_join_probe.go:72-79): sides re-mapped to probe (0) / build (1)
   j->other.clear(); j->other_build_cols.clear();
-  if (d->n_other_cond < 0 || d->n_other_cond > TG_MAX_OTHER) return fail(TG_ERR_UNSUPPORTED, "at most 8 OtherCondition items are offloaded");
-  if (d->n_other_cond > 0) {
-    if (!d->other_cond) return fail(TG_ERR_INVALID, "other_cond is NULL");
-    if (j->need_scan || j->probe_kind == PK_MARK_ONLY) return fail(TG_ERR_UNSUPPORTED, "OtherCondition with a build-side scan (outer side / left side is the build side) is not offloaded");
-    if (j->has_flag_col) return fail(TG_ERR_UNSUPPORTED, "OtherCondition on left outer semi joins (NULL-aware match flag) is not offloaded");
-    for (int i = 0; i < d->n_other_cond; i++) {
-      tg_other_item it = d->other_cond[i];
+  if (d->n_other_cond < 0 || d->n_other_cond + (int)residual.size() > TG_MAX_OTHER)
+    return fail(TG_ERR_UNSUPPORTED, "at most 8 OtherCondition items (key equalities of a multi-column key included) are offloaded");
+  if (d->n_other_cond > 0 && !d->other_cond) return fail(TG_ERR_INVALID, "other_cond is NULL");
+  std::vector<tg_other_item> items = residual;
+  for (int i = 0; i < d->n_other_cond; i++) items.push_back(d->other_cond[i]);
+  if (!items.empty()) {
+    if (j->need_scan || j->probe_kind == PK_MARK_ONLY) return fail(TG_ERR_UNSUPPORTED, "OtherCondition / several key columns with a build-side scan (outer side / left side is the build side) are not offloaded");
+    if (j->has_flag_col) return fail(TG_ERR_UNSUPPORTED, "OtherCondition / several key columns on left outer semi joins (NULL-aware match flag) are not offloaded");
+    for (size_t i = 0; i < items.size(); i++) {
+      tg_other_item it = items[i];
       if (it.op < TG_CMP_LT || it.op > TG_CMP_NE) return fail(TG_ERR_INVALID, "bad OtherCondition op");
       auto remap = [&](int32_t& side, int32_t col, bool may_be_const) -> int {
         if (side < 0) return may_be_const ? TG_OK : fail(TG_ERR_INVALID, "OtherCondition: the left operand must be a column");
@@ -282,7 +311,8 @@ static int setup(JoinImpl* j, const tg_join_desc* d) {
     }
   }
   for (Side* s : {&j->build, &j->probe}) {
-    s->needed[s->key_col] = 1;
+    if (s->key_col >= 0) s->needed[s->key_col] = 1;
+    for (int c : s->key_cols) s->needed[c] = 1;
     for (int c : s->used) {
       if (s->elem[c] != 8 && s->elem[c] != 4) return fail(TG_ERR_UNSUPPORTED, "only 4/8-byte fixed-width columns are offloaded (no DECIMAL / var-len yet)");
       s->needed[c] = 1;
@@ -295,9 +325,9 @@ static int setup(JoinImpl* j, const tg_join_desc* d) {
   // key specs; mixed signedness (NeedSignFlag, join_table_meta.go:296-303): the signed side's negative
   // values can never match
   int bk = j->build.key_col, pk = j->probe.key_col;
-  j->build_key = KeySpec{nullptr, nullptr, key_kind_of(j->build.types[bk]), 0};
-  j->probe_key = KeySpec{nullptr, nullptr, key_kind_of(j->probe.types[pk]), 0};
-  if (j->build_key.kind == KEY_I64) {
+  j->build_key = KeySpec{nullptr, nullptr, j->multi_key ? KEY_I64 : key_kind_of(j->build.types[bk]), 0};
+  j->probe_key = KeySpec{nullptr, nullptr, j->multi_key ? KEY_I64 : key_kind_of(j->probe.types[pk]), 0};
+  if (!j->multi_key && j->build_key.kind == KEY_I64) {
     bool bu = key_unsigned(j->build.types[bk], j->build.flags[bk]), pu = key_unsigned(j->probe.types[pk], j->probe.flags[pk]);
     if (bu != pu) { j->build_key.reject_negative = !bu; j->probe_key.reject_negative = !pu; }
   }
@@ -447,6 +477,25 @@ static int devchunk_view(const tg_chunk* chk, const Side& s, DevCols& v, int64_t
   return TG_OK;
 }
 
+// several equal conditions: the synthetic candidate-key column of one side's `n` device-resident rows (k_composite_key)
+static int composite_key(JoinImpl* j, const Side& s, const DevCols& v, int64_t n, DevBuf& key, DevBuf& not_null) {
+  TG_TRY(key.ensure(j->device, (size_t)(n + 1) * 8 + 16));
+  TG_TRY(not_null.ensure(j->device, (size_t)((n + 31) / 32) * 4 + 16));
+  if (n <= 0) return TG_OK;
+  MultiKeySrc src{};
+  src.nk = (int)s.key_cols.size();
+  for (int q = 0; q < src.nk; q++) {
+    const int c = s.key_cols[q];
+    src.data[q] = reinterpret_cast<const int64_t*>(v.data[c]);
+    src.nulls[q] = v.nulls[c];
+    src.reject[q] = s.key_reject[q];
+    if (!src.data[q]) return fail(TG_ERR_INVALID, "key column data is NULL");
+  }
+  k_composite_key<<<grid_for(j, n, 256, 8), 256, 0, j->stream>>>(src, n, key.as<int64_t>(), not_null.as<uint32_t>());
+  j->stats.kernel_launches++;
+  return TG_OK;
+}
+
 // ---- build --------------------------------------------------------------------------------------------
 static int build_table(JoinImpl* j) {
   const Side& b = j->build;
@@ -454,7 +503,10 @@ static int build_table(JoinImpl* j) {
   j->stats.build_rows = n;
   DevCols bview = j->bcols.view(b);
   KeySpec ks = j->build_key;
-  ks.data = bview.data[b.key_col]; ks.nulls = bview.nulls[b.key_col];
+  if (j->multi_key) {
+    TG_TRY(composite_key(j, b, bview, n, j->bkey_syn, j->bkey_syn_nn));
+    ks.data = j->bkey_syn.p; ks.nulls = j->bkey_syn_nn.as<uint8_t>();
+  } else { ks.data = bview.data[b.key_col]; ks.nulls = bview.nulls[b.key_col]; }
   unsigned long long nslots = (unsigned long long)((double)(n > 0 ? n : 1) / j->load_factor) + 32;
   // the L2 partition pass handles at most TG_MAX_PARTS slices and wants them <= ~33 MB (45 MB slices: 2.10 vs 1.93 ms,
   // profiles/r2_sweep_probe_lf_parts.jsonl): with the DEFAULT load factor a table that would need more slices is made denser,
@@ -792,7 +844,11 @@ static int probe_device(JoinImpl* j, const DevCols& pview, int64_t n, ResultBatc
   const Side& p = j->probe;
   j->stats.probe_rows += n;
   KeySpec ks = j->probe_key;
-  ks.data = pview.data[p.key_col]; ks.nulls = pview.nulls[p.key_col];
+  if (j->multi_key) {
+    if (in_seg) return fail(TG_ERR_UNSUPPORTED, "segmented device chunks: joins on several key columns take the general path");
+    TG_TRY(composite_key(j, p, pview, n, j->pkey_syn, j->pkey_syn_nn));
+    ks.data = j->pkey_syn.p; ks.nulls = j->pkey_syn_nn.as<uint8_t>();
+  } else { ks.data = pview.data[p.key_col]; ks.nulls = pview.nulls[p.key_col]; }
   TG_TRY(j->out_cursor.ensure(j->device, 64));
   if (in_seg && !fast_path_ok(j, pview)) return fail(TG_ERR_UNSUPPORTED, "segmented device chunks are only accepted by the fused fast path (unique build keys, <= 1 payload, no filters)");
   if (fast_path_ok(j, pview)) {
@@ -968,7 +1024,8 @@ static int probe_device(JoinImpl* j, const DevCols& pview, int64_t n, ResultBatc
       }
     }
     KeySpec sks = ks;
-    sks.data = sub.data[p.key_col]; sks.nulls = sub.nulls[p.key_col];
+    if (j->multi_key) { sks.data = reinterpret_cast<const int64_t*>(ks.data) + lo; sks.nulls = ks.nulls + lo / 8; }
+    else { sks.data = sub.data[p.key_col]; sks.nulls = sub.nulls[p.key_col]; }
     TG_TRY(j->tmp_cnt.ensure(j->device, (size_t)(m + 1) * 4));
     TG_TRY(j->tmp_slot.ensure(j->device, (size_t)(m + 1) * 4));
     k_probe_count<<<grid_for(j, m, 256, 8), 256, 0, j->stream>>>(sks, sub, p.filter, j->dev_other, m, j->tv, j->probe_kind, j->tmp_cnt.as<uint32_t>(),

@@ -30,7 +30,7 @@ static const uint32_t kInvalidSlot = 0xFFFFFFFFu;
 static const unsigned long long kCntMask = (1ull << 28) - 1;
 
 enum { TABLE_NONE = 0, TABLE_U1 = 1, TABLE_G = 2 };
-enum { KEY_I64 = 0, KEY_F64 = 1, KEY_F32 = 2 };
+enum { KEY_I64 = 0, KEY_F64 = 1, KEY_F32 = 2, KEY_TIME = 3 };
 enum { SRC_PROBE_COL = 0, SRC_BUILD_KEY = 1, SRC_BUILD_META = 2, SRC_BUILD_WORD = 3, SRC_FLAG = 4 };
 
 struct KeySpec {
@@ -112,6 +112,11 @@ __device__ __forceinline__ bool load_key(const KeySpec& ks, int64_t row, int64_t
   if (ks.kind == KEY_I64) {
     k = reinterpret_cast<const int64_t*>(ks.data)[row];
     if (ks.reject_negative && k < 0) return false;
+  } else if (ks.kind == KEY_TIME) {
+    // DATE / DATETIME / TIMESTAMP keys are serialized as Time.ToPackedUint (codec.go:697-707, types/time.go:646): a function
+    // of the calendar fields only.  The CoreTime bit fields above the 4 fspTt bits (types/time.go:235-251) carry exactly those
+    // fields, so equal packed values <=> equal masked words; the type / fsp bits never take part in a key comparison.
+    k = reinterpret_cast<const int64_t*>(ks.data)[row] & ~(int64_t)0xF;
   } else {
     double d = ks.kind == KEY_F64 ? reinterpret_cast<const double*>(ks.data)[row]
                                   : (double)reinterpret_cast<const float*>(ks.data)[row];
@@ -149,6 +154,52 @@ __device__ __forceinline__ uint32_t table_find(const TableView& t, int64_t k, un
     if (v.key == k) { *meta = v.meta; return (uint32_t)s; }
     if (v.key == kEmptyKey) return kInvalidSlot;
     if (++s == t.nslots) s = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// several equal conditions (join keys): FixedSerializedKey mode of the reference (join_table_meta.go:174-178: every key
+// column fixed width → codec.SerializeKeys codec.go:822 concatenates them; a row with a NULL in ANY key column has no key,
+// hash_join_v2.go / preAllocForSerializedKeyBuffer :429-447).  Here the serialized key is replaced by ONE 64-bit candidate
+// key = a mix of the key column values, written with its own NOT-NULL bitmap by this pre-pass; the table and every probe
+// kernel then run unchanged on that synthetic int64 column, and the exact equality of every key column is re-checked on each
+// candidate pair by residual `left_key_i = right_key_i` items the host appends to OtherCondition (a 64-bit collision can
+// create a candidate pair, never a result row).  reject[c]: mixed signed / unsigned pair and this side is the signed one —
+// a negative value can never equal an unsigned one (NeedSignFlag, join_table_meta.go:296-303), the row has no key.
+// ---------------------------------------------------------------------------------------------
+#define TG_MAX_JOIN_KEYS 4
+struct MultiKeySrc {
+  int32_t nk, pad;
+  const int64_t* data[TG_MAX_JOIN_KEYS];
+  const uint8_t* nulls[TG_MAX_JOIN_KEYS];
+  int32_t reject[TG_MAX_JOIN_KEYS];
+};
+__global__ void __launch_bounds__(256)
+k_composite_key(MultiKeySrc src, int64_t n, int64_t* __restrict__ out_key, uint32_t* __restrict__ out_not_null) {
+  // whole warps stride over 32-row groups; lane 0 stores the group's 32 NOT-NULL bits (LSB = first row, chunk.Column layout)
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t groups = (n + 31) >> 5;
+  for (int64_t g = warp; g < groups; g += nwarps) {
+    const int64_t i = (g << 5) + lane;
+    bool valid = i < n;
+    uint64_t h = 0;
+    if (valid) {
+      for (int c = 0; c < src.nk; c++) {
+        if (src.nulls[c] && !bit_not_null(src.nulls[c], i)) { valid = false; break; }
+        const int64_t v = src.data[c][i];
+        if (src.reject[c] && v < 0) { valid = false; break; }
+        if (c == 0) h = (uint64_t)v;
+        else {   // splitmix-style finalizer of the running value (a bijection), then the next column folded in by an odd multiply
+          h ^= h >> 30; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 27; h *= 0x94D049BB133111EBull; h ^= h >> 31;
+          h += (uint64_t)v * 0x9E3779B97F4A7C15ull + (uint64_t)c;
+        }
+      }
+      if (valid) out_key[i] = (int64_t)h; else out_key[i] = 0;
+    }
+    const unsigned bits = __ballot_sync(0xffffffffu, valid);
+    if (lane == 0) out_not_null[g] = bits;
   }
 }
 
