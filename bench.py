@@ -65,7 +65,36 @@ class ClockSampler:
         self.proc = None
         self.lines = []
 
+    NVML_REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
+
     def start(self):
+        # NVML polled every 2 ms from a thread (the default timed region is ~40 ms: an nvidia-smi child process would deliver its
+        # first sample after the region has ended); nvidia-smi -lms stays as the fall-back when NVML cannot be used
+        self.samples, self._halt, self.nv = [], threading.Event(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            try:
+                import torch
+                u = str(torch.cuda.get_device_properties(self.idx).uuid)
+                u = u if u.startswith("GPU-") else "GPU-" + u
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(u)
+                except Exception:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(u.encode())
+            except Exception:
+                h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))     # fails here, not in the thread, if unsupported
+            self.nv = (pynvml, h)
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -74,11 +103,34 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        pynvml, h = self.nv
+        while not self._halt.is_set():
+            try:
+                sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    r = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    r = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.samples.append((sm, r))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if getattr(self, "nv", None):
+            self._halt.set()
+            self.t.join(timeout=1)
+            sm = [a for a, _ in self.samples]
+            bits = 0
+            for _, r in self.samples:
+                bits |= r
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.mx, "samples": len(sm),
+                    "reasons": sorted(nm for bit, nm in self.NVML_REASONS if bits & bit), "source": "nvml, 2 ms period, timed region only"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)

@@ -445,6 +445,18 @@ int tg_partition_exchange_cf_ex(int device, const int64_t* key_dev, int64_t rows
                                 int64_t region_cap, int64_t* sent_rows_dev, uint64_t* overflow_dev, int32_t ctas_per_sm,
                                 void* stream);
 
+/* tg_partition_exchange_cf_ex whose destinations cannot lose rows to skew: a row that does not fit its destination's region
+ * is appended to a LOCAL spill area instead (column c at spill_cols_dev[c], at most spill_cap rows in total, filled through
+ * *spill_cursor_dev — device u64, zeroed by the caller, it keeps counting across calls).  After the pipeline the caller reads
+ * the cursor once and moves the spilled rows with the counted exchange (tg_partition_count + tg_partition_exchange).
+ * *overflow_dev is raised only when the spill area itself is full.  The reference's exchange has unbounded per-partition
+ * queues (executor/shuffle.go:450) — skew makes it slower, never wrong; this is the fixed-capacity equivalent.           */
+int tg_partition_exchange_cf_spill(int device, const int64_t* key_dev, int64_t rows, int32_t nparts, int32_t ncols,
+                                   const void* const* src_cols_dev, void* const* recv_cols_peer, int64_t region_base,
+                                   int64_t region_cap, int64_t* sent_rows_dev, uint64_t* overflow_dev,
+                                   void* const* spill_cols_dev, int64_t spill_cap, uint64_t* spill_cursor_dev,
+                                   int32_t ctas_per_sm, void* stream);
+
 /* Transfer stage of the count-free exchange on the SMs instead of the copy engines: region r = the first
  * min(counts_dev[count_index[r]], cap_rows) rows (8 bytes each) of src_dev[r] -> dst_peer[r] (a peer address mapped with
  * tg_ipc_open).  128-bit loads / stores, no shared memory, <= 32 registers: the kernel fits NEXT TO the persistent probe

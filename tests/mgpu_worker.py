@@ -26,6 +26,17 @@ def gen(rank, world, nb, npr, step):
     return bk, bv, pk, pv
 
 
+HOT_ID = 12345   # a build row of rank 0's shard: the key most probe rows of the skewed steps carry
+
+
+def gen_skew(rank, world, nb, npr, step):
+    """the probe shard of gen() with 60 % of the rows rewritten to ONE hot key: its owner's receive regions overflow"""
+    _, _, pk, pv = gen(rank, world, nb, npr, step)
+    rng = np.random.default_rng(9000 + 31 * step + rank)
+    hot = (np.array([HOT_ID], dtype=np.int64) * np.int64(-7046029254386353131))[0]   # wraps like the build keys of gen()
+    return np.where(rng.random(npr) < 0.6, hot, pk), pv
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", required=True)
@@ -87,6 +98,39 @@ def main():
     xm.check()
     xm.close()
     res = {f"s{s}c{c}": outs[s][c] for s in range(a.steps) for c in range(4)}
+    # skewed keys with a spill area: the hot key's owner cannot hold 60 % of every sender's rows in its regions; the regroup
+    # kernel appends what does not fit to the local spill area, the counted exchange moves it afterwards, nothing is lost
+    xs = MailboxExchange(rank, world, local, xstream, 2, a.probe_rows, dma=bool(a.dma), direct_peers=1 if a.dma == 2 else 0, sm_copy=a.dma == 3,
+                         spill_rows=2 * a.probe_rows)
+    skew_steps = 2
+    sk = [tuple(t(x) for x in gen_skew(rank, world, a.build_rows, a.probe_rows, s)) for s in range(skew_steps)]
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    souts = []
+    with torch.cuda.stream(stream):
+        xs.send(sk[0][0], [sk[0][0], sk[0][1]], stream)
+        for s in range(skew_steps):
+            if s + 1 < skew_steps:
+                xs.send(sk[s + 1][0], [sk[s + 1][0], sk[s + 1][1]], stream)
+            cols_in, seg_cnt, cap, set_, ep = xs.recv(stream)
+            rows, cols, _ = join.probe_segments(cols_in, seg_cnt, cap, sync=True)
+            souts.append([view(p, rows).cpu().numpy().copy() for p in cols])
+            xs.release(stream, set_, ep)
+    xs.check()                       # the spill area took the excess: no overflow error
+    nsp, spcols = xs.drain_spill()
+    res["spilled_rows"] = np.array([nsp])
+    with torch.cuda.stream(stream):
+        xk = KeyExchange(rank, world, local, stream, 2, 2 * a.probe_rows * skew_steps * world + 4096, "p2p")
+        lk, lv = xk.exchange(spcols[0], [spcols[0], spcols[1]])
+        if lk.numel() > 0:           # only the hot key's owner receives spilled rows
+            rows, cols, _ = join.probe([lk, lv], sync=True)
+            if rows > 0:
+                souts.append([view(p, rows).cpu().numpy().copy() for p in cols])
+    torch.cuda.synchronize(dev)
+    xk.close()
+    xs.close()
+    for c in range(4):
+        res[f"skew_c{c}"] = np.concatenate([o[c] for o in souts])
     # forced overflow: regions far too small for the rows that arrive -> every rank must see the error
     xo = MailboxExchange(rank, world, local, xstream, 2, 4096, slack=1.0)
     with torch.cuda.stream(stream):

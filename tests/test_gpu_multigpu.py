@@ -55,6 +55,14 @@ def test_mailbox_exchange_two_ranks_vs_oracle(dma):
         got = [np.concatenate([res[k][f"s{s_}c{c}"] for k in range(world)]) for c in range(4)]
         assert len(got[0]) == n, (s_, len(got[0]), n)
         assert np.array_equal(columns_sorted(ocols), columns_sorted([(g, np.zeros(len(g), dtype=bool)) for g in got])), f"step {s_}"
+    # skewed steps: spill area + counted exchange of the spilled rows; the union over ranks must still be the whole join
+    ps = [W.gen_skew(k, world, nb, npr, s_) for k in range(world) for s_ in range(2)]
+    probe = Chunk([Column(np.concatenate([p[0] for p in ps])), Column(np.concatenate([p[1] for p in ps]))])
+    n, ocols = O.OracleJoin(plan, 4).run(build.split(4096), probe.split(4096))
+    got = [np.concatenate([res[k][f"skew_c{c}"] for k in range(world)]) for c in range(4)]
+    assert sum(int(res[k]["spilled_rows"][0]) for k in range(world)) > 0.2 * 2 * world * npr, "the skewed steps must actually spill"
+    assert len(got[0]) == n, (len(got[0]), n)
+    assert np.array_equal(columns_sorted(ocols), columns_sorted([(g, np.zeros(len(g), dtype=bool)) for g in got])), "skewed steps"
     for k in range(world):
         assert int(res[k]["overflow_detected"][0]) == 1, "a receive-region overflow must be reported on every rank"
         assert int(res[k]["timeout_detected"][0]) == 1, "a silent sender must end the wait with an error, not a hang"

@@ -61,6 +61,27 @@ def _worker(rank, world, port, q):
     # a region that is too small drops rows and says so (the device path raises its sticky flag the same way)
     _, small_cnt, small_ovf = exchange_segments_host(pk, [pk, pv], world, rank, 1024, all_to_all)
     assert small_ovf and int(small_cnt.max()) == 1024
+    # skew with a spill area (tg_partition_exchange_cf_spill / MailboxExchange.drain_spill): half of the rows carry one hot key,
+    # the excess of the overflowing regions stays in the sender's spill list and travels through the counted exchange afterwards;
+    # segments + spilled rows together are exactly the rows this rank owns
+    hot = bk[0] if rank == 0 else None
+    hots = [None] * world
+    dist.all_gather_object(hots, hot)
+    sk = np.where(np.arange(npr) % 2 == 0, np.int64(hots[0]), pk)
+    spilled = []
+    cap_s = 12 * 1024            # the hot key's owner gets ~15000 rows from every sender
+    s_cols, s_cnt, s_ovf = exchange_segments_host(sk, [sk, pv], world, rank, cap_s, all_to_all, spill=spilled)
+    assert not s_ovf
+    spk = np.concatenate([e[0] for e in spilled]) if spilled else np.zeros(0, dtype=np.int64)
+    spv = np.concatenate([e[1] for e in spilled]) if spilled else np.zeros(0, dtype=np.int64)
+    rk, rv = exchange_by_key_host(spk, [spk, spv], world, all_to_all)
+    k1, v1 = segments_to_dense(s_cols, s_cnt, cap_s)
+    mine_k, mine_v = exchange_by_key_host(sk, [sk, pv], world, all_to_all)       # the counted exchange of the same rows
+    owner = int(partition_of_keys_np(np.array([hots[0]], dtype=np.int64), world)[0])
+    assert len(spk) > 0 and (int(s_cnt.max()) == cap_s) == (owner == rank)     # every sender spills; only the hot key's owner has full regions
+    assert np.array_equal(np.sort(np.concatenate([v1, rv])), np.sort(mine_v))
+    allk, allv = np.concatenate([k1, rk]), np.concatenate([v1, rv])
+    assert np.array_equal(allk[np.argsort(allv)], mine_k[np.argsort(mine_v)])
     plan = JoinPlan(abi.JOIN_INNER, [INT, INT], [INT, INT], [0], [0])
     n, cols = O.OracleJoin(plan, 2).run([Chunk([Column(lbk), Column(lbv)])], Chunk([Column(dk), Column(dv)]).split(1024))
     shard = [c[0] for c in cols]

@@ -133,7 +133,7 @@ EXPORTED_SYMBOLS = [
     "tg_agg_next", "tg_agg_close", "tg_agg_result_dev", "tg_agg_get_stats",
     "tg_vec_compare_int", "tg_vec_compare_real", "tg_vec_arith_int", "tg_vec_arith_real",
     "tg_vec_filter", "tg_topn",
-    "tg_partition_by_key", "tg_partition_of_key", "tg_partition_exchange", "tg_partition_exchange_cf", "tg_partition_exchange_cf_ex", "tg_partition_count",
+    "tg_partition_by_key", "tg_partition_of_key", "tg_partition_exchange", "tg_partition_exchange_cf", "tg_partition_exchange_cf_ex", "tg_partition_exchange_cf_spill", "tg_partition_count",
     "tg_mail_signal", "tg_mail_wait", "tg_peer_copy_regions",
     "tg_ipc_export", "tg_ipc_open", "tg_ipc_close",
 ]

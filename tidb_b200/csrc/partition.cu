@@ -111,8 +111,10 @@ static __global__ void k_zero_cf(unsigned long long* sent, int nparts) {
 
 static int exchange_cf_impl(int device, const int64_t* key_dev, int64_t rows, int32_t nparts, int32_t ncols,
                             const void* const* src_cols_dev, void* const* recv_cols_peer, int64_t region_base,
-                            int64_t region_cap, int64_t* sent_rows_dev, uint64_t* overflow_dev, int ctas_per_sm, void* stream) {
+                            int64_t region_cap, int64_t* sent_rows_dev, uint64_t* overflow_dev, int ctas_per_sm, void* stream,
+                            void* const* spill_cols_dev = nullptr, int64_t spill_cap = 0, uint64_t* spill_cursor_dev = nullptr) {
   TG_TRY(check_parts(nparts, ncols));
+  if (spill_cursor_dev && (!spill_cols_dev || spill_cap <= 0)) return fail(TG_ERR_INVALID, "a spill cursor needs spill columns and a positive spill_cap");
   if (ncols > 4) return fail(TG_ERR_UNSUPPORTED, "count-free exchange moves at most 4 columns per call");
   if (!scatter_bulk_enabled()) return fail(TG_ERR_UNSUPPORTED, "count-free exchange needs the bulk-store scatter kernel (TG_SCATTER_BULK=0 disables it)");
   if (!sent_rows_dev || !overflow_dev || region_cap <= 0) return fail(TG_ERR_INVALID, "sent_rows_dev / overflow_dev / region_cap are required");
@@ -130,6 +132,10 @@ static int exchange_cf_impl(int device, const int64_t* key_dev, int64_t rows, in
   for (int c = 0; c < ncols; c++) { d.src[c] = src_cols_dev[c]; for (int p = 0; p < nparts; p++) d.dst[p][c] = recv_cols_peer[p * ncols + c]; }
   d.dst_base = nullptr; d.base_const = region_base;   // every destination holds this sender's region at the same row offset
   d.capacity = region_cap; d.overflow = reinterpret_cast<unsigned long long*>(overflow_dev);
+  if (spill_cursor_dev) {
+    for (int c = 0; c < ncols; c++) { if (!spill_cols_dev[c]) return fail(TG_ERR_INVALID, "spill column is NULL"); d.spill[c] = spill_cols_dev[c]; }
+    d.spill_cap = spill_cap; d.spill_cursor = reinterpret_cast<unsigned long long*>(spill_cursor_dev);
+  }
   const int64_t TILE = 1024;
   const int64_t n_main = rows / TILE * TILE;
   if (n_main > 0) TG_TRY(launch_partition_scatter<false>(device, st, reinterpret_cast<const long long*>(key_dev), nullptr, n_main, d, cursors, nullptr, ctas_per_sm));
@@ -153,6 +159,15 @@ int tg_partition_exchange_cf_ex(int device, const int64_t* key_dev, int64_t rows
                                 const void* const* src_cols_dev, void* const* recv_cols_peer, int64_t region_base,
                                 int64_t region_cap, int64_t* sent_rows_dev, uint64_t* overflow_dev, int32_t ctas_per_sm, void* stream) {
   return exchange_cf_impl(device, key_dev, rows, nparts, ncols, src_cols_dev, recv_cols_peer, region_base, region_cap, sent_rows_dev, overflow_dev, ctas_per_sm, stream);
+}
+
+int tg_partition_exchange_cf_spill(int device, const int64_t* key_dev, int64_t rows, int32_t nparts, int32_t ncols,
+                                   const void* const* src_cols_dev, void* const* recv_cols_peer, int64_t region_base,
+                                   int64_t region_cap, int64_t* sent_rows_dev, uint64_t* overflow_dev, void* const* spill_cols_dev,
+                                   int64_t spill_cap, uint64_t* spill_cursor_dev, int32_t ctas_per_sm, void* stream) {
+  if (!spill_cursor_dev) return fail(TG_ERR_INVALID, "spill_cursor_dev is required (use tg_partition_exchange_cf_ex without a spill area)");
+  return exchange_cf_impl(device, key_dev, rows, nparts, ncols, src_cols_dev, recv_cols_peer, region_base, region_cap, sent_rows_dev, overflow_dev,
+                          ctas_per_sm, stream, spill_cols_dev, spill_cap, spill_cursor_dev);
 }
 
 // ---- SM-driven region copy over NVLink (the transfer stage of the count-free exchange without copy engines) --------------

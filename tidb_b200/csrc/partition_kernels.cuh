@@ -36,6 +36,13 @@ struct PartDst {
   // so a tile is placed with a shared-memory cursor — no global atomic (and its ~1 us round trip between two CTA
   // barriers) per (tile, destination).  At the end CTA b stores its fill counts to cursors[p * gridDim.x + b].
   long long sub_cap;
+  // spill_cursor != nullptr (count-free mode, no sub-segments): rows that do not fit their destination's capacity are not
+  // dropped but appended to a LOCAL spill area (column c at spill[c], at most spill_cap rows, one global cursor); the host
+  // drains it afterwards through a counted exchange.  *overflow is then raised only when the spill area itself is full.
+  // A skewed key distribution makes the exchange slower, never wrong (the reference's exchange queues are unbounded).
+  void* spill[TG_PART_MAX_COLS];
+  long long spill_cap;
+  unsigned long long* spill_cursor;
 };
 
 // HIGH = false: destination GPU, low 32 hash bits (disjoint from the slot bits).
@@ -98,7 +105,7 @@ k_partition_scatter(const long long* __restrict__ key, const uint8_t* __restrict
                     unsigned long long* __restrict__ cursors) {
   __shared__ unsigned long long s_val[PT_TILE];
   __shared__ uint32_t s_cnt[TG_MAX_PARTS], s_off[TG_MAX_PARTS + 1], s_room[TG_MAX_PARTS];
-  __shared__ unsigned long long s_gbase[TG_MAX_PARTS];
+  __shared__ unsigned long long s_gbase[TG_MAX_PARTS], s_spill[TG_MAX_PARTS];   // s_spill: first spill row of the rows that did not fit, ~0 = dropped
   const int lane = threadIdx.x & 31;
   const uint32_t P = (uint32_t)d.nparts;
   const int64_t ntiles = (n + PT_TILE - 1) / PT_TILE;
@@ -138,7 +145,15 @@ k_partition_scatter(const long long* __restrict__ key, const uint8_t* __restrict
       // rows of this tile that still fit the destination's capacity (0 = unbounded)
       unsigned long long room = d.capacity > 0 ? (old < (unsigned long long)d.capacity ? (unsigned long long)d.capacity - old : 0ull) : ~0ull;
       s_room[threadIdx.x] = room > c ? c : (uint32_t)room;
-      if (d.capacity > 0 && room < c) *d.overflow = 1ull;
+      unsigned long long sp = ~0ull;
+      if (d.capacity > 0 && room < c) {
+        if (d.spill_cursor) {
+          const unsigned long long extra = (unsigned long long)c - room;
+          sp = atomicAdd(d.spill_cursor, extra);
+          if (sp + extra > (unsigned long long)d.spill_cap) { sp = ~0ull; *d.overflow = 1ull; }
+        } else *d.overflow = 1ull;
+      }
+      s_spill[threadIdx.x] = sp;
     }
     __syncthreads();
     const uint32_t tile_rows = s_off[P];
@@ -156,6 +171,7 @@ k_partition_scatter(const long long* __restrict__ key, const uint8_t* __restrict
         while (sidx >= s_off[p + 1]) p++;   // ≤ nparts steps
         unsigned long long* dst = reinterpret_cast<unsigned long long*>(d.dst[p][c]);
         if (sidx - s_off[p] < s_room[p]) dst[s_gbase[p] + (sidx - s_off[p])] = s_val[sidx];
+        else if (s_spill[p] != ~0ull) reinterpret_cast<unsigned long long*>(d.spill[c])[s_spill[p] + (sidx - s_off[p] - s_room[p])] = s_val[sidx];
       }
       __syncthreads();
     }
@@ -279,7 +295,8 @@ k_partition_scatter_bulk(int64_t ntiles, PartDst d, unsigned long long* __restri
   unsigned long long* stage = ring + (size_t)STAGES * NC * TILE;                   // [NC][SROWS]
   uint64_t* full = reinterpret_cast<uint64_t*>(stage + (size_t)NC * SROWS);
   __shared__ uint32_t s_cnt[TG_MAX_PARTS], s_off[TG_MAX_PARTS], s_len[TG_MAX_PARTS];
-  __shared__ unsigned long long s_gbase[TG_MAX_PARTS], s_cur[TG_MAX_PARTS];
+  __shared__ unsigned long long s_gbase[TG_MAX_PARTS], s_cur[TG_MAX_PARTS], s_spg[TG_MAX_PARTS];
+  __shared__ uint32_t s_spn[TG_MAX_PARTS];    // rows of this tile's run that go to the spill area, starting at spill row s_spg
   const int tid = threadIdx.x, lane = tid & 31;
   const uint32_t P = (uint32_t)d.nparts;
   const unsigned long long pol = l2_policy_evict_first();
@@ -325,8 +342,8 @@ k_partition_scatter_bulk(int64_t ntiles, PartDst d, unsigned long long* __restri
     }
     __syncthreads();
     if (tid < 32) {
-      uint32_t c = tid < (int)P ? s_cnt[tid] : 0, len = c;
-      unsigned long long g = 0;
+      uint32_t c = tid < (int)P ? s_cnt[tid] : 0, len = c, spn = 0;
+      unsigned long long g = 0, spg = 0;
       if (tid < (int)P) {
         if (d.sub_cap > 0) {   // CTA-private sub-segment: the cursor lives in shared memory
           const unsigned long long old = s_cur[tid];
@@ -338,14 +355,21 @@ k_partition_scatter_bulk(int64_t ntiles, PartDst d, unsigned long long* __restri
           unsigned long long old = c ? atomicAdd(&cursors[tid], (unsigned long long)c) : 0ull;
           if (d.capacity > 0) {
             unsigned long long avail = old < (unsigned long long)d.capacity ? (unsigned long long)d.capacity - old : 0ull;
-            if ((unsigned long long)c > avail) { len = (uint32_t)avail; *d.overflow = 1ull; }
+            if ((unsigned long long)c > avail) {
+              len = (uint32_t)avail;
+              if (d.spill_cursor) {   // skewed destination: the rest of the run goes to the local spill area
+                spn = c - len;
+                spg = atomicAdd(d.spill_cursor, (unsigned long long)spn);
+                if (spg + spn > (unsigned long long)d.spill_cap) { spn = 0; *d.overflow = 1ull; }
+              } else *d.overflow = 1ull;
+            }
           }
           g = old + (unsigned long long)(d.dst_base ? d.dst_base[tid] : d.base_const);
         }
       }
       uint32_t w = tid < (int)P ? (((uint32_t)(g & 1) + c + 1) & ~1u) : 0, incl = w;
       for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-      if (tid < (int)P) { s_off[tid] = incl - w + (uint32_t)(g & 1); s_gbase[tid] = g; s_len[tid] = len; }
+      if (tid < (int)P) { s_off[tid] = incl - w + (uint32_t)(g & 1); s_gbase[tid] = g; s_len[tid] = len; s_spg[tid] = spg; s_spn[tid] = spn; }
     }
     if (tid < (int)P * NC) bulk_wait_read_all();   // the previous tile's bulk stores have read the staging buffer
     __syncthreads();
@@ -370,6 +394,11 @@ k_partition_scatter_bulk(int64_t ntiles, PartDst d, unsigned long long* __restri
       bulk_commit();
       if (head) dst[g] = src[so];
       if ((len - head) & 1u) dst[g + len - 1] = src[so + len - 1];
+      const uint32_t spn = s_spn[p];
+      if (spn) {   // rare (skew): scalar stores, the staging buffer is released by the bulk_wait_read_all + barrier of the next tile like the runs above
+        unsigned long long* sp = reinterpret_cast<unsigned long long*>(d.spill[c]) + s_spg[p];
+        for (uint32_t r = 0; r < spn; r++) sp[r] = src[so + len + r];
+      }
     }
   }
   if (tid < (int)P * NC) bulk_wait_read_all();

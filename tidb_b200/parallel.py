@@ -16,7 +16,7 @@ The host-side bookkeeping (counts → send/recv splits → bases) is shared with
 from __future__ import annotations
 
 import ctypes as C
-from typing import Callable, List, Sequence, Tuple
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -74,17 +74,22 @@ def region_capacity(rows_per_step: int, world: int, slack: float = 1.06) -> int:
 
 
 def exchange_segments_host(keys: np.ndarray, cols: Sequence[np.ndarray], world: int, rank: int, cap: int,
-                           all_to_all: Callable[[List], List]):
+                           all_to_all: Callable[[List], List], spill: Optional[List] = None):
     """CPU rendering of SegmentExchange (gloo tests): same region layout, same bookkeeping, same overflow rule.
     Every sender appends the rows of destination d to ITS region of d's receive buffer (at most `cap` rows, the excess is
     dropped and flagged); the receiver sees `world` segments of `cap` rows, segment s valid for seg_cnt[s] rows.
+    With `spill` (a list) the excess is appended to it instead — one entry of columns per overflowing destination — and no
+    overflow is flagged: the caller moves those rows with exchange_by_key_host afterwards (MailboxExchange.drain_spill).
     -> (received columns of world*cap rows each, seg_cnt[world], overflow flag)"""
     dest = partition_of_keys_np(keys, world)
     pieces, sent, overflow = [], np.zeros(world, dtype=np.int64), False
     for d in range(world):
         idx = np.nonzero(dest == d)[0]
         if len(idx) > cap:
-            overflow = True
+            if spill is not None:      # tg_partition_exchange_cf_spill: the excess stays on the sender, in its spill area
+                spill.append([np.ascontiguousarray(c[idx[cap:]]) for c in cols])
+            else:
+                overflow = True
             idx = idx[:cap]
         sent[d] = len(idx)
         pieces.append([np.ascontiguousarray(c[idx]) for c in cols])
@@ -461,7 +466,7 @@ class MailboxExchange:
 
     def __init__(self, rank: int, world: int, device: int, xstream, ncols: int, rows_per_step: int, slack: float = 1.06,
                  dma: bool = False, ctas_per_sm: int = 0, timeout_ms: int = 10000, copy_streams: int = 0, direct_peers: int = 0,
-                 sm_copy: bool = False, sm_copy_ctas: int = 0):
+                 sm_copy: bool = False, sm_copy_ctas: int = 0, spill_rows: int = 0):
         import torch
         import torch.distributed as dist
         from . import abi
@@ -492,6 +497,14 @@ class MailboxExchange:
         self.seg_cnt = [torch.zeros(world, dtype=torch.int64, device=self.dev) for _ in range(self.sets)]
         self.overflow = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self.errflag = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        # spill_rows > 0: rows that do not fit their destination's region (skewed keys) are appended to a local spill area by
+        # the regroup kernel instead of being dropped (tg_partition_exchange_cf_spill); drain_spill() hands them out after the
+        # pipeline so the caller can move them with the counted exchange.  Skew then costs time, not rows.
+        self.spill_rows = int(spill_rows)
+        if self.spill_rows > 0:
+            self.spill = [torch.empty(self.spill_rows + 2, dtype=torch.int64, device=self.dev) for _ in range(ncols)]
+            self.spill_cursor = torch.zeros(1, dtype=torch.int64, device=self.dev)
+            self.spill_arr = (C.c_void_p * ncols)(*[t.data_ptr() for t in self.spill])
         # receive buffers [set][col] and the mailbox block [kind][set][SLOTS] of this rank, all IPC-exported
         self.recv_ptrs, handles = [], []
         for _ in range(self.sets):
@@ -565,6 +578,37 @@ class MailboxExchange:
         a.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
         return self.torch.as_tensor(a, device=self.dev)
 
+    def _scatter(self, key, ncols, src_p, dst_arr, s_, X):
+        """the regroup kernel of one step: 1024-row tiles regrouped by destination rank, bulk stores into the regions"""
+        lib, abi = self.lib, self.abi
+        if self.spill_rows > 0:
+            if ncols != self.ncols:
+                raise ValueError("the spill area was sized for the exchange's column count")
+            abi.check(lib.tg_partition_exchange_cf_spill(self.device, C.c_void_p(key.data_ptr()), C.c_int64(key.numel()), self.world, ncols, src_p,
+                                                         dst_arr, C.c_int64(self.rank * self.cap), C.c_int64(self.cap),
+                                                         C.c_void_p(self.sent[s_].data_ptr()), C.c_void_p(self.overflow.data_ptr()),
+                                                         self.spill_arr, C.c_int64(self.spill_rows), C.c_void_p(self.spill_cursor.data_ptr()),
+                                                         C.c_int32(self.ctas_per_sm), X))
+        else:
+            abi.check(lib.tg_partition_exchange_cf_ex(self.device, C.c_void_p(key.data_ptr()), C.c_int64(key.numel()), self.world, ncols, src_p,
+                                                      dst_arr, C.c_int64(self.rank * self.cap), C.c_int64(self.cap),
+                                                      C.c_void_p(self.sent[s_].data_ptr()), C.c_void_p(self.overflow.data_ptr()), C.c_int32(self.ctas_per_sm), X))
+
+    def drain_spill(self):
+        """host call after the pipelined steps (synchronises this device): the rows the regroup kernel could not place in
+        their destination's region since the last drain, as column tensors (views of the spill area, valid until the next
+        send) -> (rows, [col tensors]); the spill cursor is reset.  The caller moves them with the counted exchange
+        (KeyExchange) and probes them like any other batch.  Collective-free; every rank must call the follow-up exchange
+        even with 0 spilled rows."""
+        if self.spill_rows <= 0:
+            return 0, []
+        self.torch.cuda.synchronize(self.dev)
+        n = int(self.spill_cursor.item())
+        if n > self.spill_rows:
+            raise RuntimeError("count-free exchange: the spill area overflowed as well (raise spill_rows)")
+        self.spill_cursor.zero_()
+        return n, [t[:n] for t in self.spill]
+
     def send(self, key, cols, compute_stream=None):
         """enqueue step k's repartition + transfer + count publication; cols[0] must be `key`.
         The SM kernel (regroup / scatter) goes on `compute_stream` (default: the exchange stream given to the constructor).
@@ -582,9 +626,7 @@ class MailboxExchange:
         if not self.dma:
             if k >= self.sets:   # every peer has finished probing the step that used this buffer set
                 abi.check(lib.tg_mail_wait(self.device, C.c_void_p(self._mail(self.KIND_ACK, s_)), self.world, C.c_int64(epoch - self.sets), None, err, C.c_int64(self.timeout_ms), X))
-            abi.check(lib.tg_partition_exchange_cf_ex(self.device, C.c_void_p(key.data_ptr()), C.c_int64(key.numel()), self.world, len(cols), src_p,
-                                                      self.peer_arr[s_], C.c_int64(self.rank * self.cap), C.c_int64(self.cap),
-                                                      C.c_void_p(self.sent[s_].data_ptr()), C.c_void_p(self.overflow.data_ptr()), C.c_int32(self.ctas_per_sm), X))
+            self._scatter(key, len(cols), src_p, self.peer_arr[s_], s_, X)
             abi.check(lib.tg_mail_signal(self.device, C.byref(self.targets[(self.KIND_COUNT, s_)]), C.c_void_p(self.sent[s_].data_ptr()), C.c_int64(epoch), X))
             self.launches += 4 if k >= self.sets else 3
             return
@@ -597,9 +639,7 @@ class MailboxExchange:
                 # stream that is stream order; on a separate exchange stream it is the ACK mailbox, which includes this rank.)
                 # Hybrid transfer: the kernel also stores into the direct peers, whose probes of step k-2 must be done.
                 abi.check(lib.tg_mail_wait(self.device, C.c_void_p(self._mail(self.KIND_ACK, s_)), self.world, C.c_int64(epoch - self.sets), None, err, C.c_int64(self.timeout_ms), X))
-            abi.check(lib.tg_partition_exchange_cf_ex(self.device, C.c_void_p(key.data_ptr()), C.c_int64(key.numel()), self.world, len(cols), src_p,
-                                                      self.stage_arr[s_], C.c_int64(self.rank * self.cap), C.c_int64(self.cap),
-                                                      C.c_void_p(self.sent[s_].data_ptr()), C.c_void_p(self.overflow.data_ptr()), C.c_int32(self.ctas_per_sm), X))
+            self._scatter(key, len(cols), src_p, self.stage_arr[s_], s_, X)
             regrouped = torch.cuda.Event(); regrouped.record(cs_)
         with torch.cuda.stream(D):
             D.wait_event(regrouped)
