@@ -550,7 +550,7 @@ def run_gpu(args):
         nvl = 16.0 * npb * (world - 1) / world / (ms_step * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak * world, "unit": "GB/s", "frac": achieved / (hbm_peak * world),
                 "traffic": None, "peak_source": peak_src + f" x {world} GPUs",
-                "kernel": "per rank and step: k_partition_scatter_bulk<0,2,4> (repartition + NVLink bulk stores) | k_partition_scatter_bulk<1,2,4> + k_probe_inner_u1_seg (L2 pass + segment probe)",
+                "kernel": "per rank and step: k_partition_scatter_bulk<0,2,4> (repartition + NVLink bulk stores) | k_partition_scatter_bulk<1,2,4> + k_probe_inner_u1_seg_lean<1,2,1,0> (L2 pass + segment probe)",
                 "algorithmic_bytes_per_launch": BYTES_PER_PROBE_ROW * npb * world,
                 "nvlink": {"payload_gbs_per_direction_per_gpu": nvl, "reference_gbs": 770.0, "frac": nvl / 770.0,
                            "note": "16 B per exchanged row; reference = measured peer-copy bandwidth per direction (B200_PROFILING.md)"}}

@@ -59,3 +59,38 @@ def test_segment_capacity_formula():
     for rows, world in [(100_000_000, 8), (100_000_000, 2), (1_000_000, 4)]:
         cap = region_capacity(rows, world)
         assert cap % 1024 == 0 and cap >= rows / world * 1.06
+
+
+def test_spill_bookkeeping_model():
+    """count-free scatter with a spill area (PartDst.spill_cursor, tg_partition_exchange_cf_spill): per (tile, destination) run
+    the first `len` rows go to the region, the rest to spill rows [spg, spg + spn); over many tiles and CTAs in any order every
+    row lands exactly once, a region never holds more than its capacity, and the cursors the receiver sees (clamped to the
+    capacity) count exactly the rows stored.  Same expressions as the kernel's warp-0 block."""
+    rng = np.random.default_rng(3)
+    for trial in range(200):
+        P, cap, spill_cap = int(rng.integers(1, 9)), int(rng.integers(0, 5000)), 1 << 20
+        cursors, spill_cursor = np.zeros(P, dtype=np.int64), 0
+        region = [[] for _ in range(P)]
+        spill, total = [], 0
+        hot = int(rng.integers(0, P))
+        for tile in range(int(rng.integers(1, 40))):
+            dest = np.where(rng.random(1024) < 0.5, hot, rng.integers(0, P, 1024))
+            cnt = np.bincount(dest, minlength=P)
+            for p in range(P):
+                c = int(cnt[p])
+                old = int(cursors[p]); cursors[p] += c                         # atomicAdd(&cursors[p], c)
+                avail = cap - old if old < cap else 0
+                ln, spn, spg = c, 0, 0
+                if c > avail:
+                    ln = avail
+                    spn = c - ln
+                    spg = spill_cursor; spill_cursor += spn                    # atomicAdd(spill_cursor, spn)
+                    assert spg + spn <= spill_cap
+                rows = [(tile, p, r) for r in range(c)]                        # staging slots so + r, r = rank inside the run
+                region[p].extend(rows[:ln])                                    # head / bulk middle / tail stores
+                assert spn == 0 or len(spill) == spg
+                spill.extend(rows[ln:ln + spn])                                # scalar spill stores src[so + len + r]
+                total += c
+        assert all(len(region[p]) == min(int(cursors[p]), cap) for p in range(P))   # what the receiver reads: min(cursor, cap)
+        placed = [x for r in region for x in r] + spill
+        assert len(placed) == total == len(set(placed))
