@@ -45,5 +45,13 @@ def cases():
     t = [(1, 1), (2, 2), (3, 4)]
     plan = JoinPlan(abi.JOIN_SEMI, [INT, INT], [INT, INT], [0, 1], [0, 1], build_is_right=True, lused=[0], rused=[])
     out.append(("(t.c, t.d) = any (select * from t) (join.result:1258-1262)", plan, _table(t, 2), _table(t, 2), 3, [(1,), (2,), (3,)]))
+    # join.result:586-598: tt1(ts timestamp) = '2001-01-01 00:00:00', tt3(ts datetime) the same instant (session time zone UTC):
+    # select * from tt1 where ts in (select ts from tt3) → the row; date-time keys compare by calendar fields, not by type bits
+    def core_time(y, mo, d, h=0, mi=0, sec=0, us=0, fsp_tt=0):      # types/time.go:235-251
+        v = (y << 50) | (mo << 46) | (d << 41) | (h << 36) | (mi << 30) | (sec << 24) | (us << 4) | fsp_tt
+        return v - (1 << 64) if v >= (1 << 63) else v
+    ts, dt = core_time(2001, 1, 1, fsp_tt=1), core_time(2001, 1, 1, fsp_tt=0)      # TIMESTAMP(0): fspTt = 0b0001, DATETIME(0): 0
+    plan = JoinPlan(abi.JOIN_SEMI, [FieldType(abi.TYPE_TIMESTAMP, 0)], [FieldType(abi.TYPE_DATETIME, 0)], [0], [0], build_is_right=True, lused=[0], rused=[])
+    out.append(("timestamp in (select datetime) (join.result:586-598)", plan, _table([(ts,)], 1), _table([(dt,), (core_time(2001, 1, 2),)], 1), 1, [(ts,)]))
     # join.result:1276-1277: A join B on A.c = B.c and A.c > 100 → empty (the one-side condition is a probe filter)
     return out

@@ -57,6 +57,17 @@ def test_sql_hash_join_goldens_on_gpu():
     assert sorted(run_gpu(ro, t1, t), key=str) == sorted([(None, None, 1, 1), (2, 3, 2, 2)], key=str)
 
 
+def test_sql_join_result_goldens_multi_key_other_condition_on_gpu():
+    # the reference's SQL known answers for several equal conditions, a non-equi residual and date-time keys
+    # (tests/sql_goldens.py, from tests/integrationtest/r/executor/jointest/join.result) through the CUDA path
+    import sql_goldens
+    for name, plan, left, right, count, rows in sql_goldens.cases():
+        got = run_gpu(plan, left, right)
+        assert len(got) == count, name
+        if rows is not None:
+            assert sorted(got) == sorted(rows), name
+
+
 @pytest.mark.parametrize("jt", JOIN_TYPES)
 @pytest.mark.parametrize("build_is_right", [True, False])
 @pytest.mark.parametrize("nulls,dup,with_sel", [(0.0, False, False), (0.15, True, False), (0.1, True, True)])
