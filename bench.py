@@ -233,10 +233,23 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # the same workload as the GPU arm at this N: configs[1] on one GPU, configs[4] / 8 per GPU otherwise — the CPU arm is ONE
+    # host process, so it builds the GLOBAL table (12.5 M x N rows) and probes a bounded sample of the global probe side
+    world = max(1, int(args.gpus))
+    per_gpu = args.build_rows is None and args.probe_rows is None and world > 1
     if args.build_rows is None:
-        args.build_rows = 10_000_000
+        args.build_rows = 10_000_000 if world == 1 else 12_500_000 * world
     if args.probe_rows is None:
-        args.probe_rows = 100_000_000
+        args.probe_rows = 100_000_000 if world == 1 else 125_000_000 * world
+    note_mem = None
+    try:
+        import psutil
+        need = args.build_rows * 160          # numpy inputs + row store + hash values + tables of the restatement, generously
+        if psutil.virtual_memory().available < need:
+            note_mem = f"host memory too small for the {args.build_rows}-row build of this configuration: built 10000000 rows instead"
+            args.build_rows = 10_000_000
+    except Exception:
+        pass
     nb, sample = args.build_rows, min(args.probe_rows, args.ref_sample_rows)
     rng = np.random.default_rng(42)
     ids = rng.permutation(nb).astype(np.int64)
@@ -251,8 +264,12 @@ def run_reference(args):
         "impl": "reference", "metric": "hash-join probe rows/sec", "value": rate, "unit": "rows/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": f"hash join {args.probe_rows}x{nb} int64 keys, 8-byte payload, 100% match (BASELINE configs[1])",
-                   "note": "CPU restatement of TiDB's HashJoinV2 algorithm (oracle/join.cpp), NOT the Go binary: no Go toolchain in this image"},
+        "config": {"workload": (f"hash join {args.probe_rows}x{nb} int64 keys, 8-byte payload, 100% match (BASELINE configs[1])" if world == 1 else
+                                f"hash join {args.probe_rows}x{nb} int64 keys (the GPU arm's partitioned join over {world} GPUs, "
+                                f"{args.probe_rows // world}x{nb // world} per GPU), 8-byte payload, 100% match, in ONE host process "
+                                f"(BASELINE configs[4] / 8 per GPU" + ("" if world != 8 else " = the 1Bx100M join") + ")"),
+                   "note": "CPU restatement of TiDB's HashJoinV2 algorithm (oracle/join.cpp), NOT the Go binary: no Go toolchain in this image"
+                           + ("; " + note_mem if note_mem else "")},
         "cpu_baseline": {"value": rate, "unit": "rows/s", "cores": threads, "kind": "port",
                          "sample": f"full {nb}-row build ({bsec:.2f}s, untimed) + probe of {sample} rows as 1024-row chunks per step"},
         "e2e": {"value": rate, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
