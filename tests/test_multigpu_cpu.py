@@ -126,3 +126,79 @@ def test_partition_mirror_matches_c_function():
     for nparts in (1, 2, 3, 8, 16):
         exp = np.array([lib.tg_partition_of_key(int(k), nparts) for k in keys])
         assert np.array_equal(partition_of_keys_np(keys, nparts), exp)
+
+
+def _q3_worker(rank, world, port, q):
+    """The distributed Q3-shape PLAN (tidb_b200/q3.py:Q3Distributed, tpch_suite_out.json:99-123) restated with the oracle operators
+    and the host exchange: broadcast customer, J1 on the local orders shard, filtered orders and lineitem repartitioned by order
+    key, J2 + HashAgg + TopN shard-local (the GROUP BY key contains the partition key), global TopN over world x 10 rows."""
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import torch
+    import oracle_lib as O
+    import topn as OT
+    from test_gpu_q3 import oracle_q3
+    from tidb_b200 import abi, q3
+    from tidb_b200.chunk import Chunk, Column
+    from tidb_b200.parallel import exchange_by_key_host, partition_of_keys_np
+    from tidb_b200.plan import FilterItem, JoinPlan
+    INT = q3.INT
+    d = q3.gen(torch.device("cpu"), 4000, 40000, 160000, rank=rank, world=world)
+    h = {k: v.numpy() for k, v in d.__dict__.items()}
+
+    def all_gather(x):
+        out = [None] * world
+        dist.all_gather_object(out, x)
+        return out
+
+    def all_to_all(pieces):
+        return [g[rank] for g in all_gather(pieces)]
+
+    # 1. broadcast side + J1 on the local orders shard
+    ck = np.concatenate(all_gather(h["c_custkey"])); cs = np.concatenate(all_gather(h["c_seg"]))
+    j1 = JoinPlan(abi.JOIN_INNER, [INT] * 4, [INT] * 2, [1], [0], build_is_right=True, lused=[0, 2, 3], rused=[],
+                  build_filter=[FilterItem(abi.CMP_EQ, 1, const_i64=q3.SEGMENT)], probe_filter=[FilterItem(abi.CMP_LT, 2, const_i64=q3.DATE)])
+    n1, c1 = O.OracleJoin(j1, 2).run(Chunk([Column(ck), Column(cs)]).split(4096),
+                                     Chunk([Column(h["o_orderkey"]), Column(h["o_custkey"]), Column(h["o_date"]), Column(h["o_prio"])]).split(4096))
+    o_cols = [v.copy() for v, _ in c1] if n1 else [np.zeros(0, dtype=np.int64)] * 3
+    # 2. repartition by order key: equal order keys meet on one rank
+    ok, od, op = exchange_by_key_host(o_cols[0], o_cols, world, all_to_all)
+    lk, lp, ld, ls = exchange_by_key_host(h["l_orderkey"], [h["l_orderkey"], h["l_price"].view(np.int64), h["l_disc"].view(np.int64), h["l_ship"]], world, all_to_all)
+    assert np.all(partition_of_keys_np(ok, world) == rank) and np.all(partition_of_keys_np(lk, world) == rank)
+    # 3. shard-local J2 + HashAgg: reuse the single-process plan on the shard, with the exchanged J1 output as "orders ⋈ customer"
+    shard = {"c_custkey": np.array([1], dtype=np.int64), "c_seg": np.array([q3.SEGMENT], dtype=np.int64),        # one matching customer:
+             "o_orderkey": ok, "o_custkey": np.ones(len(ok), dtype=np.int64), "o_date": od, "o_prio": op,          # J1 passes the shard through
+             "l_orderkey": lk, "l_price": lp.view(np.float64), "l_disc": ld.view(np.float64), "l_ship": ls}
+    _n1, n2, ng, (gk, rev, gd, gp) = oracle_q3(shard)
+    assert _n1 == len(ok)
+    local_top = OT.topn_rows(list(zip(gk.tolist(), rev.tolist(), gd.tolist(), gp.tolist())), ["int", "real", "int", "int"], [(1, True), (2, False)], 0, 10)
+    # 4. global TopN over the world x 10 local rows; group counts add up (groups never span ranks)
+    tops = all_gather(local_top); counts = all_gather((n1, n2, ng)); shards = all_gather(h)
+    if rank == 0:
+        final = OT.topn_rows([r for t in tops for r in t], ["int", "real", "int", "int"], [(1, True), (2, False)], 0, 10)
+        whole = {k: np.concatenate([s[k] for s in shards]) for k in h}
+        w1, w2, wg, (wk, wrev, wd, wp) = oracle_q3(whole)
+        exp = OT.topn_rows(list(zip(wk.tolist(), wrev.tolist(), wd.tolist(), wp.tolist())), ["int", "real", "int", "int"], [(1, True), (2, False)], 0, 10)
+        ok_ = (sum(c[0] for c in counts), sum(c[1] for c in counts), sum(c[2] for c in counts)) == (w1, w2, wg) and len(final) == len(exp) == 10
+        ok_ = ok_ and all((f[0], f[2], f[3]) == (e[0], e[2], e[3]) and abs(f[1] - e[1]) <= 1e-9 * abs(e[1]) for f, e in zip(final, exp))
+        q.put(bool(ok_))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_q3_plan_gloo():
+    from tidb_b200 import build
+    build.build()
+    import oracle_lib
+    oracle_lib.build_oracle()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_q3_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0, f"rank exited with {p.exitcode}"
+    assert q.get(timeout=5) is True
