@@ -325,3 +325,28 @@ def test_oracle_time_keys_vs_nested_loop(jt, build_is_right):
     want = nested_loop_join(plan, l, r)
     assert len(want) > 0
     assert_rows_equal(want, run_oracle(plan, l, r))
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_oracle_fuzz_keys_filters_other_condition_vs_nested_loop(seed):
+    """randomized differential test of the oracle against the independent nested loop over the shapes the device accepts:
+    1-3 key columns (integer family, mixed signedness), optional OtherCondition items (column vs column across sides, column
+    vs constant), optional filter on the probe side, NULLs everywhere, duplicate keys, ragged chunks"""
+    from tidb_b200.plan import OtherCond
+    rng = np.random.default_rng(88000 + seed)
+    nkeys = int(rng.integers(1, 4))
+    jt, brt = [(abi.JOIN_INNER, True), (abi.JOIN_INNER, False), (abi.JOIN_LEFT_OUTER, True), (abi.JOIN_RIGHT_OUTER, False),
+               (abi.JOIN_SEMI, True), (abi.JOIN_ANTI_SEMI, True)][int(rng.integers(0, 6))]
+    ltypes, rtypes, l, r = make_multikey_case(rng, int(rng.integers(1, 400)), int(rng.integers(1, 600)), float(rng.choice([0.0, 0.1])), nkeys,
+                                              key_range=int(rng.integers(2, 9)), unsigned_second=bool(rng.integers(0, 2)) and nkeys >= 2)
+    other = []
+    if rng.random() < 0.6:
+        other.append(OtherCond(int(rng.integers(0, 6)), 0, 0, 1, 3))                                  # left.col0 OP right.col3
+    if rng.random() < 0.4:
+        other.append(OtherCond(int(rng.integers(0, 6)), 1, 3, -1, -1, const_i64=int(rng.integers(-1 << 39, 1 << 39))))   # right.col3 OP const
+    semi = jt >= abi.JOIN_SEMI
+    # a filter on the probe side (the outer side of the outer joins): filtered outer rows are still emitted NULL-padded
+    pf = [FilterItem(abi.CMP_GT, 0 if brt else 3, const_i64=int(rng.integers(-1 << 39, 1 << 39)))] if rng.random() < 0.5 else []
+    plan = JoinPlan(jt, ltypes, rtypes, list(range(1, 1 + nkeys)), list(range(nkeys)), build_is_right=brt,
+                    lused=[0, 1, 2, 3], rused=[] if semi else [3, 0, 1], other_cond=other, probe_filter=pf)
+    assert_rows_equal(nested_loop_join(plan, l, r), run_oracle(plan, l, r, int(rng.integers(1, 6))))
