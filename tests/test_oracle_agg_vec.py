@@ -102,6 +102,43 @@ def test_agg_random_vs_numpy():
         assert r[5] == y[m].min() and r[6] == y[m].max()
 
 
+@pytest.mark.parametrize("ngroup,pc,fc", [(2, 1, 1), (3, 5, 5), (4, 3, 2)])
+def test_agg_multi_column_group_by_and_fused_argument_vs_python(ngroup, pc, fc):
+    # GetGroupKey over several columns (agg_util.go:106: the encoded columns concatenated, NULL = NilFlag, so NULL is a key value
+    # of its own in every position) and the aggregate argument l * (1 - d) evaluated below the aggregate (func_sum.go:90
+    # args[0].EvalReal): the oracle against a plain Python dictionary
+    rng = np.random.default_rng(300 + ngroup)
+    n = 6000
+    gcols = [Column(rng.integers(-3, 3, n).astype(np.int64), rng.random(n) < 0.08) for _ in range(ngroup)]
+    a = np.floor(rng.random(n) * 1000) / 4
+    b = np.floor(rng.random(n) * 10) / 100
+    an = rng.random(n) < 0.05
+    cols = gcols + [Column(a, an), Column(b)]
+    ia, ib = ngroup, ngroup + 1
+    plan = AggPlan([INT] * ngroup + [DBL, DBL], list(range(ngroup)),
+                   [AggFunc(abi.AGG_FIRSTROW, c) for c in range(ngroup)] +
+                   [AggFunc(abi.AGG_SUM, ia, abi.TYPE_DOUBLE, arg_col2=ib, arg_expr=abi.ARGEXPR_MUL_CSUB, arg_const=1.0),
+                    AggFunc(abi.AGG_AVG, ia, abi.TYPE_DOUBLE, arg_col2=ib, arg_expr=abi.ARGEXPR_MUL),
+                    AggFunc(abi.AGG_COUNT, ia, abi.TYPE_DOUBLE), AggFunc(abi.AGG_COUNT, -1)])
+    got = {tuple(r[:ngroup]): r[ngroup:] for r in run_agg(plan, Chunk(cols).split(777), pc, fc)}
+    exp = {}
+    gv = [(c.data, c.nulls()) for c in gcols]
+    for i in range(n):
+        k = tuple(None if nl[i] else int(v[i]) for v, nl in gv)
+        e = exp.setdefault(k, [0.0, 0.0, 0, 0])
+        e[3] += 1
+        if not an[i]:
+            e[0] += a[i] * (1.0 - b[i]); e[1] += a[i] * b[i]; e[2] += 1
+    assert set(got) == set(exp)
+    for k, (s1, s2, cnt, rows) in exp.items():
+        r = got[k]
+        assert r[2] == cnt and r[3] == rows
+        if cnt:
+            assert r[0] == pytest.approx(s1, rel=1e-9) and r[1] == pytest.approx(s2 / cnt, rel=1e-9)
+        else:
+            assert r[0] is None and r[1] is None
+
+
 # ---- VecEval -----------------------------------------------------------------------------------------
 def test_vec_compare_int_and_nulls():
     a = Column(np.array([1, 2, 3, -4, 5], dtype=np.int64), np.array([0, 0, 1, 0, 0], dtype=bool))
